@@ -1,0 +1,177 @@
+/* vitk.h — C ABI of libvitk.so, the B200 (sm_100a) kernel library behind the ViT training hot path.
+ *
+ * The reference (TaiMingLu/vision_transformers_torch_xla) has no FFI of its own: its operator seam
+ * is Python (`models/_compat.py:27-172` resolves Attention/Mlp/PatchEmbed/LayerNorm by name, and
+ * `engine.py:257-274` drives model -> criterion -> backward -> optimizer.step).  Each entry point
+ * below replaces the PyTorch *library* op that those call sites dispatch to, and
+ * is what a binding on the reference side would call (INTEGRATION.md shows the ctypes stub).
+ *
+ * Conventions
+ *  - Plain pointers + sizes only.  All pointers are DEVICE pointers unless stated otherwise.
+ *  - `stream` is a cudaStream_t passed as void*.  Every call only enqueues work; no host sync.
+ *  - The library never allocates, frees or retains device memory.
+ *  - Return 0 on success, a negative vitk_status otherwise; vitk_last_error() returns a
+ *    thread-local message.  Nothing throws across the ABI.
+ *  - bf16 buffers are passed as void* (raw __nv_bfloat16 storage).
+ */
+#ifndef VITK_H_
+#define VITK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VITK_ABI_VERSION 1
+
+enum vitk_status {
+  VITK_STATUS_OK = 0,
+  VITK_STATUS_SHAPE = -1,
+  VITK_STATUS_ALIGN = -2,
+  VITK_STATUS_DTYPE = -3,
+  VITK_STATUS_CUDA = -4,
+  VITK_STATUS_DRIVER = -5,
+  VITK_STATUS_UNSUPPORTED = -6
+};
+
+int vitk_abi_version(void);
+const char* vitk_last_error(void);
+/* Compile-time target of the device code in this library, e.g. "sm_100a". */
+const char* vitk_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM — tcgen05/TMEM bf16 GEMM with fused epilogues.   D[M,N] = opA(A)[M,K] * opB(B)[N,K]^T
+ * Replaces: nn.Linear fwd/dgrad/wgrad for attn.qkv / attn.proj / mlp.fc1 / mlp.fc2 / head
+ *   (reference models/vision_transformer.py:149-171, 618; timm Attention/Mlp), and the
+ *   Conv2d(k=s=16) patchify of PatchEmbed (vision_transformer.py:552-560).
+ * ---------------------------------------------------------------------------------------------- */
+enum vitk_epilogue {
+  VITK_EPI_BF16 = 0,   /* out_bf16[m,n]  = rowscale[m/g] * (acc + bias[n])                         */
+  VITK_EPI_GELU = 1,   /* h = acc + bias; aux_bf16 = h; out_bf16 = gelu_erf(h)        (mlp.fc1)    */
+  VITK_EPI_RESID = 2,  /* out_f32 = resid_f32 + rowscale[m/g]*colscale[n]*(acc+bias)  (proj, fc2)  */
+  VITK_EPI_F32 = 3,    /* out_f32 = acc + bias                                        (head)       */
+  VITK_EPI_DGELU = 4,  /* out_bf16 = acc * gelu'(aux_bf16[m,n])                       (fc2 dgrad)  */
+  VITK_EPI_ATOMIC = 5, /* out_f32 += acc   via red.global.add (split-K)               (wgrad)      */
+  VITK_EPI_PATCH = 6   /* out_f32[b*(P+prefix)+prefix+t, n] = acc + bias[n] + pos[prefix+t, n]     */
+};
+
+typedef struct vitk_gemm_args {
+  const void* A;       /* bf16.  K-major: [M, K] row pitch lda.  MN-major: [K, M] row pitch lda.   */
+  const void* B;       /* bf16.  K-major: [N, K] row pitch ldb.  MN-major: [K, N] row pitch ldb.   */
+  int64_t lda, ldb;    /* in elements, multiples of 8                                              */
+  int32_t a_mn_major, b_mn_major;
+  int32_t M, N, K;
+  int32_t epilogue;    /* enum vitk_epilogue                                                       */
+  void* out;           /* bf16 or f32 depending on the epilogue                                    */
+  int64_t ld_out;
+  void* aux;           /* GELU: pre-activation output (bf16); DGELU: pre-activation input (bf16)   */
+  int64_t ld_aux;
+  const float* bias;   /* [N] or NULL                                                              */
+  const float* resid;  /* RESID: fp32 [M, N] residual stream input                                 */
+  int64_t ld_resid;
+  const float* rowscale; /* per-sample DropPath scale (mask/keep_prob), indexed by m/rows_per_group, or NULL */
+  int32_t rows_per_group;
+  const float* colscale; /* LayerScale gamma [N] or NULL                                           */
+  const float* pos;    /* PATCH: pos_embed fp32 [(P+prefix), N]                                    */
+  int32_t tokens_per_img; /* PATCH: P                                                              */
+  int32_t prefix;      /* PATCH: number of prefix (cls/dist) tokens                                */
+  int32_t splits;      /* ATOMIC: split-K factor, 0 = choose to fill 148 SMs                       */
+  int32_t block_n;     /* 0 = auto; otherwise 128, 192 or 256                                      */
+} vitk_gemm_args;
+
+int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (eps = 1e-6 in the reference: timm LayerNorm; vision_transformer.py:148,163,603,616)
+ * fwd: y_bf16 = (x - mean) * rstd * gamma + beta over the last dim; x is the fp32 residual stream.
+ *      Row r of x starts at x + r*ld_x (lets the 'token' pool normalise only the cls rows).
+ * bwd: dx = LN'(dy); g_out = (g_in ? g_in : 0) + dx; gb_out = bf16(rowscale * g_out) (optional);
+ *      dgamma/dbeta are ACCUMULATED (atomicAdd) into fp32 [dim] buffers.
+ * ---------------------------------------------------------------------------------------------- */
+int vitk_layernorm_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta,
+                       void* y_bf16, int64_t ld_y, float* mean, float* rstd, int64_t rows,
+                       int32_t dim, float eps, void* stream);
+int vitk_layernorm_bwd(const void* dy_bf16, int64_t ld_dy, const float* x, int64_t ld_x,
+                       const float* mean, const float* rstd, const float* gamma, const float* g_in,
+                       float* g_out, int64_t ld_g, void* gb_out_bf16, const float* rowscale,
+                       int32_t rows_per_group, float* dgamma, float* dbeta, int64_t rows,
+                       int32_t dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention (timm Attention fused path = F.scaled_dot_product_attention, dropout 0, no mask)
+ * qkv: bf16 [B, N, 3, H, hd] (exactly the qkv Linear output), out: bf16 [B, N, H*hd],
+ * lse: fp32 [B, H, N] (natural-log sum-exp of scaled scores).  hd must be 64.
+ * ---------------------------------------------------------------------------------------------- */
+int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H,
+                  int32_t head_dim, float scale, void* stream);
+int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                  void* dqkv, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Patch embedding helpers (PatchEmbed + _pos_embed: vision_transformer.py:552-560, 743-780)
+ * patchify: fp32 NCHW image -> bf16 [B*P, C*ps*ps] rows in (c, ph, pw) order == proj.weight.view(D,-1)
+ * prefix_rows: x[b, j, :] = prefix_tok[j, :] + pos[j, :] for j < prefix (cls / dist tokens)
+ * embed_bwd: from g fp32 [B, N, D]: gp_bf16 [B*P, D] (patch rows), dpos[N, D] += sum_b g,
+ *            dprefix[prefix, D] += sum_b g[b, j, :]
+ * ---------------------------------------------------------------------------------------------- */
+int vitk_patchify(const float* img, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W,
+                  int32_t ps, void* stream);
+int vitk_prefix_rows(float* x, const float* prefix_tok, const float* pos, int32_t B, int32_t N,
+                     int32_t D, int32_t prefix, void* stream);
+int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix, int32_t B, int32_t N,
+                   int32_t D, int32_t prefix, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pooling (global_pool_nlc: vision_transformer.py:419-441).  mode 0 = 'avg' over non-prefix
+ * tokens, mode 1 = 'token' (x[:, 0]).  bwd writes the full g [B, N, D] (zeros elsewhere).
+ * ---------------------------------------------------------------------------------------------- */
+int vitk_pool_fwd(const float* x, float* pooled, int32_t B, int32_t N, int32_t D, int32_t prefix,
+                  int32_t mode, void* stream);
+int vitk_pool_bwd(const float* dpooled, float* g, int32_t B, int32_t N, int32_t D, int32_t prefix,
+                  int32_t mode, void* stream);
+
+/* out[c] += sum_r x[r, c]   (bias gradients).  x bf16 [rows, cols] pitch ld. */
+int vitk_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int64_t rows, int32_t cols,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses (timm SoftTargetCrossEntropy / LabelSmoothingCrossEntropy selected at reference
+ * main.py:926-935; DistillationLoss main.py:939-968).  One fused forward+backward kernel:
+ *   base   = mean_b sum_c -t[b,c] * log_softmax(x)[b,c]
+ *            (t = soft_targets, or the smoothed one-hot of labels when soft_targets == NULL)
+ *   kd     = T^2 * mean_b KL(softmax(teacher/T) || softmax(x/T))          (teacher != NULL)
+ *   loss   = (1 - alpha) * base + alpha * kd           (alpha = 0 when teacher == NULL)
+ * Writes loss[0] (fp32 scalar, overwritten) and dlogits fp32 [B, C] = d loss / d x.
+ * ---------------------------------------------------------------------------------------------- */
+int vitk_ce_fwd_bwd(const float* logits, const float* soft_targets, const int64_t* labels,
+                    float smoothing, const float* teacher_logits, float kd_alpha, float kd_temp,
+                    float* loss, float* dlogits, float* row_loss_scratch, int32_t B, int32_t C,
+                    void* stream);
+/* out_bf16[i] = in_f32[i] * scale_dev[0]   (applies the upstream grad of the loss, no host sync) */
+int vitk_scale_cast_bf16(const float* in, const float* scale_dev, void* out_bf16, int64_t n,
+                         void* stream);
+/* out_bf16[i] = in_f32[i] */
+int vitk_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW over flat buffers (torch.optim.AdamW semantics, reference
+ * optim_factory.py:248-249; stepped at engine.py:185/271).  All parameters live in one flat fp32
+ * buffer; `chunk_group[i]` gives the param-group id of elements [i*chunk, (i+1)*chunk).
+ *   g' = g * grad_scale;  p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2
+ *   p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps);   shadow_bf16 = bf16(p);  ema = d ema + (1-d) p
+ * lr[] / wd[] are HOST arrays of length num_groups (copied by value into the launch).
+ * ---------------------------------------------------------------------------------------------- */
+int vitk_adamw_flat(float* p, float* g, float* m, float* v, void* shadow_bf16, float* ema,
+                    int64_t n, const uint8_t* chunk_group, int32_t chunk, int32_t num_groups,
+                    const float* lr, const float* wd, float beta1, float beta2, float eps,
+                    int64_t step, float grad_scale, float ema_decay, int32_t zero_grad,
+                    void* stream);
+/* out[0] += sum_i x[i]^2 (for clip_grad_norm_) */
+int vitk_sumsq(const float* x, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITK_H_ */

@@ -1,0 +1,67 @@
+"""tcgen05 attention fwd/bwd vs torch fp32 softmax attention on the same bf16-rounded qkv."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, B, N, H, hd, dout=None):
+    q, k, v = qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)  # [B,H,N,hd]
+    q = q.detach().requires_grad_(True)
+    k = k.detach().requires_grad_(True)
+    v = v.detach().requires_grad_(True)
+    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+    lse = torch.logsumexp(s, dim=-1)
+    o = torch.softmax(s, dim=-1) @ v
+    out = o.transpose(1, 2).reshape(B, N, H * hd)
+    if dout is None:
+        return out, lse, None
+    out.backward(dout.float())
+    dqkv = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B, N, 3 * H * hd)
+    return out, lse, dqkv
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 577, 4), (1, 300, 2)])
+def test_attn_fwd(cuda_device, B, N, H):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    hd = 64
+    torch.manual_seed(0)
+    qkv = torch.randn(B, N, 3 * H * hd, device=cuda_device).bfloat16()
+    out = torch.full((B, N, H * hd), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    lse = torch.full((B, H, N), float("nan"), device=cuda_device)
+    L.attn_fwd(qkv, out, lse, B, N, H, hd, hd ** -0.5)
+    ref, ref_lse, _ = _ref(qkv, B, N, H, hd)
+    assert rel_err(out.float(), ref) < 1.5e-2  # bf16 P and bf16 output rounding
+    assert rel_err(lse, ref_lse) < 5e-3
+
+
+@pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 100, 2)])
+def test_attn_bwd(cuda_device, B, N, H):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    hd = 64
+    torch.manual_seed(1)
+    qkv = torch.randn(B, N, 3 * H * hd, device=cuda_device).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=cuda_device).bfloat16()
+    out = torch.empty((B, N, H * hd), device=cuda_device, dtype=torch.bfloat16)
+    lse = torch.empty((B, H, N), device=cuda_device)
+    dqkv = torch.full((B, N, 3 * H * hd), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    L.attn_fwd(qkv, out, lse, B, N, H, hd, hd ** -0.5)
+    L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, hd, hd ** -0.5)
+    _, _, ref = _ref(qkv, B, N, H, hd, dout)
+    d = dqkv.float().view(B, N, 3, H * hd)
+    r = ref.view(B, N, 3, H * hd)
+    for i, name in enumerate("qkv"):
+        assert rel_err(d[:, :, i], r[:, :, i]) < 2e-2, f"d{name}"
+
+
+def test_attn_unsupported_raises(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    qkv = torch.zeros(1, 16, 3 * 32, device=cuda_device, dtype=torch.bfloat16)
+    out = torch.zeros(1, 16, 32, device=cuda_device, dtype=torch.bfloat16)
+    lse = torch.zeros(1, 1, 16, device=cuda_device)
+    with pytest.raises(L.VitkError):
+        L.attn_fwd(qkv, out, lse, 1, 16, 1, 32, 32 ** -0.5)

@@ -1,0 +1,152 @@
+"""tcgen05 GEMM (vitk_gemm_bf16) vs a plain torch fp32 reference on the same bf16-rounded inputs.
+
+Tolerances: fp32 outputs are fp32-accumulate checks (<= 1e-4 of the reference RMS; split-K atomics
+and K=3072 accumulate-order noise included); bf16 outputs add one bf16 rounding (<= 6e-3).
+"""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 2e-4
+BF16_TOL = 8e-3
+
+
+def _mk(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 128), (300, 256, 768), (256, 192, 192), (200, 128, 256),
+                                   (256, 1000, 768), (1576, 576, 192), (4096, 2304, 768), (1000, 768, 3072)])
+def test_fprop_f32(cuda_device, M, N, K):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    a = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((N, K), cuda_device, 0.05, seed=2).bfloat16()
+    bias = _mk((N,), cuda_device, seed=3)
+    out = torch.full((M, N), float("nan"), device=cuda_device)
+    L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_F32, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < F32_TOL
+
+
+@pytest.mark.parametrize("block_n", [128, 192, 256])
+def test_fprop_block_n_forced(cuda_device, block_n):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    M, N, K = 384, 768, 320
+    a = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((N, K), cuda_device, 0.05, seed=2).bfloat16()
+    out = torch.full((M, N), float("nan"), device=cuda_device)
+    L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_F32, block_n=block_n)
+    assert rel_err(out, a.float() @ w.float().t()) < F32_TOL
+
+
+def test_fprop_bf16_rowscale(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    M, N, K = 394, 768, 768
+    a = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((N, K), cuda_device, 0.05, seed=2).bfloat16()
+    bias = _mk((N,), cuda_device, seed=3)
+    rs = torch.tensor([0.0, 1.25], device=cuda_device)
+    out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_BF16, bias=bias, rowscale=rs, rows_per_group=197)
+    ref = (a.float() @ w.float().t() + bias) * rs.repeat_interleave(197)[:, None]
+    assert rel_err(out.float(), ref) < BF16_TOL
+
+
+def test_fprop_gelu_dual(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    M, N, K = 500, 3072, 768
+    a = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((N, K), cuda_device, 0.05, seed=2).bfloat16()
+    bias = _mk((N,), cuda_device, seed=3)
+    out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    aux = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_GELU, bias=bias, aux=aux)
+    h = a.float() @ w.float().t() + bias
+    assert rel_err(aux.float(), h) < BF16_TOL
+    assert rel_err(out.float(), torch.nn.functional.gelu(h)) < BF16_TOL
+
+
+def test_fprop_resid_scales(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    M, N, K = 394, 768, 3072
+    a = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((N, K), cuda_device, 0.02, seed=2).bfloat16()
+    bias = _mk((N,), cuda_device, seed=3)
+    resid = _mk((M, N), cuda_device, seed=4)
+    rs = torch.tensor([1.0 / 0.9, 0.0], device=cuda_device)
+    cs = _mk((N,), cuda_device, seed=5)
+    out = torch.empty((M, N), device=cuda_device)
+    L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_RESID, bias=bias, resid=resid, rowscale=rs, rows_per_group=197,
+           colscale=cs)
+    ref = resid + rs.repeat_interleave(197)[:, None] * cs[None, :] * (a.float() @ w.float().t() + bias)
+    assert rel_err(out, ref) < F32_TOL
+    out2 = torch.empty((M, N), device=cuda_device)
+    L.gemm(a, w, out2, M=M, N=N, K=K, epilogue=L.EPI_RESID, bias=bias, resid=resid)
+    assert rel_err(out2, resid + a.float() @ w.float().t() + bias) < F32_TOL
+
+
+def test_patch_epilogue(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    Bn, P, D, K, prefix = 3, 196, 192, 768, 1
+    a = _mk((Bn * P, K), cuda_device, seed=1).bfloat16()
+    w = _mk((D, K), cuda_device, 0.05, seed=2).bfloat16()
+    bias = _mk((D,), cuda_device, seed=3)
+    pos = _mk((P + prefix, D), cuda_device, seed=4)
+    out = torch.zeros((Bn, P + prefix, D), device=cuda_device)
+    L.gemm(a, w, out, M=Bn * P, N=D, K=K, epilogue=L.EPI_PATCH, bias=bias, pos=pos, tokens_per_img=P, prefix=prefix)
+    ref = torch.zeros_like(out)
+    ref[:, prefix:] = (a.float() @ w.float().t() + bias).view(Bn, P, D) + pos[prefix:]
+    assert rel_err(out, ref) < F32_TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (394, 768, 2304), (500, 768, 3072), (256, 768, 1000), (300, 384, 1536)])
+def test_dgrad_b_mn_major(cuda_device, M, N, K):
+    """dX[M, N=in] = dY[M, K=out] @ W[K=out, N=in]: B is W itself, MN-major."""
+    from vision_transformers_torch_xla_b200 import _lib as L
+    dy = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((K, N), cuda_device, 0.05, seed=2).bfloat16()
+    out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    L.gemm(dy, w, out, M=M, N=N, K=K, epilogue=L.EPI_BF16, b_mn=True)
+    assert rel_err(out.float(), dy.float() @ w.float()) < BF16_TOL
+
+
+def test_dgrad_dgelu(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    M, N, K = 394, 3072, 768
+    dy = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((K, N), cuda_device, 0.05, seed=2).bfloat16()
+    h = _mk((M, N), cuda_device, seed=3).bfloat16()
+    out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    L.gemm(dy, w, out, M=M, N=N, K=K, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
+    hf = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).backward(dy.float() @ w.float())
+    assert rel_err(out.float(), hf.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 256, 64, 1), (768, 768, 1576, 0), (2304, 768, 4000, 0), (1000, 768, 256, 0),
+                                          (576, 192, 1576, 3), (768, 3072, 50432, 0)])
+def test_wgrad_mn_mn_atomic(cuda_device, M, N, K, splits):
+    """dW[M=out, N=in] += dY[K=tokens, M]^T @ X[K=tokens, N]; fp32 red.add with split-K."""
+    from vision_transformers_torch_xla_b200 import _lib as L
+    dy = _mk((K, M), cuda_device, seed=1).bfloat16()
+    x = _mk((K, N), cuda_device, seed=2).bfloat16()
+    init = _mk((M, N), cuda_device, seed=3)
+    out = init.clone()
+    L.gemm(dy, x, out, M=M, N=N, K=K, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, splits=splits)
+    ref = init + dy.float().t() @ x.float()
+    assert rel_err(out, ref) < F32_TOL
+
+
+def test_gemm_rejects_bad_args(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    a = torch.zeros((128, 64), device=cuda_device, dtype=torch.bfloat16)
+    out = torch.zeros((128, 12), device=cuda_device)
+    with pytest.raises(L.VitkError):
+        L.gemm(a, a, out, M=128, N=12, K=64, epilogue=L.EPI_F32)  # N % 8 != 0
+    with pytest.raises(L.VitkError):
+        L.gemm(a, a, out, M=0, N=16, K=64, epilogue=L.EPI_F32)  # empty

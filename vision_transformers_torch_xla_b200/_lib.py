@@ -1,0 +1,316 @@
+"""ctypes binding of ``libvitk.so`` (C ABI declared in ``include/vitk.h``).
+
+This is the only place where Python touches the kernel library.  Every wrapper takes torch tensors,
+checks device / dtype / contiguity, and passes raw device pointers plus the current CUDA stream
+through the C ABI.  There is **no fallback**: if the shared library is missing or a call fails the
+wrapper raises, it never routes to PyTorch kernels or to the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvitk.so")
+
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_ATOMIC, EPI_PATCH = range(7)
+
+#: every symbol include/vitk.h declares (tests check the library exports exactly these)
+EXPORTED_SYMBOLS = (
+    "vitk_abi_version", "vitk_last_error", "vitk_arch", "vitk_gemm_bf16", "vitk_layernorm_fwd",
+    "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_patchify", "vitk_prefix_rows",
+    "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
+    "vitk_scale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
+)
+
+
+class GemmArgs(Structure):
+    """Mirror of ``struct vitk_gemm_args`` (include/vitk.h)."""
+
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p), ("lda", c_int64), ("ldb", c_int64),
+        ("a_mn_major", c_int32), ("b_mn_major", c_int32),
+        ("M", c_int32), ("N", c_int32), ("K", c_int32), ("epilogue", c_int32),
+        ("out", c_void_p), ("ld_out", c_int64), ("aux", c_void_p), ("ld_aux", c_int64),
+        ("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int64),
+        ("rowscale", c_void_p), ("rows_per_group", c_int32), ("colscale", c_void_p),
+        ("pos", c_void_p), ("tokens_per_img", c_int32), ("prefix", c_int32),
+        ("splits", c_int32), ("block_n", c_int32),
+    ]
+
+
+class VitkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libvitk.so (built in-tree by ``__graft_entry__.build()``); raise loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VitkError(
+            f"{LIB_PATH} not found: the sm_100a kernel library is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C "
+            "vision_transformers_torch_xla_b200/csrc`). There is no CPU/PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.vitk_abi_version.restype = c_int32
+    lib.vitk_last_error.restype = c_char_p
+    lib.vitk_arch.restype = c_char_p
+    lib.vitk_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
+    lib.vitk_layernorm_fwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                       c_void_p, c_int64, c_int32, c_float, c_void_p]
+    lib.vitk_layernorm_bwd.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
+                                       c_void_p, c_int64, c_int32, c_void_p]
+    lib.vitk_attn_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]
+    lib.vitk_attn_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                  c_int32, c_float, c_void_p]
+    lib.vitk_patchify.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.vitk_prefix_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.vitk_embed_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.vitk_pool_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.vitk_pool_bwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.vitk_colsum_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]
+    lib.vitk_ce_fwd_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float, c_float, c_void_p,
+                                    c_void_p, c_void_p, c_int32, c_int32, c_void_p]
+    lib.vitk_scale_cast_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.vitk_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.vitk_adamw_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                    c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_float, c_float, c_float,
+                                    c_int64, c_float, c_float, c_int32, c_void_p]
+    lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(lib, name)
+        if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version"):
+            fn.restype = c_int32
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().vitk_last_error().decode("utf-8", "replace")
+        raise VitkError(f"{what} failed (status {rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise VitkError(f"{name}: expected a CUDA tensor (the vitk kernels have no CPU path)")
+    if t.dtype != dtype:
+        raise VitkError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------
+# launch counter (bench.py reports how many of OUR kernels ran inside the timed region)
+# ------------------------------------------------------------------------------------------------
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM
+# ------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, epilogue: int,
+         a_mn: bool = False, b_mn: bool = False, lda: Optional[int] = None, ldb: Optional[int] = None,
+         ld_out: Optional[int] = None, aux: Optional[torch.Tensor] = None, ld_aux: Optional[int] = None,
+         bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+         rowscale: Optional[torch.Tensor] = None, rows_per_group: int = 1,
+         colscale: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
+         tokens_per_img: int = 0, prefix: int = 0, splits: int = 0, block_n: int = 0) -> None:
+    """D[M,N] = opA(a) @ opB(b)^T with a fused epilogue; see ``enum vitk_epilogue`` in include/vitk.h."""
+    _req(a, torch.bfloat16, "gemm A")
+    _req(b, torch.bfloat16, "gemm B")
+    args = GemmArgs()
+    args.A, args.B = a.data_ptr(), b.data_ptr()
+    args.lda = lda if lda is not None else (M if a_mn else K)
+    args.ldb = ldb if ldb is not None else (N if b_mn else K)
+    args.a_mn_major, args.b_mn_major = int(a_mn), int(b_mn)
+    args.M, args.N, args.K, args.epilogue = M, N, K, epilogue
+    args.out, args.ld_out = out.data_ptr(), (ld_out if ld_out is not None else N)
+    args.aux, args.ld_aux = _ptr(aux), (ld_aux if ld_aux is not None else N)
+    args.bias = _ptr(bias)
+    args.resid, args.ld_resid = _ptr(resid), N
+    args.rowscale, args.rows_per_group = _ptr(rowscale), rows_per_group
+    args.colscale = _ptr(colscale)
+    args.pos, args.tokens_per_img, args.prefix = _ptr(pos), tokens_per_img, prefix
+    args.splits, args.block_n = splits, block_n
+    for t, nm in ((bias, "bias"), (resid, "resid"), (rowscale, "rowscale"), (colscale, "colscale"), (pos, "pos")):
+        if t is not None:
+            _req(t, torch.float32, f"gemm {nm}")
+    _check(load().vitk_gemm_bf16(ctypes.byref(args), _stream()), "vitk_gemm_bf16")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------------
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor,
+                  mean: Optional[torch.Tensor], rstd: Optional[torch.Tensor], rows: int, dim: int,
+                  eps: float, ld_x: Optional[int] = None, ld_y: Optional[int] = None) -> None:
+    _req(x, torch.float32, "layernorm x")
+    _req(y, torch.bfloat16, "layernorm y")
+    _req(gamma, torch.float32, "layernorm gamma")
+    _check(load().vitk_layernorm_fwd(x.data_ptr(), ld_x or dim, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                     ld_y or dim, _ptr(mean), _ptr(rstd), rows, dim, eps, _stream()),
+           "vitk_layernorm_fwd")
+    _count()
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                  g_in: Optional[torch.Tensor], g_out: torch.Tensor, gb_out: Optional[torch.Tensor],
+                  rowscale: Optional[torch.Tensor], rows_per_group: int, dgamma: Optional[torch.Tensor],
+                  dbeta: Optional[torch.Tensor], rows: int, dim: int, ld_x: Optional[int] = None,
+                  ld_dy: Optional[int] = None, ld_g: Optional[int] = None) -> None:
+    _req(dy, torch.bfloat16, "layernorm_bwd dy")
+    _req(x, torch.float32, "layernorm_bwd x")
+    _req(g_out, torch.float32, "layernorm_bwd g_out")
+    _check(load().vitk_layernorm_bwd(dy.data_ptr(), ld_dy or dim, x.data_ptr(), ld_x or dim, mean.data_ptr(),
+                                     rstd.data_ptr(), gamma.data_ptr(), _ptr(g_in), g_out.data_ptr(), ld_g or dim,
+                                     _ptr(gb_out), _ptr(rowscale), rows_per_group, _ptr(dgamma), _ptr(dbeta), rows,
+                                     dim, _stream()), "vitk_layernorm_bwd")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# Attention
+# ------------------------------------------------------------------------------------------------
+def attn_fwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, B: int, N: int, H: int, hd: int,
+             scale: float) -> None:
+    _req(qkv, torch.bfloat16, "attn qkv")
+    _req(out, torch.bfloat16, "attn out")
+    _req(lse, torch.float32, "attn lse")
+    _check(load().vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd, scale, _stream()),
+           "vitk_attn_fwd")
+    _count()
+
+
+def attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor,
+             B: int, N: int, H: int, hd: int, scale: float) -> None:
+    for t, nm in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
+        _req(t, torch.bfloat16, f"attn_bwd {nm}")
+    _check(load().vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# embedding / pooling / reductions
+# ------------------------------------------------------------------------------------------------
+def patchify(img: torch.Tensor, patches: torch.Tensor, ps: int) -> None:
+    _req(img, torch.float32, "patchify img")
+    _req(patches, torch.bfloat16, "patchify out")
+    B, C, H, W = img.shape
+    _check(load().vitk_patchify(img.data_ptr(), patches.data_ptr(), B, C, H, W, ps, _stream()), "vitk_patchify")
+    _count()
+
+
+def prefix_rows(x: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor, B: int, N: int, D: int, prefix: int) -> None:
+    _req(x, torch.float32, "prefix_rows x")
+    _check(load().vitk_prefix_rows(x.data_ptr(), tok.data_ptr(), pos.data_ptr(), B, N, D, prefix, _stream()),
+           "vitk_prefix_rows")
+    _count()
+
+
+def embed_bwd(g: torch.Tensor, gp: Optional[torch.Tensor], dpos: Optional[torch.Tensor],
+              dprefix: Optional[torch.Tensor], B: int, N: int, D: int, prefix: int) -> None:
+    _req(g, torch.float32, "embed_bwd g")
+    _check(load().vitk_embed_bwd(g.data_ptr(), _ptr(gp), _ptr(dpos), _ptr(dprefix), B, N, D, prefix, _stream()),
+           "vitk_embed_bwd")
+    _count()
+
+
+def pool_fwd(x: torch.Tensor, pooled: torch.Tensor, B: int, N: int, D: int, prefix: int, mode: int) -> None:
+    _req(x, torch.float32, "pool x")
+    _check(load().vitk_pool_fwd(x.data_ptr(), pooled.data_ptr(), B, N, D, prefix, mode, _stream()), "vitk_pool_fwd")
+    _count()
+
+
+def pool_bwd(dpooled: torch.Tensor, g: torch.Tensor, B: int, N: int, D: int, prefix: int, mode: int) -> None:
+    _req(dpooled, torch.float32, "pool_bwd dpooled")
+    _check(load().vitk_pool_bwd(dpooled.data_ptr(), g.data_ptr(), B, N, D, prefix, mode, _stream()), "vitk_pool_bwd")
+    _count()
+
+
+def colsum_bf16(x: torch.Tensor, out: torch.Tensor, rows: int, cols: int, ld: Optional[int] = None) -> None:
+    _req(x, torch.bfloat16, "colsum x")
+    _req(out, torch.float32, "colsum out")
+    _check(load().vitk_colsum_bf16(x.data_ptr(), ld or cols, out.data_ptr(), rows, cols, _stream()), "vitk_colsum_bf16")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# loss / casts
+# ------------------------------------------------------------------------------------------------
+def ce_fwd_bwd(logits: torch.Tensor, soft: Optional[torch.Tensor], labels: Optional[torch.Tensor], smoothing: float,
+               teacher: Optional[torch.Tensor], alpha: float, temp: float, loss: torch.Tensor,
+               dlogits: torch.Tensor, scratch: torch.Tensor) -> None:
+    _req(logits, torch.float32, "ce logits")
+    B, C = logits.shape
+    if soft is not None:
+        _req(soft, torch.float32, "ce soft targets")
+    if labels is not None:
+        _req(labels, torch.int64, "ce labels")
+    if teacher is not None:
+        _req(teacher, torch.float32, "ce teacher logits")
+    _check(load().vitk_ce_fwd_bwd(logits.data_ptr(), _ptr(soft), _ptr(labels), smoothing, _ptr(teacher), alpha, temp,
+                                  loss.data_ptr(), dlogits.data_ptr(), scratch.data_ptr(), B, C, _stream()),
+           "vitk_ce_fwd_bwd")
+    _count(2)
+
+
+def scale_cast_bf16(src: torch.Tensor, scale: Optional[torch.Tensor], dst: torch.Tensor) -> None:
+    _req(src, torch.float32, "scale_cast src")
+    _req(dst, torch.bfloat16, "scale_cast dst")
+    _check(load().vitk_scale_cast_bf16(src.data_ptr(), _ptr(scale), dst.data_ptr(), src.numel(), _stream()),
+           "vitk_scale_cast_bf16")
+    _count()
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    scale_cast_bf16(src, None, dst)
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+def adamw_flat(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, shadow: Optional[torch.Tensor],
+               ema: Optional[torch.Tensor], chunk_group: Optional[torch.Tensor], chunk: int, lrs, wds, beta1: float,
+               beta2: float, eps: float, step: int, grad_scale: float = 1.0, ema_decay: float = 0.0,
+               zero_grad: bool = False) -> None:
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _req(t, torch.float32, f"adamw {nm}")
+    n = p.numel()
+    ng = len(lrs)
+    lr_arr = (c_float * ng)(*[float(x) for x in lrs])
+    wd_arr = (c_float * ng)(*[float(x) for x in wds])
+    _check(load().vitk_adamw_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), _ptr(ema), n,
+                                  _ptr(chunk_group), chunk, ng, lr_arr, wd_arr, beta1, beta2, eps, step, grad_scale,
+                                  ema_decay, int(zero_grad), _stream()), "vitk_adamw_flat")
+    _count()
+
+
+def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
+    _req(x, torch.float32, "sumsq x")
+    _check(load().vitk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
+    _count()

@@ -1,0 +1,536 @@
+// vitk_attn.cu — multi-head attention forward / backward on tcgen05 tensor cores (sm_100a).
+//
+// Replaces F.scaled_dot_product_attention(q, k, v) (dropout 0, no mask, scale = hd^-0.5) at the
+// timm Attention call site constructed by /root/reference/models/vision_transformer.py:149-159
+// (witness of the same math in-tree: /root/reference/models/eva.py:146-194).
+//
+// Layout: qkv bf16 [B, N, 3, H, 64] exactly as the qkv Linear writes it; out / dout bf16
+// [B, N, H*64]; lse fp32 [B, H, N].  Tiles are staged by TMA straight out of those tensors (3-D
+// tensor maps, rows past N are zero-filled by the TMA unit) into 128-byte-swizzled smem, S / dP /
+// O / dK / dV / dQ accumulate in TMEM, and thread t of the CTA owns row t of every 128-row tile
+// (TMEM lane == row), so the softmax needs no cross-thread reduction at all.
+//
+// The same smem bytes serve as a K-major operand ([rows][64 contiguous] = rows x K) and as an
+// MN-major operand (K rows x 64 contiguous MN) — only the UMMA descriptor differs — which is how
+// P / dS feed P*V, P^T*dO, dS^T*Q and dS*K without any transposes.
+#include "vitk_common.cuh"
+#include "vitk_internal.h"
+
+namespace {
+using namespace vitk;
+
+constexpr int HD = 64;
+constexpr int TILE = 128;
+constexpr uint32_t TILE_BYTES = TILE * HD * 2;  // 16 KB: [128 rows][128 B]
+constexpr int FWD_MAX_T = 5;                    // N <= 640
+constexpr int BWD_MAX_T = 2;                    // N <= 256 (dQ accumulators live in TMEM)
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t roundup16(int v) { return (uint32_t)((v + 15) & ~15); }
+
+// Store 8 consecutive bf16 (one 16-byte unit `u8` of row `r`) into a [chunk][128 rows][128 B] swizzled tile.
+__device__ __forceinline__ void st_swz(uint8_t* tile, int r, int col8, uint4 val) {
+  const int chunk = col8 >> 3;  // 64-column chunk
+  const int u = col8 & 7;       // 16-byte unit inside the 128-byte row
+  uint8_t* p = tile + chunk * TILE_BYTES + r * 128 + ((u ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(p) = val;
+}
+
+// ================================================================================================
+// Forward
+// ================================================================================================
+// smem: Q [16K] | K_j, V_j for all kv tiles [T * 32K] | P [32K] | barriers
+template <int T>
+struct FwdSmem {
+  static constexpr uint32_t Q_OFF = 0;
+  static constexpr uint32_t KV_OFF = TILE_BYTES;
+  static constexpr uint32_t P_OFF = KV_OFF + T * 2 * TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = P_OFF + 2 * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 128;
+};
+
+template <int T>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
+                float* __restrict__ lse, int N, int H, float scale) {
+  using L = FwdSmem<T>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* bar_kv = bar_q + 1;       // [T]
+  uint64_t* bar_s = bar_kv + T;
+  uint64_t* bar_o = bar_s + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_o + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = (N + TILE - 1) / TILE;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 32) {
+    mbar_init(bar_q, 1);
+    for (int j = 0; j < T; ++j) mbar_init(&bar_kv[j], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;         // S: 128 columns
+  const uint32_t tmem_o = tmem_base + 128;   // O_j: 64 columns
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_arrive_expect_tx(bar_q, TILE_BYTES);
+    tma_load_3d(smem + L::Q_OFF, &tm_qkv, bar_q, h * HD, q0, b);
+    for (int j = 0; j < nkv; ++j) {
+      mbar_arrive_expect_tx(&bar_kv[j], 2 * TILE_BYTES);
+      tma_load_3d(smem + L::KV_OFF + j * 2 * TILE_BYTES, &tm_qkv, &bar_kv[j], (H + h) * HD, j * TILE, b);
+      tma_load_3d(smem + L::KV_OFF + j * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, &bar_kv[j],
+                  (2 * H + h) * HD, j * TILE, b);
+    }
+  }
+
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const int r = threadIdx.x;  // row inside the q tile
+  const float c2 = scale * LOG2E;
+  float m_run = -INFINITY, l_run = 0.f;
+  float o_acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+
+  uint8_t* sP = smem + L::P_OFF;
+  const uint32_t sQ_u = smem_u32(smem + L::Q_OFF);
+  const uint32_t sP_u = smem_u32(sP);
+
+  for (int j = 0; j < nkv; ++j) {
+    const int kvn = min(TILE, N - j * TILE);
+    const uint32_t n_eff = roundup16(kvn);
+    const uint32_t sK_u = smem_u32(smem + L::KV_OFF + j * 2 * TILE_BYTES);
+    const uint32_t sV_u = sK_u + TILE_BYTES;
+    if (threadIdx.x == 0) {
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(&bar_kv[j], 0);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16_ss(tmem_s, umma_desc_kmajor(sQ_u + k * 32), umma_desc_kmajor(sK_u + k * 32), idesc, k > 0);
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, j & 1);
+    tc_fence_after();
+
+    // ---- online softmax over this kv tile: pass 1 row max, pass 2 exponentials -> P (bf16, smem) ----
+    const int nchunks = (int)(n_eff + 31) / 32;
+    float mx = m_run;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t sv[32];
+      tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c * 32 + i < kvn) mx = fmaxf(mx, __uint_as_float(sv[i]));
+    }
+    const float alpha = exp2f((m_run - mx) * c2);  // 0 on the first tile (m_run = -inf)
+    const float mc = mx * c2;
+    float rowsum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t sv[32];
+      tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+      tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float e = exp2f(fmaf(__uint_as_float(sv[i]), c2, -mc));
+        p[i] = (c * 32 + i < kvn) ? e : 0.f;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+          uint4 u;
+          u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
+          u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+          u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
+          u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+          st_swz(sP, r, c * 4 + g, u);
+          // the row sum uses the bf16-rounded probabilities so that P*V and l stay consistent
+          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+          rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+        }
+      }
+    }
+    l_run = l_run * alpha + rowsum;
+    m_run = mx;
+
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
+      const int ksteps = (int)n_eff / 16;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint32_t a_addr = sP_u + (k >> 2) * TILE_BYTES + (k & 3) * 32;
+        umma_bf16_ss(tmem_o, umma_desc_kmajor(a_addr), umma_desc_mnmajor(sV_u + k * 2048, TILE_BYTES), idesc, k > 0);
+      }
+      umma_commit(bar_o);
+    }
+    mbar_wait(bar_o, j & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t ov[32];
+      tmem_ld_32x32(tmem_o + lane_addr + c * 32, ov);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(ov[i]));
+    }
+    tc_fence_before();
+  }
+
+  const int q = q0 + r;
+  if (q < N) {
+    const float inv = 1.0f / l_run;
+    __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * HD) + h * HD;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 u;
+      u.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
+      u.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
+      u.z = pack_bf16x2(o_acc[g * 8 + 4] * inv, o_acc[g * 8 + 5] * inv);
+      u.w = pack_bf16x2(o_acc[g * 8 + 6] * inv, o_acc[g * 8 + 7] * inv);
+      *reinterpret_cast<uint4*>(orow + g * 8) = u;
+    }
+    if (lse) lse[((long long)b * H + h) * N + q] = m_run * scale + __logf(l_run);
+  }
+
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ================================================================================================
+// Backward (N <= 256): one CTA per (b, h); kv tile j outer, q tile i inner.
+// TMEM: S [0,128) | dP [128,256) | dV_j [256,320) | dK_j [320,384) | dQ_0 [384,448) | dQ_1 [448,512)
+// smem: Q_i, dO_i (T * 32K) | K_j, V_j (T * 32K) | P (32K) | dS (32K) | barriers
+// ================================================================================================
+struct BwdSmem {
+  static constexpr uint32_t QDO_OFF = 0;
+  static constexpr uint32_t KV_OFF = BWD_MAX_T * 2 * TILE_BYTES;
+  static constexpr uint32_t P_OFF = KV_OFF + BWD_MAX_T * 2 * TILE_BYTES;
+  static constexpr uint32_t DS_OFF = P_OFF + 2 * TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = DS_OFF + 2 * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 128;
+};
+
+__device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
+    u.y = pack_bf16x2(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
+    u.z = pack_bf16x2(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
+    u.w = pack_bf16x2(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
+    *reinterpret_cast<uint4*>(dst + g * 8) = u;
+  }
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(b[g * 8 + 0]), __uint_as_float(b[g * 8 + 1]));
+    u.y = pack_bf16x2(__uint_as_float(b[g * 8 + 2]), __uint_as_float(b[g * 8 + 3]));
+    u.z = pack_bf16x2(__uint_as_float(b[g * 8 + 4]), __uint_as_float(b[g * 8 + 5]));
+    u.w = pack_bf16x2(__uint_as_float(b[g * 8 + 6]), __uint_as_float(b[g * 8 + 7]));
+    *reinterpret_cast<uint4*>(dst + 32 + g * 8) = u;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+  using L = BwdSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* bar_sp = bar_ld + 1;
+  uint64_t* bar_drain = bar_sp + 1;  // completes once per kv tile j
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_drain + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nt = (N + TILE - 1) / TILE;  // q tiles == kv tiles
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 32) {
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_sp, 1);
+    mbar_init(bar_drain, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320;
+  const uint32_t tm_dq = tmem_base + 384;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_arrive_expect_tx(bar_ld, nt * 4 * TILE_BYTES);
+    for (int t = 0; t < nt; ++t) {
+      tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, h * HD, t * TILE, b);
+      tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_do, bar_ld, h * HD, t * TILE, b);
+      tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, (H + h) * HD, t * TILE, b);
+      tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, bar_ld, (2 * H + h) * HD, t * TILE, b);
+    }
+  }
+
+  // per-row statistics for the (up to) two q tiles this thread owns a row of
+  const int r = threadIdx.x;
+  float lse2[BWD_MAX_T], dsum[BWD_MAX_T];
+#pragma unroll
+  for (int i = 0; i < BWD_MAX_T; ++i) {
+    lse2[i] = 0.f;
+    dsum[i] = 0.f;
+    const int q = i * TILE + r;
+    if (i < nt && q < N) {
+      lse2[i] = lse[((long long)b * H + h) * N + q] * LOG2E;
+      const uint4* op = reinterpret_cast<const uint4*>(out + ((long long)b * N + q) * (H * HD) + h * HD);
+      const uint4* dp = reinterpret_cast<const uint4*>(dout + ((long long)b * N + q) * (H * HD) + h * HD);
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 a = __ldg(op + g), d = __ldg(dp + g);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+        s += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+      }
+      dsum[i] = s;
+    }
+  }
+
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const float c2 = scale * LOG2E;
+  uint8_t* sP = smem + L::P_OFF;
+  uint8_t* sDS = smem + L::DS_OFF;
+  const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
+  uint32_t sp_phase = 0;
+
+  // issue S = Q_i K_j^T and dP = dO_i V_j^T
+  auto issue_s_dp = [&](int j, int i) {
+    const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
+    const uint32_t sQ = smem_u32(smem + L::QDO_OFF + i * 2 * TILE_BYTES), sDO = sQ + TILE_BYTES;
+    const uint32_t sK = smem_u32(smem + L::KV_OFF + j * 2 * TILE_BYTES), sV = sK + TILE_BYTES;
+    const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      umma_bf16_ss(tm_s, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc, k > 0);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      umma_bf16_ss(tm_dp, umma_desc_kmajor(sDO + k * 32), umma_desc_kmajor(sV + k * 32), idesc, k > 0);
+    umma_commit(bar_sp);
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    issue_s_dp(0, 0);
+  }
+
+  for (int j = 0; j < nt; ++j) {
+    const int kvn = min(TILE, N - j * TILE);
+    const uint32_t n_eff = roundup16(kvn);
+    const int nchunks = (int)(n_eff + 31) / 32;
+    for (int i = 0; i < nt; ++i) {
+      const int qn = min(TILE, N - i * TILE);
+      const uint32_t q_eff = roundup16(qn);
+      const bool row_ok = r < qn;
+      const float my_lse2 = (i == 0) ? lse2[0] : lse2[1];
+      const float my_d = (i == 0) ? dsum[0] : dsum[1];
+
+      // S, dP ready; this also implies the previous iteration's dV/dK/dQ MMAs (which read P/dS) retired.
+      mbar_wait(bar_sp, sp_phase);
+      sp_phase ^= 1;
+      tc_fence_after();
+
+      // every thread executes the (.sync.aligned) TMEM loads; only rows < q_eff compute and store
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld_32x32(tm_s + lane_addr + c * 32, sv);
+        tmem_ld_32x32(tm_dp + lane_addr + c * 32, dv);
+        tmem_ld_wait();
+        if ((uint32_t)r < q_eff) {
+          float p[32], ds[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const bool ok = row_ok && (c * 32 + k < kvn);
+            const float e = exp2f(fmaf(__uint_as_float(sv[k]), c2, -my_lse2));
+            p[k] = ok ? e : 0.f;
+            ds[k] = ok ? e * (__uint_as_float(dv[k]) - my_d) * scale : 0.f;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+              uint4 u, w;
+              u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
+              u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+              u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
+              u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+              w.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]);
+              w.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
+              w.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]);
+              w.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
+              st_swz(sP, r, c * 4 + g, u);
+              st_swz(sDS, r, c * 4 + g, w);
+            }
+          }
+        }
+      }
+
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tc_fence_after();
+        const uint32_t sQ = smem_u32(smem + L::QDO_OFF + i * 2 * TILE_BYTES), sDO = sQ + TILE_BYTES;
+        const uint32_t sK = smem_u32(smem + L::KV_OFF + j * 2 * TILE_BYTES);
+        // dV_j += P^T dO_i ; dK_j += dS^T Q_i   (A MN-major [kv chunks][q rows][64], B MN-major)
+        const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);
+        const int qsteps = (int)q_eff / 16;
+        for (int k = 0; k < qsteps; ++k)
+          umma_bf16_ss(tm_dv, umma_desc_mnmajor(sP_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sDO + k * 2048, TILE_BYTES),
+                       idesc_t, (i > 0 || k > 0));
+        for (int k = 0; k < qsteps; ++k)
+          umma_bf16_ss(tm_dk, umma_desc_mnmajor(sDS_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sQ + k * 2048, TILE_BYTES),
+                       idesc_t, (i > 0 || k > 0));
+        // dQ_i += dS K_j   (A K-major, B = K_j MN-major)
+        const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);
+        const int ksteps = (int)n_eff / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint32_t a_addr = sDS_u + (k >> 2) * TILE_BYTES + (k & 3) * 32;
+          umma_bf16_ss(tm_dq + i * HD, umma_desc_kmajor(a_addr), umma_desc_mnmajor(sK + k * 2048, TILE_BYTES), idesc_q,
+                       (j > 0 || k > 0));
+        }
+        if (i == nt - 1) umma_commit(bar_drain);
+        // next S/dP pair queues right behind on the tensor pipe
+        int ni = i + 1, nj = j;
+        if (ni == nt) { ni = 0; nj = j + 1; }
+        if (nj < nt) issue_s_dp(nj, ni);
+      }
+    }
+
+    // ---- drain dV_j, dK_j (row = kv index) ----
+    // tcgen05 ops retire in issue order, so this also covers every earlier MMA of this kv tile.
+    mbar_wait(bar_drain, j & 1);
+    tc_fence_after();
+    {
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(tm_dv + lane_addr, a0);
+      tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
+      tmem_ld_wait();
+      const int kv = j * TILE + r;
+      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (2 * H + h) * HD, a0, a1);
+      tmem_ld_32x32(tm_dk + lane_addr, a0);
+      tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
+      tmem_ld_wait();
+      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (H + h) * HD, a0, a1);
+    }
+    // NOTE: the next kv tile's dV/dK MMAs (accumulate = 0) are only issued after the next
+    // iteration's __syncthreads, i.e. after every thread finished these TMEM reads.
+    tc_fence_before();
+  }
+
+  // ---- drain dQ_i ----
+  tc_fence_after();
+  for (int i = 0; i < nt; ++i) {
+    uint32_t a0[32], a1[32];
+    tmem_ld_32x32(tm_dq + i * HD + lane_addr, a0);
+    tmem_ld_32x32(tm_dq + i * HD + lane_addr + 32, a1);
+    tmem_ld_wait();
+    const int q = i * TILE + r;
+    if (q < N) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * HD) + h * HD, a0, a1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int T>
+int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
+  auto kern = attn_fwd_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<T>::BYTES);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((N + TILE - 1) / TILE, H, B);
+  kern<<<grid, 128, FwdSmem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale);
+  return vitk_check_launch("attn_fwd");
+}
+
+}  // namespace
+
+extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t head_dim,
+                             float scale, void* stream) {
+  VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_fwd: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_REQUIRE(head_dim == HD, VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d (only 64 is built)", head_dim);
+  VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_fwd: N=%d > %d", N, FWD_MAX_T * TILE);
+  VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, VITK_ERR_ALIGN, "attn_fwd: unaligned");
+  CUtensorMap tm;
+  int rc = vitk_make_tmap_3d(&tm, qkv, 2, (uint64_t)3 * H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)3 * H * HD,
+                             (uint64_t)N * 3 * H * HD, HD, TILE, 1);
+  if (rc) return rc;
+  const int T = (N + TILE - 1) / TILE;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (T) {
+    case 1: return launch_fwd<1>(tm, out, lse, B, N, H, scale, s);
+    case 2: return launch_fwd<2>(tm, out, lse, B, N, H, scale, s);
+    case 3: return launch_fwd<3>(tm, out, lse, B, N, H, scale, s);
+    case 4: return launch_fwd<4>(tm, out, lse, B, N, H, scale, s);
+    default: return launch_fwd<5>(tm, out, lse, B, N, H, scale, s);
+  }
+}
+
+extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int32_t B,
+                             int32_t N, int32_t H, int32_t head_dim, float scale, void* stream) {
+  VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
+  VITK_REQUIRE(head_dim == HD, VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (only 64 is built)", head_dim);
+  VITK_REQUIRE(N <= BWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_bwd: N=%d > %d not built yet", N, BWD_MAX_T * TILE);
+  VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
+               VITK_ERR_ALIGN, "attn_bwd: unaligned");
+  CUtensorMap tm_qkv, tm_do;
+  int rc = vitk_make_tmap_3d(&tm_qkv, qkv, 2, (uint64_t)3 * H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)3 * H * HD,
+                             (uint64_t)N * 3 * H * HD, HD, TILE, 1);
+  if (rc) return rc;
+  rc = vitk_make_tmap_3d(&tm_do, dout, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD,
+                         HD, TILE, 1);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem::BYTES);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid(H, B);
+  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, (cudaStream_t)stream>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
+                                                                       (const __nv_bfloat16*)dout, lse,
+                                                                       (__nv_bfloat16*)dqkv, N, H, scale);
+  return vitk_check_launch("attn_bwd");
+}

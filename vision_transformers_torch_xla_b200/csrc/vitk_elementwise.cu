@@ -1,0 +1,532 @@
+// vitk_elementwise.cu — bandwidth-bound helpers of the ViT training step:
+// patchify (im2col + cast), prefix-token rows, embedding backward, pooling, bias-gradient column
+// sums, fused cross-entropy (soft-target / label-smoothing / KD) forward+backward, flat AdamW.
+//
+// Reference call sites: PatchEmbed + _pos_embed (/root/reference/models/vision_transformer.py:552-560,
+// 743-780), global_pool_nlc (:419-441), losses (/root/reference/main.py:926-968, timm.loss),
+// torch.optim.AdamW (/root/reference/optim_factory.py:248-249).
+#include "vitk_common.cuh"
+#include "vitk_internal.h"
+
+namespace {
+using namespace vitk;
+
+// ------------------------------------------------------------------------------------------------
+// patchify: fp32 NCHW -> bf16 [B*P, C*ps*ps], column order (c, ph, pw)
+// ------------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                int B, int C, int H, int W, int ps) {
+  const long long total = (long long)B * C * H * (W / 8);
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int wv = W / 8;
+  const int xv = (int)(idx % wv);
+  long long t = idx / wv;
+  const int y = (int)(t % H);
+  t /= H;
+  const int c = (int)(t % C);
+  const int b = (int)(t / C);
+  const float4* src = reinterpret_cast<const float4*>(img + (((long long)b * C + c) * H + y) * W + xv * 8);
+  const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
+  const int gw = W / ps, gh = H / ps;
+  const int py = y / ps, ph = y - py * ps;
+  const int x0 = xv * 8;
+  const int px = x0 / ps, pw = x0 - px * ps;
+  const long long row = (long long)b * gh * gw + (long long)py * gw + px;
+  const int col = (c * ps + ph) * ps + pw;
+  uint4 u;
+  u.x = pack_bf16x2(a0.x, a0.y);
+  u.y = pack_bf16x2(a0.z, a0.w);
+  u.z = pack_bf16x2(a1.x, a1.y);
+  u.w = pack_bf16x2(a1.z, a1.w);
+  *reinterpret_cast<uint4*>(out + row * ((long long)C * ps * ps) + col) = u;
+}
+
+__global__ void prefix_rows_kernel(float* __restrict__ x, const float* __restrict__ tok,
+                                   const float* __restrict__ pos, int B, int N, int D, int prefix) {
+  const long long total = (long long)B * prefix * D;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int d = (int)(idx % D);
+  const int j = (int)((idx / D) % prefix);
+  const int b = (int)(idx / ((long long)D * prefix));
+  x[((long long)b * N + j) * D + d] = tok[j * D + d] + pos[j * D + d];
+}
+
+// grid: (ceil(N*D/4 / 256), bchunks).  Thread owns one float4 column group of one token.
+__global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ gp,
+                                 float* __restrict__ dpos, float* __restrict__ dprefix, int B, int N,
+                                 int D, int prefix) {
+  const int dv = D / 4;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * dv) return;
+  const int n = (int)(idx / dv);
+  const int c = (int)(idx % dv);
+  const int bper = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * bper;
+  const int b1 = min(B, b0 + bper);
+  const int P = N - prefix;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int b = b0; b < b1; ++b) {
+    const float4 v = *reinterpret_cast<const float4*>(g + ((long long)b * N + n) * D + c * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (gp != nullptr && n >= prefix) {
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(gp + ((long long)b * P + (n - prefix)) * D + c * 4) = o;
+    }
+  }
+  if (b1 > b0) {
+    if (dpos) {
+      float* o = dpos + (long long)n * D + c * 4;
+      atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+    }
+    if (dprefix && n < prefix) {
+      float* o = dprefix + (long long)n * D + c * 4;
+      atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
+    }
+  }
+}
+
+// pooled[b, d] = mean_{t >= prefix} x[b, t, d]   (mode 0)  or  x[b, 0, d]  (mode 1)
+// grid: (ceil(D/4/64), B), block (64, 4): 4 token lanes reduced through smem.
+__global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ pooled, int N, int D,
+                                int prefix, int mode) {
+  __shared__ float4 part[4][64];
+  const int c = blockIdx.x * 64 + threadIdx.x;
+  const int b = blockIdx.y;
+  const int dv = D / 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < dv) {
+    if (mode == 1) {
+      if (threadIdx.y == 0) acc = *reinterpret_cast<const float4*>(x + ((long long)b * N) * D + c * 4);
+    } else {
+      for (int t = prefix + threadIdx.y; t < N; t += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(x + ((long long)b * N + t) * D + c * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < dv) {
+    float4 r = part[0][threadIdx.x];
+    for (int k = 1; k < 4; ++k) {
+      const float4 v = part[k][threadIdx.x];
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    if (mode == 0) {
+      const float inv = 1.0f / (float)(N - prefix);
+      r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+    }
+    *reinterpret_cast<float4*>(pooled + (long long)b * D + c * 4) = r;
+  }
+}
+
+__global__ void pool_bwd_kernel(const float* __restrict__ dpooled, float* __restrict__ g, int B, int N,
+                                int D, int prefix, int mode) {
+  const int dv = D / 4;
+  const long long total = (long long)B * N * dv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % dv);
+  const int t = (int)((idx / dv) % N);
+  const int b = (int)(idx / ((long long)dv * N));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool live = (mode == 1) ? (t == 0) : (t >= prefix);
+  if (live) {
+    r = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)b * D + c * 4));
+    if (mode == 0) {
+      const float inv = 1.0f / (float)(N - prefix);
+      r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+    }
+  }
+  *reinterpret_cast<float4*>(g + ((long long)b * N + t) * D + c * 4) = r;
+}
+
+// out[c] += sum_r x[r, c].  block (32, 8): 32 lanes x 8 columns each = 256 columns, 8 row lanes.
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out,
+                                   long long rows, int cols) {
+  __shared__ float part[8][256];
+  const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+  const long long rper = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * rper;
+  const long long r1 = min(rows, r0 + rper);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < cols) {
+#pragma unroll 4
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + r * ld + c0);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int c = blockIdx.x * 256 + tid;
+  if (c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][tid];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused cross-entropy forward + backward.  One CTA (256 threads) per batch row.
+// ------------------------------------------------------------------------------------------------
+constexpr int CE_THREADS = 256;
+constexpr int CE_MAXPT = 16;  // up to 4096 classes
+
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  float r = sh[0];
+#pragma unroll
+  for (int i = 1; i < CE_THREADS / 32; ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+  return r;
+}
+
+__global__ void __launch_bounds__(CE_THREADS)
+ce_kernel(const float* __restrict__ logits, const float* __restrict__ soft, const long long* __restrict__ labels,
+          float smoothing, const float* __restrict__ teacher, float alpha, float T,
+          float* __restrict__ dlogits, float* __restrict__ row_loss, int B, int C) {
+  __shared__ float sh[CE_THREADS / 32];
+  const int b = blockIdx.x;
+  const float* xr = logits + (long long)b * C;
+  float xv[CE_MAXPT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < CE_MAXPT; ++i) {
+    const int c = threadIdx.x + i * CE_THREADS;
+    xv[i] = (c < C) ? xr[c] : -INFINITY;
+    mx = fmaxf(mx, xv[i]);
+  }
+  mx = block_reduce(mx, true, sh);
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < CE_MAXPT; ++i) {
+    const int c = threadIdx.x + i * CE_THREADS;
+    if (c < C) se += __expf(xv[i] - mx);
+  }
+  se = block_reduce(se, false, sh);
+  const float lse = mx + __logf(se);
+
+  // base term: -sum_c t_c * (x_c - lse)
+  const long long label = (soft == nullptr && labels != nullptr) ? labels[b] : -1;
+  const float off_v = smoothing / (float)C, on_v = 1.0f - smoothing + off_v;
+  float tv[CE_MAXPT];
+  float base = 0.f, tsum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CE_MAXPT; ++i) {
+    const int c = threadIdx.x + i * CE_THREADS;
+    tv[i] = 0.f;
+    if (c < C) {
+      tv[i] = soft ? soft[(long long)b * C + c] : ((long long)c == label ? on_v : off_v);
+      base -= tv[i] * (xv[i] - lse);
+      tsum += tv[i];
+    }
+  }
+  base = block_reduce(base, false, sh);
+  tsum = block_reduce(tsum, false, sh);
+
+  float kd = 0.f;
+  float lse_s = 0.f, lse_t = 0.f;
+  const float invT = 1.0f / T;
+  if (teacher != nullptr) {
+    const float* zr = teacher + (long long)b * C;
+    float zmx = -INFINITY;
+    float zv[CE_MAXPT];
+#pragma unroll
+    for (int i = 0; i < CE_MAXPT; ++i) {
+      const int c = threadIdx.x + i * CE_THREADS;
+      zv[i] = (c < C) ? zr[c] * invT : -INFINITY;
+      zmx = fmaxf(zmx, zv[i]);
+    }
+    zmx = block_reduce(zmx, true, sh);
+    float zs = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < CE_MAXPT; ++i) {
+      const int c = threadIdx.x + i * CE_THREADS;
+      if (c < C) {
+        zs += __expf(zv[i] - zmx);
+        ss += __expf((xv[i] - mx) * invT);
+      }
+    }
+    zs = block_reduce(zs, false, sh);
+    ss = block_reduce(ss, false, sh);
+    lse_t = zmx + __logf(zs);
+    lse_s = mx * invT + __logf(ss);
+#pragma unroll
+    for (int i = 0; i < CE_MAXPT; ++i) {
+      const int c = threadIdx.x + i * CE_THREADS;
+      if (c < C) {
+        const float lpt = zv[i] - lse_t;
+        const float lps = xv[i] * invT - lse_s;
+        const float pt = __expf(lpt);
+        kd += pt * (lpt - lps);
+        // stash p_t - p_s(T) contribution in zv for the gradient pass
+        zv[i] = __expf(lps) - pt;
+      }
+    }
+    kd = block_reduce(kd, false, sh);
+    const float invB = 1.0f / (float)B;
+#pragma unroll
+    for (int i = 0; i < CE_MAXPT; ++i) {
+      const int c = threadIdx.x + i * CE_THREADS;
+      if (c < C) {
+        const float p = __expf(xv[i] - lse);
+        const float gbase = (p * tsum - tv[i]) * invB;
+        dlogits[(long long)b * C + c] = (1.0f - alpha) * gbase + alpha * T * zv[i] * invB;
+      }
+    }
+    if (threadIdx.x == 0) row_loss[b] = (1.0f - alpha) * base + alpha * T * T * kd;
+  } else {
+    const float invB = 1.0f / (float)B;
+#pragma unroll
+    for (int i = 0; i < CE_MAXPT; ++i) {
+      const int c = threadIdx.x + i * CE_THREADS;
+      if (c < C) {
+        const float p = __expf(xv[i] - lse);
+        dlogits[(long long)b * C + c] = (p * tsum - tv[i]) * invB;
+      }
+    }
+    if (threadIdx.x == 0) row_loss[b] = base;
+  }
+}
+
+__global__ void mean_rows_kernel(const float* __restrict__ row_loss, float* __restrict__ loss, int B) {
+  __shared__ float sh[CE_THREADS / 32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < B; i += CE_THREADS) s += row_loss[i];
+  s = block_reduce(s, false, sh);
+  if (threadIdx.x == 0) loss[0] = s / (float)B;
+}
+
+__global__ void scale_cast_kernel(const float* __restrict__ in, const float* __restrict__ scale,
+                                  __nv_bfloat16* __restrict__ out, long long n) {
+  const float s = scale ? __ldg(scale) : 1.0f;
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i4);
+    uint2 o;
+    o.x = pack_bf16x2(v.x * s, v.y * s);
+    o.y = pack_bf16x2(v.z * s, v.w * s);
+    *reinterpret_cast<uint2*>(out + i4) = o;
+  } else {
+    for (long long i = i4; i < n; ++i) out[i] = __float2bfloat16(in[i] * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flat AdamW
+// ------------------------------------------------------------------------------------------------
+constexpr int ADAMW_MAX_GROUPS = 8;
+struct AdamwHyper {
+  float lr[ADAMW_MAX_GROUPS];
+  float wd[ADAMW_MAX_GROUPS];
+  float beta1, beta2, eps, inv_bc1, inv_sqrt_bc2, grad_scale, ema_decay;
+  int zero_grad;
+};
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ shadow, float* __restrict__ ema, long long n,
+             const uint8_t* __restrict__ chunk_group, int chunk, const AdamwHyper h) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const int grp = chunk_group ? chunk_group[i4 / chunk] : 0;
+  const float lr = h.lr[grp], wd = h.wd[grp];
+  float4 pv = *reinterpret_cast<float4*>(p + i4);
+  float4 gv = *reinterpret_cast<float4*>(g + i4);
+  float4 mv = *reinterpret_cast<float4*>(m + i4);
+  float4 vv = *reinterpret_cast<float4*>(v + i4);
+  const float decay = 1.0f - lr * wd;
+  const float step = lr * h.inv_bc1;
+#define VITK_ADAMW_ONE(P, G, M, V)                              \
+  {                                                             \
+    const float gg = (G) * h.grad_scale;                        \
+    (P) *= decay;                                               \
+    (M) = h.beta1 * (M) + (1.0f - h.beta1) * gg;                \
+    (V) = h.beta2 * (V) + (1.0f - h.beta2) * gg * gg;           \
+    const float denom = sqrtf(V) * h.inv_sqrt_bc2 + h.eps;      \
+    (P) -= step * ((M) / denom);                                \
+  }
+  VITK_ADAMW_ONE(pv.x, gv.x, mv.x, vv.x)
+  VITK_ADAMW_ONE(pv.y, gv.y, mv.y, vv.y)
+  VITK_ADAMW_ONE(pv.z, gv.z, mv.z, vv.z)
+  VITK_ADAMW_ONE(pv.w, gv.w, mv.w, vv.w)
+#undef VITK_ADAMW_ONE
+  *reinterpret_cast<float4*>(p + i4) = pv;
+  *reinterpret_cast<float4*>(m + i4) = mv;
+  *reinterpret_cast<float4*>(v + i4) = vv;
+  if (h.zero_grad) *reinterpret_cast<float4*>(g + i4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (shadow) {
+    uint2 o;
+    o.x = pack_bf16x2(pv.x, pv.y);
+    o.y = pack_bf16x2(pv.z, pv.w);
+    *reinterpret_cast<uint2*>(shadow + i4) = o;
+  }
+  if (ema) {
+    float4 e = *reinterpret_cast<float4*>(ema + i4);
+    const float d = h.ema_decay;
+    e.x = d * e.x + (1.0f - d) * pv.x; e.y = d * e.y + (1.0f - d) * pv.y;
+    e.z = d * e.z + (1.0f - d) * pv.z; e.w = d * e.w + (1.0f - d) * pv.w;
+    *reinterpret_cast<float4*>(ema + i4) = e;
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sh[CE_THREADS / 32];
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    } else {
+      for (long long j = i; j < n; ++j) s += x[j] * x[j];
+    }
+  }
+  s = block_reduce(s, false, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+
+extern "C" int vitk_patchify(const float* img, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W,
+                             int32_t ps, void* stream) {
+  VITK_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && ps > 0, VITK_ERR_SHAPE, "patchify: bad shape");
+  VITK_REQUIRE(H % ps == 0 && W % ps == 0 && ps % 8 == 0, VITK_ERR_SHAPE,
+               "patchify: H=%d W=%d must be multiples of ps=%d and ps a multiple of 8", H, W, ps);
+  VITK_REQUIRE(((uintptr_t)img & 15) == 0 && ((uintptr_t)patches_bf16 & 15) == 0, VITK_ERR_ALIGN, "patchify: unaligned");
+  const long long total = (long long)B * C * H * (W / 8);
+  patchify_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)patches_bf16, B, C, H, W, ps);
+  return vitk_check_launch("patchify");
+}
+
+extern "C" int vitk_prefix_rows(float* x, const float* prefix_tok, const float* pos, int32_t B, int32_t N, int32_t D,
+                                int32_t prefix, void* stream) {
+  VITK_REQUIRE(B > 0 && N > 0 && D > 0 && prefix >= 0 && prefix <= N, VITK_ERR_SHAPE, "prefix_rows: bad shape");
+  if (prefix == 0) return VITK_OK;
+  const long long total = (long long)B * prefix * D;
+  prefix_rows_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, prefix_tok, pos, B, N, D, prefix);
+  return vitk_check_launch("prefix_rows");
+}
+
+extern "C" int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix, int32_t B, int32_t N,
+                              int32_t D, int32_t prefix, void* stream) {
+  VITK_REQUIRE(B > 0 && N > 0 && D > 0 && D % 4 == 0 && prefix >= 0 && prefix <= N, VITK_ERR_SHAPE, "embed_bwd: bad shape");
+  const long long total = (long long)N * (D / 4);
+  const int bchunks = B >= 32 ? 8 : 1;
+  dim3 grid(blocks_for(total, 256), bchunks);
+  embed_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)gp_bf16, dpos, dprefix, B, N, D, prefix);
+  return vitk_check_launch("embed_bwd");
+}
+
+extern "C" int vitk_pool_fwd(const float* x, float* pooled, int32_t B, int32_t N, int32_t D, int32_t prefix,
+                             int32_t mode, void* stream) {
+  VITK_REQUIRE(B > 0 && N > prefix && D > 0 && D % 4 == 0, VITK_ERR_SHAPE, "pool_fwd: bad shape");
+  VITK_REQUIRE(mode == 0 || mode == 1, VITK_ERR_UNSUPPORTED, "pool_fwd: mode %d (0=avg, 1=token)", mode);
+  dim3 grid(blocks_for(D / 4, 64), B), block(64, 4);
+  pool_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, pooled, N, D, prefix, mode);
+  return vitk_check_launch("pool_fwd");
+}
+
+extern "C" int vitk_pool_bwd(const float* dpooled, float* g, int32_t B, int32_t N, int32_t D, int32_t prefix,
+                             int32_t mode, void* stream) {
+  VITK_REQUIRE(B > 0 && N > prefix && D > 0 && D % 4 == 0, VITK_ERR_SHAPE, "pool_bwd: bad shape");
+  VITK_REQUIRE(mode == 0 || mode == 1, VITK_ERR_UNSUPPORTED, "pool_bwd: mode %d (0=avg, 1=token)", mode);
+  const long long total = (long long)B * N * (D / 4);
+  pool_bwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dpooled, g, B, N, D, prefix, mode);
+  return vitk_check_launch("pool_bwd");
+}
+
+extern "C" int vitk_colsum_bf16(const void* x_bf16, int64_t ld, float* out, int64_t rows, int32_t cols, void* stream) {
+  VITK_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0, VITK_ERR_SHAPE, "colsum: cols/ld must be multiples of 8");
+  if (rows == 0) return VITK_OK;
+  const unsigned gx = blocks_for(cols, 256);
+  long long gy = (long long)vitk_num_sms() * 4 / gx;
+  if (gy < 1) gy = 1;
+  const long long maxgy = (rows + 63) / 64;
+  if (gy > maxgy) gy = maxgy;
+  dim3 grid(gx, (unsigned)gy), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, ld, out, rows, cols);
+  return vitk_check_launch("colsum_bf16");
+}
+
+extern "C" int vitk_ce_fwd_bwd(const float* logits, const float* soft_targets, const int64_t* labels, float smoothing,
+                               const float* teacher_logits, float kd_alpha, float kd_temp, float* loss, float* dlogits,
+                               float* row_loss_scratch, int32_t B, int32_t C, void* stream) {
+  VITK_REQUIRE(B > 0 && C > 0 && C <= CE_THREADS * CE_MAXPT, VITK_ERR_SHAPE, "ce: C=%d must be in [1, %d]", C, CE_THREADS * CE_MAXPT);
+  VITK_REQUIRE(soft_targets != nullptr || labels != nullptr, VITK_ERR_SHAPE, "ce: need soft_targets or labels");
+  VITK_REQUIRE(loss && dlogits && row_loss_scratch, VITK_ERR_SHAPE, "ce: loss/dlogits/scratch required");
+  if (teacher_logits != nullptr) VITK_REQUIRE(kd_temp > 0.f, VITK_ERR_SHAPE, "ce: kd_temp must be > 0");
+  const float alpha = teacher_logits ? kd_alpha : 0.f;
+  ce_kernel<<<B, CE_THREADS, 0, (cudaStream_t)stream>>>(logits, soft_targets, (const long long*)labels, smoothing,
+                                                        teacher_logits, alpha, teacher_logits ? kd_temp : 1.f, dlogits,
+                                                        row_loss_scratch, B, C);
+  int rc = vitk_check_launch("ce");
+  if (rc) return rc;
+  mean_rows_kernel<<<1, CE_THREADS, 0, (cudaStream_t)stream>>>(row_loss_scratch, loss, B);
+  return vitk_check_launch("ce_mean");
+}
+
+extern "C" int vitk_scale_cast_bf16(const float* in, const float* scale_dev, void* out_bf16, int64_t n, void* stream) {
+  VITK_REQUIRE(n >= 0, VITK_ERR_SHAPE, "scale_cast: n < 0");
+  VITK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, VITK_ERR_ALIGN, "scale_cast: unaligned");
+  if (n == 0) return VITK_OK;
+  scale_cast_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, scale_dev, (__nv_bfloat16*)out_bf16, n);
+  return vitk_check_launch("scale_cast");
+}
+
+extern "C" int vitk_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
+  return vitk_scale_cast_bf16(in, nullptr, out_bf16, n, stream);
+}
+
+extern "C" int vitk_adamw_flat(float* p, float* g, float* m, float* v, void* shadow_bf16, float* ema, int64_t n,
+                               const uint8_t* chunk_group, int32_t chunk, int32_t num_groups, const float* lr,
+                               const float* wd, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                               float ema_decay, int32_t zero_grad, void* stream) {
+  VITK_REQUIRE(n >= 0 && n % 4 == 0, VITK_ERR_SHAPE, "adamw: n=%lld must be a multiple of 4", (long long)n);
+  VITK_REQUIRE(num_groups >= 1 && num_groups <= ADAMW_MAX_GROUPS, VITK_ERR_SHAPE, "adamw: num_groups=%d not in [1,%d]", num_groups, ADAMW_MAX_GROUPS);
+  VITK_REQUIRE(chunk_group == nullptr || (chunk > 0 && chunk % 4 == 0), VITK_ERR_SHAPE, "adamw: chunk must be a positive multiple of 4");
+  VITK_REQUIRE(step >= 1, VITK_ERR_SHAPE, "adamw: step must be >= 1");
+  VITK_REQUIRE(lr && wd, VITK_ERR_SHAPE, "adamw: lr/wd arrays required");
+  if (n == 0) return VITK_OK;
+  AdamwHyper h;
+  for (int i = 0; i < ADAMW_MAX_GROUPS; ++i) {
+    h.lr[i] = i < num_groups ? lr[i] : 0.f;
+    h.wd[i] = i < num_groups ? wd[i] : 0.f;
+  }
+  h.beta1 = beta1; h.beta2 = beta2; h.eps = eps;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  h.inv_bc1 = (float)(1.0 / bc1);
+  h.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  h.grad_scale = grad_scale; h.ema_decay = ema_decay; h.zero_grad = zero_grad;
+  adamw_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)shadow_bf16, ema, n,
+                                                                          chunk_group, chunk > 0 ? chunk : 4, h);
+  return vitk_check_launch("adamw");
+}
+
+extern "C" int vitk_sumsq(const float* x, int64_t n, float* out, void* stream) {
+  VITK_REQUIRE(n >= 0 && out, VITK_ERR_SHAPE, "sumsq: bad args");
+  if (n == 0) return VITK_OK;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)vitk_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  return vitk_check_launch("sumsq");
+}

@@ -1,0 +1,483 @@
+// vitk_gemm.cu — persistent warp-specialised tcgen05/TMEM bf16 GEMM for sm_100a.
+//
+//   D[M,N] = opA(A)[M,K] * opB(B)[N,K]^T      (fp32 accumulation in TMEM)
+//
+// Replaces the library GEMMs dispatched by the reference's nn.Linear / Conv2d-patchify
+// call sites (SURVEY §2.4 K1,K4,K6,K7,K8,K10): qkv/proj (timm Attention via
+// /root/reference/models/vision_transformer.py:149-159), fc1/fc2 (Mlp, :164-171), head (:618)
+// and their dgrad/wgrad in autograd.
+//
+// Roles (384 threads, 1 CTA / SM, persistent over output tiles):
+//   warp 0      TMA producer   (global -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1      MMA issuer     (one elected thread: tcgen05.mma 128 x BLOCK_N x 16, cta_group::1)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue       (tcgen05.ld accumulator -> fused epilogue -> global)
+// Accumulators are double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs.
+//
+// Operand layouts: "K-major" = stored [rows][K] (K contiguous), "MN-major" = stored [K][rows].
+//   fprop  Y  = X  W^T   : A K-major,  B K-major   (W is [N,K] like nn.Linear.weight)
+//   dgrad  dX = dY W     : A K-major,  B MN-major  (W itself, no transposed copy)
+//   wgrad  dW = dY^T X   : A MN-major, B MN-major  (split-K, fp32 red.add into the grad buffer)
+#include "vitk_common.cuh"
+#include "vitk_internal.h"
+
+namespace {
+
+using namespace vitk;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+
+struct GemmParams {
+  int M, N, K;
+  int num_m_tiles, num_n_tiles, num_k_blocks, splits;
+  void* out;
+  long long ld_out;
+  void* aux;
+  long long ld_aux;
+  const float* bias;
+  const float* resid;
+  long long ld_resid;
+  const float* rowscale;
+  int rows_per_group;
+  const float* colscale;
+  const float* pos;
+  int tokens_per_img;
+  int prefix;
+};
+
+template <int BLOCK_N>
+struct TileCfg {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 192 ? 5 : 6);
+  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+// One 32-column chunk of one accumulator row.  `acc` holds the raw fp32 bits.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&acc)[32], int row,
+                                               int col0, float rs) {
+  // number of valid 8-column groups in this chunk (N % 8 == 0 is a host-side requirement)
+  const int ngroups = min(4, (p.N - col0) >> 3);
+  if (row >= p.M || ngroups <= 0) return;
+
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+
+  if constexpr (EPI != EPI_ATOMIC && EPI != EPI_DGELU) {
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g < ngroups) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 8 + 4));
+          v[g * 8 + 0] += b0.x; v[g * 8 + 1] += b0.y; v[g * 8 + 2] += b0.z; v[g * 8 + 3] += b0.w;
+          v[g * 8 + 4] += b1.x; v[g * 8 + 5] += b1.y; v[g * 8 + 6] += b1.z; v[g * 8 + 7] += b1.w;
+        }
+      }
+    }
+  }
+
+  if constexpr (EPI == EPI_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < ngroups) {
+        uint4 u;
+        u.x = pack_bf16x2(v[g * 8 + 0] * rs, v[g * 8 + 1] * rs);
+        u.y = pack_bf16x2(v[g * 8 + 2] * rs, v[g * 8 + 3] * rs);
+        u.z = pack_bf16x2(v[g * 8 + 4] * rs, v[g * 8 + 5] * rs);
+        u.w = pack_bf16x2(v[g * 8 + 6] * rs, v[g * 8 + 7] * rs);
+        *reinterpret_cast<uint4*>(o + g * 8) = u;
+      }
+    }
+  } else if constexpr (EPI == EPI_GELU) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + col0;
+    __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < ngroups) {
+        uint4 uh, ug;
+        float gl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gl[j] = gelu_fwd(v[g * 8 + j]);
+        uh.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+        uh.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+        uh.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+        uh.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+        ug.x = pack_bf16x2(gl[0], gl[1]);
+        ug.y = pack_bf16x2(gl[2], gl[3]);
+        ug.z = pack_bf16x2(gl[4], gl[5]);
+        ug.w = pack_bf16x2(gl[6], gl[7]);
+        *reinterpret_cast<uint4*>(a + g * 8) = uh;
+        *reinterpret_cast<uint4*>(o + g * 8) = ug;
+      }
+    }
+  } else if constexpr (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_PATCH) {
+    long long orow = row;
+    const float* addp = nullptr;
+    if constexpr (EPI == EPI_RESID) {
+      addp = p.resid + (long long)row * p.ld_resid + col0;
+    }
+    if constexpr (EPI == EPI_PATCH) {
+      // row = b * P + patch  ->  output token row b * (P + prefix) + prefix + patch
+      const int b = row / p.tokens_per_img;
+      const int t = row - b * p.tokens_per_img;
+      orow = (long long)b * (p.tokens_per_img + p.prefix) + p.prefix + t;
+      addp = p.pos + (long long)(p.prefix + t) * p.N + col0;
+    }
+    float* o = reinterpret_cast<float*>(p.out) + orow * p.ld_out + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < ngroups) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = g * 8 + h * 4;
+          float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if constexpr (EPI == EPI_RESID) {
+            float4 cs = make_float4(rs, rs, rs, rs);
+            if (p.colscale != nullptr) {
+              const float4 c = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j));
+              cs.x *= c.x; cs.y *= c.y; cs.z *= c.z; cs.w *= c.w;
+            }
+            const float4 a = *reinterpret_cast<const float4*>(addp + j);
+            r.x = fmaf(r.x, cs.x, a.x); r.y = fmaf(r.y, cs.y, a.y);
+            r.z = fmaf(r.z, cs.z, a.z); r.w = fmaf(r.w, cs.w, a.w);
+          }
+          if constexpr (EPI == EPI_PATCH) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(addp + j));
+            r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+          }
+          *reinterpret_cast<float4*>(o + j) = r;
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_DGELU) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + col0;
+    const __nv_bfloat16* hp =
+        reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < ngroups) {
+        const uint4 hu = *reinterpret_cast<const uint4*>(hp + g * 8);
+        const float2 h0 = unpack_bf16x2(hu.x), h1 = unpack_bf16x2(hu.y);
+        const float2 h2 = unpack_bf16x2(hu.z), h3 = unpack_bf16x2(hu.w);
+        uint4 u;
+        u.x = pack_bf16x2(v[g * 8 + 0] * gelu_bwd(h0.x), v[g * 8 + 1] * gelu_bwd(h0.y));
+        u.y = pack_bf16x2(v[g * 8 + 2] * gelu_bwd(h1.x), v[g * 8 + 3] * gelu_bwd(h1.y));
+        u.z = pack_bf16x2(v[g * 8 + 4] * gelu_bwd(h2.x), v[g * 8 + 5] * gelu_bwd(h2.y));
+        u.w = pack_bf16x2(v[g * 8 + 6] * gelu_bwd(h3.x), v[g * 8 + 7] * gelu_bwd(h3.y));
+        *reinterpret_cast<uint4*>(o + g * 8) = u;
+      }
+    }
+  } else if constexpr (EPI == EPI_ATOMIC) {
+    float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g < ngroups) {
+        red_add_v4(o + g * 8, v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+        red_add_v4(o + g * 8 + 4, v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+      }
+    }
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmParams p) {
+  using Cfg = TileCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_units = p.num_m_tiles * p.num_n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.splits;
+        const int tile = unit / p.splits;
+        const int n_blk = tile % p.num_n_tiles;
+        const int m_blk = tile / p.num_n_tiles;
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if constexpr (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d(sA + c * (BLOCK_K * 128), &tmA, &full_bar[stage],
+                          m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 64; ++c)
+              tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage],
+                          n_blk * BLOCK_N + c * 64, kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(BLOCK_M, BLOCK_N, 1 /*bf16*/, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.splits;
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: advance 16 elements = 32 B inside the 128 B swizzle row.
+            // MN-major: advance 16 k-rows = 2 swizzle atoms = 2048 B.
+            const uint64_t adesc = A_MN ? umma_desc_mnmajor(sA + k * 2048, BLOCK_K * 128)
+                                        : umma_desc_kmajor(sA + k * 32);
+            const uint64_t bdesc = B_MN ? umma_desc_mnmajor(sB + k * 2048, BLOCK_K * 128)
+                                        : umma_desc_kmajor(sB + k * 32);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;
+    const int quad = warp & 3;       // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;        // column half of the tile
+    constexpr int HALF_N = BLOCK_N / 2;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit / p.splits;
+      const int n_blk = tile % p.num_n_tiles;
+      const int m_blk = tile / p.num_n_tiles;
+      const int row = m_blk * BLOCK_M + quad * 32 + lane;
+      float rs = 1.0f;
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID) {
+        if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
+      }
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < HALF_N / 32; ++c) {
+        const int col_in_tile = half * HALF_N + c * 32;
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col_in_tile;
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr, acc);
+        tmem_ld_wait();
+        epilogue_chunk<EPI>(p, acc, row, n_blk * BLOCK_N + col_in_tile, rs);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+int launch_gemm(const vitk_gemm_args* a, int splits, cudaStream_t stream) {
+  using Cfg = TileCfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, BLOCK_K, BLOCK_M);
+  else       rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->M, a->K, a->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!B_MN) rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->K, a->N, a->ldb, BLOCK_K, BLOCK_N);
+  else       rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.num_m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
+  p.num_k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
+  p.splits = splits;
+  p.out = a->out; p.ld_out = a->ld_out;
+  p.aux = a->aux; p.ld_aux = a->ld_aux;
+  p.bias = a->bias;
+  p.resid = a->resid; p.ld_resid = a->ld_resid;
+  p.rowscale = a->rowscale; p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.colscale = a->colscale;
+  p.pos = a->pos; p.tokens_per_img = a->tokens_per_img > 0 ? a->tokens_per_img : 1;
+  p.prefix = a->prefix;
+
+  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  static bool attr_set = false;  // per-instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess)
+      return vitk_set_error(VITK_ERR_CUDA, "gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
+  const int grid = units < vitk_num_sms() ? units : vitk_num_sms();
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return vitk_check_launch("gemm");
+}
+
+int pick_splits(int tiles, int num_k_blocks, int sms) {
+  // choose the split-K factor that fills whole waves of `sms` CTAs; prefer fewer splits on ties
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 32 && s <= num_k_blocks; ++s) {
+    const int units = tiles * s;
+    const int waves = (units + sms - 1) / sms;
+    double eff = (double)units / ((double)waves * sms);
+    eff -= 0.004 * s;  // each split adds one more pass of red.add traffic over the tile
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+template <int BLOCK_N>
+int dispatch(const vitk_gemm_args* a, cudaStream_t stream) {
+  const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
+  const int tiles = ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + BLOCK_N - 1) / BLOCK_N);
+  const int nkb = (a->K + BLOCK_K - 1) / BLOCK_K;
+  if (a->epilogue == EPI_ATOMIC) {
+    int splits = a->splits > 0 ? a->splits : pick_splits(tiles, nkb, vitk_num_sms());
+    if (splits > nkb) splits = nkb;
+    if (amn && bmn) return launch_gemm<BLOCK_N, true, true, EPI_ATOMIC>(a, splits, stream);
+    if (!amn && !bmn) return launch_gemm<BLOCK_N, false, false, EPI_ATOMIC>(a, splits, stream);
+    return vitk_set_error(VITK_ERR_UNSUPPORTED, "gemm: EPI_ATOMIC needs both operands in the same major");
+  }
+  if (!amn && !bmn) {
+    switch (a->epilogue) {
+      case EPI_BF16:  return launch_gemm<BLOCK_N, false, false, EPI_BF16>(a, 1, stream);
+      case EPI_GELU:  return launch_gemm<BLOCK_N, false, false, EPI_GELU>(a, 1, stream);
+      case EPI_RESID: return launch_gemm<BLOCK_N, false, false, EPI_RESID>(a, 1, stream);
+      case EPI_F32:   return launch_gemm<BLOCK_N, false, false, EPI_F32>(a, 1, stream);
+      case EPI_PATCH: return launch_gemm<BLOCK_N, false, false, EPI_PATCH>(a, 1, stream);
+      case EPI_DGELU: return launch_gemm<BLOCK_N, false, false, EPI_DGELU>(a, 1, stream);
+    }
+  } else if (!amn && bmn) {
+    switch (a->epilogue) {
+      case EPI_BF16:  return launch_gemm<BLOCK_N, false, true, EPI_BF16>(a, 1, stream);
+      case EPI_DGELU: return launch_gemm<BLOCK_N, false, true, EPI_DGELU>(a, 1, stream);
+      case EPI_F32:   return launch_gemm<BLOCK_N, false, true, EPI_F32>(a, 1, stream);
+    }
+  }
+  return vitk_set_error(VITK_ERR_UNSUPPORTED, "gemm: unsupported layout/epilogue combination (a_mn=%d b_mn=%d epi=%d)",
+                        (int)amn, (int)bmn, a->epilogue);
+}
+
+}  // namespace
+
+extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VITK_REQUIRE(a != nullptr, VITK_ERR_SHAPE, "gemm: null args");
+  VITK_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, VITK_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
+  VITK_REQUIRE(a->N % 8 == 0, VITK_ERR_SHAPE, "gemm: N=%d must be a multiple of 8", a->N);
+  VITK_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, VITK_ERR_ALIGN, "gemm: lda/ldb must be multiples of 8 elements (16 B)");
+  VITK_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
+               VITK_ERR_ALIGN, "gemm: A/B must be 16-byte aligned");
+  VITK_REQUIRE(a->out != nullptr && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, VITK_ERR_ALIGN, "gemm: out must be 16-byte aligned");
+  VITK_REQUIRE(a->ld_out % 8 == 0, VITK_ERR_ALIGN, "gemm: ld_out must be a multiple of 8");
+  if (a->epilogue == EPI_GELU || a->epilogue == EPI_DGELU)
+    VITK_REQUIRE(a->aux != nullptr && a->ld_aux % 8 == 0, VITK_ERR_ALIGN, "gemm: aux pointer/ld required for GELU epilogues");
+  if (a->epilogue == EPI_RESID)
+    VITK_REQUIRE(a->resid != nullptr && a->ld_resid % 4 == 0, VITK_ERR_ALIGN, "gemm: resid pointer/ld required");
+  if (a->epilogue == EPI_PATCH)
+    VITK_REQUIRE(a->pos != nullptr && a->tokens_per_img > 0, VITK_ERR_SHAPE, "gemm: pos/tokens_per_img required");
+
+  int bn = a->block_n;
+  if (bn == 0) {
+    if (a->N % 256 == 0) bn = 256;
+    else if (a->N % 192 == 0) bn = 192;
+    else if (a->N % 128 == 0) bn = 128;
+    else bn = (a->N > 192) ? 256 : (a->N > 128 ? 192 : 128);
+  }
+  switch (bn) {
+    case 256: return dispatch<256>(a, stream);
+    case 192: return dispatch<192>(a, stream);
+    case 128: return dispatch<128>(a, stream);
+  }
+  return vitk_set_error(VITK_ERR_UNSUPPORTED, "gemm: block_n=%d not in {128,192,256}", bn);
+}

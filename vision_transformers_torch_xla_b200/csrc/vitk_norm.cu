@@ -1,0 +1,204 @@
+// vitk_norm.cu — LayerNorm forward / backward for the fp32 residual stream (HBM-bound kernels).
+//
+// Replaces aten::native_layer_norm(+_backward) at the reference's norm1/norm2/norm/fc_norm call
+// sites (/root/reference/models/vision_transformer.py:148,163,603,616; timm LayerNorm, eps 1e-6).
+// One warp owns one row: the row lives in registers (<= 1024 columns), statistics are two-pass in
+// fp32, all global accesses are 16-byte (fp32) / 8-byte (bf16) vectors and fully coalesced.
+//
+// Algorithmic bytes per row (D columns): fwd 4D (x) + 2D (y) + 8 (stats);
+// bwd 2D (dy) + 4D (x) + 4D (g_in) + 4D (g_out) + 2D (gb) + 8.
+#include "vitk_common.cuh"
+#include "vitk_internal.h"
+
+namespace {
+using namespace vitk;
+
+constexpr int MAXV = 8;  // float4 vectors per lane -> up to 1024 columns
+constexpr int LN_WARPS = 8;
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, long long ld_x, const float* __restrict__ gamma,
+              const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long ld_y,
+              float* __restrict__ mean, float* __restrict__ rstd, long long rows, int dim, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * LN_WARPS + warp;
+  if (row >= rows) return;
+  const int nvec = dim >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ld_x);
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i] = xr[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mu = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float a = v[i].x - mu, b = v[i].y - mu, cc = v[i].z - mu, d = v[i].w - mu;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / (float)dim + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  uint2* yr = reinterpret_cast<uint2*>(y + row * ld_y);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(g4 + c);
+      const float4 b = __ldg(b4 + c);
+      uint2 o;
+      o.x = pack_bf16x2(fmaf((v[i].x - mu) * rs, g.x, b.x), fmaf((v[i].y - mu) * rs, g.y, b.y));
+      o.y = pack_bf16x2(fmaf((v[i].z - mu) * rs, g.z, b.z), fmaf((v[i].w - mu) * rs, g.w, b.w));
+      yr[c] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ x,
+              long long ld_x, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const float* __restrict__ gamma, const float* __restrict__ g_in,
+              float* __restrict__ g_out, long long ld_g, __nv_bfloat16* __restrict__ gb_out,
+              const float* __restrict__ rowscale, int rows_per_group, float* __restrict__ dgamma,
+              float* __restrict__ dbeta, long long rows, int dim) {
+  extern __shared__ float red[];  // [2][dim]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = dim >> 2;
+  for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  float4 ag[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float4 gm[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+  }
+  const float inv_dim = 1.0f / (float)dim;
+
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows;
+       row += (long long)gridDim.x * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * ld_dy);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ld_x);
+    float4 xh[MAXV], dg[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const uint2 d = dyr[c];
+        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
+        const float4 xv = xr[c];
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        ab[i].x += d0.x; ab[i].y += d0.y; ab[i].z += d1.x; ab[i].w += d1.y;
+        ag[i].x = fmaf(d0.x, xh[i].x, ag[i].x); ag[i].y = fmaf(d0.y, xh[i].y, ag[i].y);
+        ag[i].z = fmaf(d1.x, xh[i].z, ag[i].z); ag[i].w = fmaf(d1.y, xh[i].w, ag[i].w);
+        dg[i] = make_float4(d0.x * gm[i].x, d0.y * gm[i].y, d1.x * gm[i].z, d1.y * gm[i].w);
+        s1 += (dg[i].x + dg[i].y) + (dg[i].z + dg[i].w);
+        s2 += (dg[i].x * xh[i].x + dg[i].y * xh[i].y) + (dg[i].z * xh[i].z + dg[i].w * xh[i].w);
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_dim;
+    const float c2 = warp_sum(s2) * inv_dim;
+    const float scale = (rowscale != nullptr) ? __ldg(rowscale + row / rows_per_group) : 1.0f;
+    float4* gor = reinterpret_cast<float4*>(g_out + row * ld_g);
+    const float4* gir = g_in ? reinterpret_cast<const float4*>(g_in + row * ld_g) : nullptr;
+    uint2* gbr = gb_out ? reinterpret_cast<uint2*>(gb_out + row * (long long)dim) : nullptr;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float4 r;
+        r.x = rs * (dg[i].x - c1 - xh[i].x * c2);
+        r.y = rs * (dg[i].y - c1 - xh[i].y * c2);
+        r.z = rs * (dg[i].z - c1 - xh[i].z * c2);
+        r.w = rs * (dg[i].w - c1 - xh[i].w * c2);
+        if (gir) {
+          const float4 gi = gir[c];
+          r.x += gi.x; r.y += gi.y; r.z += gi.z; r.w += gi.w;
+        }
+        gor[c] = r;
+        if (gbr) {
+          uint2 o;
+          o.x = pack_bf16x2(r.x * scale, r.y * scale);
+          o.y = pack_bf16x2(r.z * scale, r.w * scale);
+          gbr[c] = o;
+        }
+      }
+    }
+  }
+
+  // CTA-level reduction of the per-lane column partials, then one atomic per column per CTA.
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float* rg = red + c * 4;
+      float* rb = red + dim + c * 4;
+      atomicAdd(rg + 0, ag[i].x); atomicAdd(rg + 1, ag[i].y);
+      atomicAdd(rg + 2, ag[i].z); atomicAdd(rg + 3, ag[i].w);
+      atomicAdd(rb + 0, ab[i].x); atomicAdd(rb + 1, ab[i].y);
+      atomicAdd(rb + 2, ab[i].z); atomicAdd(rb + 3, ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, red[i]);
+    if (dbeta) atomicAdd(dbeta + i, red[dim + i]);
+  }
+}
+
+}  // namespace
+
+extern "C" int vitk_layernorm_fwd(const float* x, int64_t ld_x, const float* gamma, const float* beta,
+                                  void* y_bf16, int64_t ld_y, float* mean, float* rstd, int64_t rows,
+                                  int32_t dim, float eps, void* stream) {
+  VITK_REQUIRE(rows >= 0 && dim > 0, VITK_ERR_SHAPE, "layernorm_fwd: bad shape rows=%lld dim=%d", (long long)rows, dim);
+  VITK_REQUIRE(dim % 4 == 0 && dim <= MAXV * 128, VITK_ERR_SHAPE, "layernorm_fwd: dim=%d must be a multiple of 4 and <= %d", dim, MAXV * 128);
+  VITK_REQUIRE(ld_x % 4 == 0 && ld_y % 4 == 0, VITK_ERR_ALIGN, "layernorm_fwd: row pitches must be multiples of 4 elements");
+  VITK_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y_bf16 & 7) == 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0,
+               VITK_ERR_ALIGN, "layernorm_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return VITK_OK;
+  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  ln_fwd_kernel<<<grid, LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      x, ld_x, gamma, beta, (__nv_bfloat16*)y_bf16, ld_y, mean, rstd, rows, dim, eps);
+  return vitk_check_launch("layernorm_fwd");
+}
+
+extern "C" int vitk_layernorm_bwd(const void* dy_bf16, int64_t ld_dy, const float* x, int64_t ld_x,
+                                  const float* mean, const float* rstd, const float* gamma,
+                                  const float* g_in, float* g_out, int64_t ld_g, void* gb_out_bf16,
+                                  const float* rowscale, int32_t rows_per_group, float* dgamma,
+                                  float* dbeta, int64_t rows, int32_t dim, void* stream) {
+  VITK_REQUIRE(rows >= 0 && dim > 0, VITK_ERR_SHAPE, "layernorm_bwd: bad shape");
+  VITK_REQUIRE(dim % 4 == 0 && dim <= MAXV * 128, VITK_ERR_SHAPE, "layernorm_bwd: dim=%d must be a multiple of 4 and <= %d", dim, MAXV * 128);
+  VITK_REQUIRE(ld_x % 4 == 0 && ld_dy % 4 == 0 && ld_g % 4 == 0, VITK_ERR_ALIGN, "layernorm_bwd: row pitches must be multiples of 4 elements");
+  VITK_REQUIRE(mean && rstd && g_out, VITK_ERR_SHAPE, "layernorm_bwd: mean/rstd/g_out required");
+  if (rows == 0) return VITK_OK;
+  long long want = (rows + LN_WARPS - 1) / LN_WARPS;
+  const long long cap = (long long)vitk_num_sms() * 4;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  ln_bwd_kernel<<<grid, LN_WARPS * 32, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy_bf16, ld_dy, x, ld_x, mean, rstd, gamma, g_in, g_out, ld_g,
+      (__nv_bfloat16*)gb_out_bf16, rowscale, rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, dim);
+  return vitk_check_launch("layernorm_bwd");
+}
