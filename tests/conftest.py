@@ -25,7 +25,20 @@ def rel_err(a, b):
     """max |a-b| normalised by the RMS of the reference (north_star's per-tensor metric)."""
     import torch
 
-    a = a.double().flatten()
-    b = b.double().flatten()
+    a = a.detach().double().flatten()
+    b = b.detach().double().flatten()
     rms = b.pow(2).mean().sqrt().clamp_min(1e-30)
     return float((a - b).abs().max() / rms)
+
+
+def elem_err(a, b):
+    """max |a-b| / (|b| + rms(b)): elementwise-relative error with an RMS floor.
+
+    One bf16 rounding of the output costs at most 2^-8 = 3.9e-3 here regardless of how far into the
+    tail of the distribution the element sits, so bf16-output kernels are checked with this metric
+    (a stricter statement than the north-star's max/RMS <= 2e-2, which is asserted as well).
+    """
+    a = a.detach().double().flatten()
+    b = b.detach().double().flatten()
+    rms = b.pow(2).mean().sqrt().clamp_min(1e-30)
+    return float(((a - b).abs() / (b.abs() + rms)).max())

@@ -3,7 +3,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import rel_err
+from conftest import elem_err, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -23,7 +23,7 @@ def test_layernorm_fwd_bwd(cuda_device, rows, dim):
     gr = gamma.clone().requires_grad_(True)
     br = beta.clone().requires_grad_(True)
     ref = F.layer_norm(xr, (dim,), gr, br, 1e-6)
-    assert rel_err(y.float(), ref) < 8e-3
+    assert elem_err(y.float(), ref) < 6e-3
     assert rel_err(mean, x.mean(-1)) < 1e-5
     assert rel_err(rstd, (x.var(-1, unbiased=False) + 1e-6).rsqrt()) < 1e-5
 
@@ -39,7 +39,7 @@ def test_layernorm_fwd_bwd(cuda_device, rows, dim):
     ref.backward(dy.float())
     want = g_in + xr.grad
     assert rel_err(g_out, want) < 1e-4
-    assert rel_err(gb.float(), want * rs.repeat_interleave(group)[:rows, None]) < 8e-3
+    assert elem_err(gb.float(), want * rs.repeat_interleave(group)[:rows, None]) < 6e-3
     assert rel_err(dgamma, gr.grad) < 1e-4
     assert rel_err(dbeta, br.grad) < 1e-4
     # without g_in / gb / rowscale
@@ -59,7 +59,7 @@ def test_layernorm_strided_rows(cuda_device):
     mean = torch.empty(B, device=cuda_device)
     rstd = torch.empty(B, device=cuda_device)
     L.layernorm_fwd(x, gamma, beta, y, mean, rstd, B, D, 1e-6, ld_x=N * D)
-    assert rel_err(y.float(), F.layer_norm(x[:, 0], (D,), gamma, beta, 1e-6)) < 8e-3
+    assert elem_err(y.float(), F.layer_norm(x[:, 0], (D,), gamma, beta, 1e-6)) < 6e-3
 
 
 @pytest.mark.parametrize("B,S", [(2, 224), (1, 384)])
