@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Headline benchmark: ViT-B/16 224px bf16 training images/sec (BASELINE.json `metric`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--model NAME] [--batch B] [--impl ours|reference]
+
+One process per GPU (torchrun for N>1).  A step = forward + loss + backward + AdamW on one synthetic batch.
+Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the public
+API (`engine.train_one_epoch`) with pinned host batches (H2D copy + loss read-back inside the timed region).
+`roofline` times every tcgen05 GEMM launch of the timed region with CUDA events; `cpu_baseline` times the
+CPU oracle (restated reference eager path) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+#: algorithmic train GFLOP per image (SURVEY §8 header formula), used for the tensor-roofline fraction
+TRAIN_GFLOP_PER_IMG = {
+    "vit_tiny_patch16_224": 7.464, "vit_small_patch16_224": 27.478, "vit_base_patch16_224": 105.152,
+    "deit_base_distilled_patch16_224": 105.710, "vit_large_patch16_384": 1145.492, "my_vit_b": 105.152,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], hbm=d["hbm_gbs"], src="measured")
+    return dict(tf=1400.0, tf_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s, p in zip(sm, pw) if p > 300] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build(model_name, batch, device, drop_path):
+    from vision_transformers_torch_xla_b200 import optim_factory
+    from vision_transformers_torch_xla_b200.losses import SoftTargetCrossEntropy
+    from vision_transformers_torch_xla_b200.models import create_model
+
+    torch.manual_seed(0)
+    kw = dict(num_classes=1000, drop_path_rate=drop_path)
+    if not model_name.startswith("deit_"):
+        kw["global_pool"] = "avg"  # what reference main.py:643-649 passes
+    model = create_model(model_name, pretrained=False, **kw).to(device)
+    model.train()
+
+    class Args:
+        opt, lr, weight_decay, opt_eps, opt_betas = "adamw", 1e-3, 0.05, 1e-8, None
+
+    opt = optim_factory.create_optimizer(Args, model)
+    return model, opt, SoftTargetCrossEntropy()
+
+
+def synth_batch(batch, img, gen):
+    """ImageNet-shaped synthetic batch: N(0,1) images, mixup-style soft targets (smoothing 0.1)."""
+    from oracle.vit_oracle import mixup_soft_targets  # data recipe only (host side, shared with the CPU arm)
+
+    x = torch.randn(batch, 3, img, img, generator=gen)
+    y = mixup_soft_targets(torch.randint(0, 1000, (batch,), generator=gen), 1000, 0.7, 0.1)
+    return x, y
+
+
+def run_reference(args):
+    """CPU arm: the restated reference eager path (oracle) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import vit_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample_b = 8
+    torch.manual_seed(0)
+    kw = dict(num_classes=1000)
+    if not args.model.startswith("deit_"):
+        kw["global_pool"] = "avg"
+    model = O.create_model(args.model, **kw)
+    model.train()
+    opt = O.create_optimizer(model, lr=1e-3, weight_decay=0.05)
+    crit = O.SoftTargetCrossEntropy()
+    img = model.patch_embed.img_size[0]
+    gen = torch.Generator().manual_seed(0)
+    x, y = synth_batch(sample_b, img, gen)
+    for _ in range(args.warmup):
+        O.train_step(model, crit, opt, x, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.train_step(model, crit, opt, x, y)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = sample_b / dt
+    cores = torch.get_num_threads()
+    sample = f"{args.model} fwd+bwd+AdamW fp32 eager CPU, batch {sample_b} per step (bounded sample of batch {args.batch})"
+    print(json.dumps({
+        "impl": "reference", "metric": "train images/sec", "value": v, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} train step, {img}x{img}, batch {args.batch}/GPU", "sample_batch": sample_b},
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def cpu_baseline(model_name, batch):
+    from oracle import vit_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample_b = 8
+    kw = dict(num_classes=1000)
+    if not model_name.startswith("deit_"):
+        kw["global_pool"] = "avg"
+    torch.manual_seed(0)
+    model = O.create_model(model_name, **kw)
+    model.train()
+    opt = O.create_optimizer(model, lr=1e-3, weight_decay=0.05)
+    crit = O.SoftTargetCrossEntropy()
+    img = model.patch_embed.img_size[0]
+    x, y = synth_batch(sample_b, img, torch.Generator().manual_seed(0))
+    O.train_step(model, crit, opt, x, y)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 8 and n < 20):
+        O.train_step(model, crit, opt, x, y)
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": sample_b / dt, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{model_name} fwd+bwd+AdamW fp32 eager on CPU, batch {sample_b}, {n} timed steps "
+                      f"({dt * 1e3:.0f} ms/step)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--model", default="vit_base_patch16_224")
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--drop-path", type=float, default=0.1, help="reference launch value (run_train.sh:58)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print a per-kernel-family time table to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from vision_transformers_torch_xla_b200 import _lib as L
+    from vision_transformers_torch_xla_b200 import engine, utils
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = utils.init_distributed_mode(None, backend="nccl") if world > 1 else False
+    L.load()
+
+    model, opt, crit = build(args.model, args.batch, dev, args.drop_path)
+    train_model = model
+    if distributed:
+        from vision_transformers_torch_xla_b200.parallel import DataParallel
+
+        train_model = DataParallel(model, optimizer=opt)
+    img = model.patch_embed.img_size[0]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = [tuple(t.pin_memory() for t in synth_batch(args.batch, img, gen)) for _ in range(2)]
+    dev_batches = [(x.to(dev), y.to(dev)) for x, y in host]
+
+    def step(i):
+        x, y = dev_batches[i % 2]
+        loss = crit(train_model(x), y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return loss
+
+    def barrier():
+        if distributed:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+
+    # ---------------- timed region 1: inputs resident in HBM ----------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.gemm_timing_begin()
+    launches0 = L.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count - launches0
+    gemm_flops, gemm_ms, gemm_n = L.gemm_timing_end()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if distributed:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * args.batch * args.steps / (ms / 1e3)
+    final_loss = float(loss.item())
+
+    # ---------------- timed region 2: end to end through engine.train_one_epoch ----------------
+    e2e = None
+    if not args.no_e2e:
+        loader = [host[i % 2] for i in range(args.steps)]
+        barrier()
+        e0.record()
+        engine.train_one_epoch(train_model, crit, loader, opt, dev, 0, None, log_freq=1, update_freq=1, quiet=True)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if distributed:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        h2d = sum(v.numel() * v.element_size() for v in host[0])
+        e2e = {"value": world * args.batch * args.steps / (float(t.item()) / 1e3), "unit": "img/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "api": "engine.train_one_epoch(model, SoftTargetCrossEntropy, pinned-host loader, FusedAdamW, log_freq=1)"}
+
+    if args.breakdown and rank == 0:
+        L.breakdown_begin()
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        for fam, (n, tms) in sorted(L.breakdown_end().items(), key=lambda kv: -kv[1][1]):
+            print(f"  {fam:24s} {n / 3:7.1f} launches/step {tms / 3:9.3f} ms/step", file=sys.stderr)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    gflop_img = TRAIN_GFLOP_PER_IMG.get(args.model)
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    out = {
+        "metric": "train images/sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model} train step (fwd + SoftTargetCE + bwd + AdamW), {img}x{img}, batch "
+                               f"{args.batch}/GPU, drop_path {args.drop_path}", "global_batch": world * args.batch,
+                   "parallelism": f"dp{world}", "l2": "per-step working set (>10 GB of activations) >> 126 MB L2",
+                   "final_loss": final_loss},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "vitk gemm_kernel (tcgen05, all fprop/dgrad/wgrad launches)",
+                     "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
+                     "frac": (achieved_tf / pk["tf"]) if achieved_tf else None, "traffic": None,
+                     "launches_timed": gemm_n, "gemm_ms_per_step": gemm_ms / args.steps,
+                     "peak_source": f"bf16_tflops_sustained, {pk['src']}"},
+    }
+    if gflop_img:
+        step_tf = value / world * gflop_img * 1e9 / 1e12
+        out["model_flops"] = {"train_gflop_per_img": gflop_img, "achieved_tflops_per_gpu": step_tf,
+                              "frac_of_measured_sustained": step_tf / pk["tf"], "frac_of_nominal_2250": step_tf / 2250.0}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.model, args.batch)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

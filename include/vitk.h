@@ -152,6 +152,9 @@ int vitk_ce_fwd_bwd(const float* logits, const float* soft_targets, const int64_
 /* out_bf16[i] = in_f32[i] * scale_dev[0]   (applies the upstream grad of the loss, no host sync) */
 int vitk_scale_cast_bf16(const float* in, const float* scale_dev, void* out_bf16, int64_t n,
                          void* stream);
+/* out_bf16[i] = in_f32[i] * rowscale[i / elems_per_group]  (DropPath scale on a gradient stream; rowscale may be NULL) */
+int vitk_rowscale_cast_bf16(const float* in, const float* rowscale, int64_t elems_per_group,
+                            void* out_bf16, int64_t n, void* stream);
 /* out_bf16[i] = in_f32[i] */
 int vitk_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 

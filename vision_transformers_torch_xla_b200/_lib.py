@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "vitk_abi_version", "vitk_last_error", "vitk_arch", "vitk_gemm_bf16", "vitk_layernorm_fwd",
     "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_patchify", "vitk_prefix_rows",
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
-    "vitk_scale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
+    "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
 )
 
 
@@ -83,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.vitk_ce_fwd_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float, c_float, c_void_p,
                                     c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.vitk_scale_cast_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.vitk_rowscale_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]
     lib.vitk_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.vitk_adamw_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                     c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_float, c_float, c_float,
@@ -121,11 +122,63 @@ def _req(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
 # launch counter (bench.py reports how many of OUR kernels ran inside the timed region)
 # ------------------------------------------------------------------------------------------------
 launch_count = 0
+_gemm_timing = None   # list of (flops, start_event, end_event) while bench.py times the GEMM launches
+_breakdown = None     # family -> list of (start_event, end_event) for the per-family time table
 
 
 def _count(n: int = 1) -> None:
     global launch_count
     launch_count += n
+
+
+def gemm_timing_begin() -> None:
+    global _gemm_timing
+    _gemm_timing = []
+
+
+def gemm_timing_end():
+    """(total algorithmic flops, total device ms, launches) of the GEMM launches since gemm_timing_begin()."""
+    global _gemm_timing
+    rec, _gemm_timing = _gemm_timing or [], None
+    torch.cuda.synchronize()
+    return (sum(f for f, _, _ in rec), sum(a.elapsed_time(b) for _, a, b in rec), len(rec))
+
+
+def breakdown_begin() -> None:
+    global _breakdown
+    _breakdown = {}
+
+
+def breakdown_end():
+    global _breakdown
+    rec, _breakdown = _breakdown or {}, None
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in rec.items()}
+
+
+class _Timed:
+    """Brackets one launch with CUDA events on the launching stream when a measurement is active."""
+
+    __slots__ = ("family", "flops", "e0")
+
+    def __init__(self, family: str, flops: float = 0.0):
+        self.family, self.flops, self.e0 = family, flops, None
+
+    def __enter__(self):
+        if _breakdown is not None or (_gemm_timing is not None and self.flops):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            if _gemm_timing is not None and self.flops:
+                _gemm_timing.append((self.flops, self.e0, e1))
+            if _breakdown is not None:
+                _breakdown.setdefault(self.family, []).append((self.e0, e1))
+        return False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -158,7 +211,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     for t, nm in ((bias, "bias"), (resid, "resid"), (rowscale, "rowscale"), (colscale, "colscale"), (pos, "pos")):
         if t is not None:
             _req(t, torch.float32, f"gemm {nm}")
-    _check(load().vitk_gemm_bf16(ctypes.byref(args), _stream()), "vitk_gemm_bf16")
+    role = "wgrad" if epilogue == EPI_ATOMIC else ("dgrad" if b_mn else "fprop")
+    with _Timed(f"gemm.{role}.epi{epilogue} {M}x{N}x{K}", 2.0 * M * N * K):
+        _check(load().vitk_gemm_bf16(ctypes.byref(args), _stream()), "vitk_gemm_bf16")
     _count()
 
 
@@ -171,9 +226,10 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: t
     _req(x, torch.float32, "layernorm x")
     _req(y, torch.bfloat16, "layernorm y")
     _req(gamma, torch.float32, "layernorm gamma")
-    _check(load().vitk_layernorm_fwd(x.data_ptr(), ld_x or dim, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
-                                     ld_y or dim, _ptr(mean), _ptr(rstd), rows, dim, eps, _stream()),
-           "vitk_layernorm_fwd")
+    with _Timed("layernorm_fwd"):
+        _check(load().vitk_layernorm_fwd(x.data_ptr(), ld_x or dim, gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                         ld_y or dim, _ptr(mean), _ptr(rstd), rows, dim, eps, _stream()),
+               "vitk_layernorm_fwd")
     _count()
 
 
@@ -185,10 +241,11 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     _req(dy, torch.bfloat16, "layernorm_bwd dy")
     _req(x, torch.float32, "layernorm_bwd x")
     _req(g_out, torch.float32, "layernorm_bwd g_out")
-    _check(load().vitk_layernorm_bwd(dy.data_ptr(), ld_dy or dim, x.data_ptr(), ld_x or dim, mean.data_ptr(),
-                                     rstd.data_ptr(), gamma.data_ptr(), _ptr(g_in), g_out.data_ptr(), ld_g or dim,
-                                     _ptr(gb_out), _ptr(rowscale), rows_per_group, _ptr(dgamma), _ptr(dbeta), rows,
-                                     dim, _stream()), "vitk_layernorm_bwd")
+    with _Timed("layernorm_bwd"):
+        _check(load().vitk_layernorm_bwd(dy.data_ptr(), ld_dy or dim, x.data_ptr(), ld_x or dim, mean.data_ptr(),
+                                         rstd.data_ptr(), gamma.data_ptr(), _ptr(g_in), g_out.data_ptr(), ld_g or dim,
+                                         _ptr(gb_out), _ptr(rowscale), rows_per_group, _ptr(dgamma), _ptr(dbeta), rows,
+                                         dim, _stream()), "vitk_layernorm_bwd")
     _count()
 
 
@@ -200,8 +257,9 @@ def attn_fwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, B: int, N:
     _req(qkv, torch.bfloat16, "attn qkv")
     _req(out, torch.bfloat16, "attn out")
     _req(lse, torch.float32, "attn lse")
-    _check(load().vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd, scale, _stream()),
-           "vitk_attn_fwd")
+    with _Timed("attn_fwd"):
+        _check(load().vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd, scale, _stream()),
+               "vitk_attn_fwd")
     _count()
 
 
@@ -209,8 +267,9 @@ def attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torc
              B: int, N: int, H: int, hd: int, scale: float) -> None:
     for t, nm in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, f"attn_bwd {nm}")
-    _check(load().vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
+    with _Timed("attn_bwd"):
+        _check(load().vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                    B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
     _count()
 
 
@@ -221,41 +280,47 @@ def patchify(img: torch.Tensor, patches: torch.Tensor, ps: int) -> None:
     _req(img, torch.float32, "patchify img")
     _req(patches, torch.bfloat16, "patchify out")
     B, C, H, W = img.shape
-    _check(load().vitk_patchify(img.data_ptr(), patches.data_ptr(), B, C, H, W, ps, _stream()), "vitk_patchify")
+    with _Timed("patchify"):
+        _check(load().vitk_patchify(img.data_ptr(), patches.data_ptr(), B, C, H, W, ps, _stream()), "vitk_patchify")
     _count()
 
 
 def prefix_rows(x: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor, B: int, N: int, D: int, prefix: int) -> None:
     _req(x, torch.float32, "prefix_rows x")
-    _check(load().vitk_prefix_rows(x.data_ptr(), tok.data_ptr(), pos.data_ptr(), B, N, D, prefix, _stream()),
-           "vitk_prefix_rows")
+    with _Timed("prefix_rows"):
+        _check(load().vitk_prefix_rows(x.data_ptr(), tok.data_ptr(), pos.data_ptr(), B, N, D, prefix, _stream()),
+               "vitk_prefix_rows")
     _count()
 
 
 def embed_bwd(g: torch.Tensor, gp: Optional[torch.Tensor], dpos: Optional[torch.Tensor],
               dprefix: Optional[torch.Tensor], B: int, N: int, D: int, prefix: int) -> None:
     _req(g, torch.float32, "embed_bwd g")
-    _check(load().vitk_embed_bwd(g.data_ptr(), _ptr(gp), _ptr(dpos), _ptr(dprefix), B, N, D, prefix, _stream()),
-           "vitk_embed_bwd")
+    with _Timed("embed_bwd"):
+        _check(load().vitk_embed_bwd(g.data_ptr(), _ptr(gp), _ptr(dpos), _ptr(dprefix), B, N, D, prefix, _stream()),
+               "vitk_embed_bwd")
     _count()
 
 
 def pool_fwd(x: torch.Tensor, pooled: torch.Tensor, B: int, N: int, D: int, prefix: int, mode: int) -> None:
     _req(x, torch.float32, "pool x")
-    _check(load().vitk_pool_fwd(x.data_ptr(), pooled.data_ptr(), B, N, D, prefix, mode, _stream()), "vitk_pool_fwd")
+    with _Timed("pool_fwd"):
+        _check(load().vitk_pool_fwd(x.data_ptr(), pooled.data_ptr(), B, N, D, prefix, mode, _stream()), "vitk_pool_fwd")
     _count()
 
 
 def pool_bwd(dpooled: torch.Tensor, g: torch.Tensor, B: int, N: int, D: int, prefix: int, mode: int) -> None:
     _req(dpooled, torch.float32, "pool_bwd dpooled")
-    _check(load().vitk_pool_bwd(dpooled.data_ptr(), g.data_ptr(), B, N, D, prefix, mode, _stream()), "vitk_pool_bwd")
+    with _Timed("pool_bwd"):
+        _check(load().vitk_pool_bwd(dpooled.data_ptr(), g.data_ptr(), B, N, D, prefix, mode, _stream()), "vitk_pool_bwd")
     _count()
 
 
 def colsum_bf16(x: torch.Tensor, out: torch.Tensor, rows: int, cols: int, ld: Optional[int] = None) -> None:
     _req(x, torch.bfloat16, "colsum x")
     _req(out, torch.float32, "colsum out")
-    _check(load().vitk_colsum_bf16(x.data_ptr(), ld or cols, out.data_ptr(), rows, cols, _stream()), "vitk_colsum_bf16")
+    with _Timed("colsum_bf16"):
+        _check(load().vitk_colsum_bf16(x.data_ptr(), ld or cols, out.data_ptr(), rows, cols, _stream()), "vitk_colsum_bf16")
     _count()
 
 
@@ -273,17 +338,29 @@ def ce_fwd_bwd(logits: torch.Tensor, soft: Optional[torch.Tensor], labels: Optio
         _req(labels, torch.int64, "ce labels")
     if teacher is not None:
         _req(teacher, torch.float32, "ce teacher logits")
-    _check(load().vitk_ce_fwd_bwd(logits.data_ptr(), _ptr(soft), _ptr(labels), smoothing, _ptr(teacher), alpha, temp,
-                                  loss.data_ptr(), dlogits.data_ptr(), scratch.data_ptr(), B, C, _stream()),
-           "vitk_ce_fwd_bwd")
+    with _Timed("ce_fwd_bwd"):
+        _check(load().vitk_ce_fwd_bwd(logits.data_ptr(), _ptr(soft), _ptr(labels), smoothing, _ptr(teacher), alpha, temp,
+                                      loss.data_ptr(), dlogits.data_ptr(), scratch.data_ptr(), B, C, _stream()),
+               "vitk_ce_fwd_bwd")
     _count(2)
 
 
 def scale_cast_bf16(src: torch.Tensor, scale: Optional[torch.Tensor], dst: torch.Tensor) -> None:
     _req(src, torch.float32, "scale_cast src")
     _req(dst, torch.bfloat16, "scale_cast dst")
-    _check(load().vitk_scale_cast_bf16(src.data_ptr(), _ptr(scale), dst.data_ptr(), src.numel(), _stream()),
-           "vitk_scale_cast_bf16")
+    with _Timed("scale_cast_bf16"):
+        _check(load().vitk_scale_cast_bf16(src.data_ptr(), _ptr(scale), dst.data_ptr(), src.numel(), _stream()),
+               "vitk_scale_cast_bf16")
+    _count()
+
+
+def rowscale_cast_bf16(src: torch.Tensor, rowscale: Optional[torch.Tensor], elems_per_group: int,
+                       dst: torch.Tensor) -> None:
+    _req(src, torch.float32, "rowscale_cast src")
+    _req(dst, torch.bfloat16, "rowscale_cast dst")
+    with _Timed("rowscale_cast_bf16"):
+        _check(load().vitk_rowscale_cast_bf16(src.data_ptr(), _ptr(rowscale), elems_per_group, dst.data_ptr(),
+                                              src.numel(), _stream()), "vitk_rowscale_cast_bf16")
     _count()
 
 
@@ -304,13 +381,15 @@ def adamw_flat(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
     ng = len(lrs)
     lr_arr = (c_float * ng)(*[float(x) for x in lrs])
     wd_arr = (c_float * ng)(*[float(x) for x in wds])
-    _check(load().vitk_adamw_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), _ptr(ema), n,
-                                  _ptr(chunk_group), chunk, ng, lr_arr, wd_arr, beta1, beta2, eps, step, grad_scale,
-                                  ema_decay, int(zero_grad), _stream()), "vitk_adamw_flat")
+    with _Timed("adamw_flat"):
+        _check(load().vitk_adamw_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), _ptr(ema), n,
+                                      _ptr(chunk_group), chunk, ng, lr_arr, wd_arr, beta1, beta2, eps, step, grad_scale,
+                                      ema_decay, int(zero_grad), _stream()), "vitk_adamw_flat")
     _count()
 
 
 def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
     _req(x, torch.float32, "sumsq x")
-    _check(load().vitk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
+    with _Timed("sumsq"):
+        _check(load().vitk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
     _count()

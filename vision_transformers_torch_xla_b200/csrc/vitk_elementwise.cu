@@ -326,6 +326,19 @@ __global__ void scale_cast_kernel(const float* __restrict__ in, const float* __r
   }
 }
 
+// out_bf16[i] = in_f32[i] * rowscale[i / elems_per_group]   (DropPath scale applied to a gradient stream)
+__global__ void rowscale_cast_kernel(const float* __restrict__ in, const float* __restrict__ rowscale,
+                                     long long elems_per_group, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  const float s = rowscale ? __ldg(rowscale + i4 / elems_per_group) : 1.0f;
+  const float4 v = *reinterpret_cast<const float4*>(in + i4);
+  uint2 o;
+  o.x = pack_bf16x2(v.x * s, v.y * s);
+  o.y = pack_bf16x2(v.z * s, v.w * s);
+  *reinterpret_cast<uint2*>(out + i4) = o;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Flat AdamW
 // ------------------------------------------------------------------------------------------------
@@ -488,6 +501,18 @@ extern "C" int vitk_scale_cast_bf16(const float* in, const float* scale_dev, voi
   if (n == 0) return VITK_OK;
   scale_cast_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, scale_dev, (__nv_bfloat16*)out_bf16, n);
   return vitk_check_launch("scale_cast");
+}
+
+extern "C" int vitk_rowscale_cast_bf16(const float* in, const float* rowscale, int64_t elems_per_group, void* out_bf16,
+                                       int64_t n, void* stream) {
+  VITK_REQUIRE(n >= 0 && n % 4 == 0, VITK_ERR_SHAPE, "rowscale_cast: n must be a non-negative multiple of 4");
+  VITK_REQUIRE(rowscale == nullptr || (elems_per_group > 0 && elems_per_group % 4 == 0), VITK_ERR_SHAPE,
+               "rowscale_cast: elems_per_group must be a positive multiple of 4");
+  VITK_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, VITK_ERR_ALIGN, "rowscale_cast: unaligned");
+  if (n == 0) return VITK_OK;
+  rowscale_cast_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, rowscale, elems_per_group > 0 ? elems_per_group : 4,
+                                                                                 (__nv_bfloat16*)out_bf16, n);
+  return vitk_check_launch("rowscale_cast");
 }
 
 extern "C" int vitk_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {

@@ -1,0 +1,137 @@
+"""Training / evaluation loops with the call contract of /root/reference/engine.py.
+
+``train_one_epoch`` keeps the reference signature (engine.py:19-24) and the semantics of its eager branch
+(257-274): per-iteration LR/WD schedule write (98-103, including the ``is not None`` quirk that also
+rewrites the no-decay group — SURVEY Appendix D #1), ``loss / update_freq``, backward, step every
+``update_freq`` micro-batches, ``zero_grad``, optional EMA, meters, returned ``{meter: global_avg}``.
+What changes underneath: model, criterion and optimizer run on the vitk sm_100a kernels, gradient
+averaging across ranks is the bucketed NCCL all-reduce of ``parallel.DataParallel`` overlapped with
+backward, and the device is only synchronised when a metric is actually read (every ``log_freq`` steps)
+instead of after every step (engine.py:278-279, 290-299).
+"""
+from __future__ import annotations
+
+import time
+from typing import Iterable, Optional
+
+import torch
+
+from . import utils
+from .losses import CrossEntropyLoss
+
+
+def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loader: Iterable,
+                    optimizer: torch.optim.Optimizer, device: torch.device, epoch: int, loss_scaler=None,
+                    max_norm: float = 0, model_ema=None, mixup_fn=None, log_writer=None, wandb_logger=None,
+                    start_steps=None, lr_schedule_values=None, wd_schedule_values=None,
+                    num_training_steps_per_epoch=None, update_freq=None, use_amp=False, tpu: bool = False,
+                    log_freq: int = 10, wd_quirk: bool = True, quiet: bool = True):
+    if tpu:
+        raise NotImplementedError("tpu=True selects the reference's torch_xla branch; this build targets B200 (CUDA)")
+    if loss_scaler is not None and use_amp:
+        raise NotImplementedError("GradScaler/AMP is not used: the kernels compute in bf16 with fp32 accumulation "
+                                  "and fp32 master weights, no loss scaling is needed")
+    update_freq = update_freq or 1
+    start_steps = start_steps or 0
+    model.train(True)
+    metric_logger = utils.MetricLogger(delimiter="  ")
+    header = f"Epoch: [{epoch}]"
+    if log_writer is not None and num_training_steps_per_epoch is not None:
+        log_writer.set_step(epoch * num_training_steps_per_epoch * update_freq)
+    optimizer.zero_grad()
+    last_loss = None
+    for data_iter_step, (samples, targets) in enumerate(metric_logger.log_every(data_loader, 10, header, quiet=quiet)):
+        step = data_iter_step // update_freq
+        if num_training_steps_per_epoch is not None and step >= num_training_steps_per_epoch:
+            continue
+        it = start_steps + step
+        if (lr_schedule_values is not None or wd_schedule_values is not None) and data_iter_step % update_freq == 0:
+            for param_group in optimizer.param_groups:
+                if lr_schedule_values is not None:
+                    param_group["lr"] = lr_schedule_values[it] * param_group.get("lr_scale", 1.0)
+                if wd_schedule_values is not None:
+                    wd = param_group.get("weight_decay", None)
+                    if (wd is not None) if wd_quirk else (wd is not None and wd > 0):
+                        param_group["weight_decay"] = wd_schedule_values[it]
+        if mixup_fn is not None:
+            samples, targets = mixup_fn(samples, targets)
+        samples = samples.to(device, non_blocking=True)
+        targets = targets.to(device, non_blocking=True)
+
+        output = model(samples)
+        loss = criterion(output, targets)
+        loss = loss / update_freq
+        loss.backward()
+        if (data_iter_step + 1) % update_freq == 0:
+            if max_norm and max_norm > 0:
+                clip_grad_norm_(optimizer, max_norm)
+            optimizer.step()
+            optimizer.zero_grad()
+            if model_ema is not None:
+                model_ema.update(model)
+        last_loss = loss
+
+        if mixup_fn is None and not isinstance(output, tuple) and targets.dtype == torch.int64:
+            class_acc = (output.max(-1)[-1] == targets).float().mean()
+        else:
+            class_acc = None
+        lr = optimizer.param_groups[0]["lr"]
+        if data_iter_step % log_freq == 0 or data_iter_step < 5:
+            metric_logger.update(loss=loss.item())  # the only host<->device sync of the step
+            if class_acc is not None:
+                metric_logger.meters["class_acc"].update(class_acc.item(), n=samples.size(0))
+            metric_logger.update(lr=lr)
+            if log_writer is not None:
+                log_writer.update(loss=metric_logger.meters["loss"].value, lr=lr)
+            if wandb_logger is not None:
+                wandb_logger._wandb.log({"train/loss": metric_logger.meters["loss"].value, "train/learning_rate": lr,
+                                         "train/epoch": epoch, "train/step": start_steps + data_iter_step})
+    if last_loss is not None and "loss" not in metric_logger.meters:
+        metric_logger.update(loss=last_loss.item())
+    metric_logger.synchronize_between_processes()
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}
+
+
+def clip_grad_norm_(optimizer, max_norm: float) -> torch.Tensor:
+    """Global-L2 gradient clipping over the flat gradient buffer(s) (vitk_sumsq), no host sync: the clip
+    coefficient stays on the device and is folded into the gradients with one in-place multiply."""
+    from . import _lib as L
+    from .optim_factory import FusedAdamW
+
+    if not isinstance(optimizer, FusedAdamW):
+        raise NotImplementedError("clip_grad_norm_ is built for FusedAdamW")
+    if optimizer._plan is None:
+        optimizer._build_plan()
+    dev = optimizer._plan[0]["store"].device
+    total = torch.zeros(1, device=dev)
+    for e in optimizer._plan:
+        L.sumsq(e["store"].grad, total)
+    norm = total.sqrt() * optimizer.grad_scale
+    coef = (max_norm / (norm + 1e-6)).clamp(max=1.0)
+    for e in optimizer._plan:
+        e["store"].grad.mul_(coef)
+    return norm
+
+
+@torch.no_grad()
+def evaluate(data_loader, model, device, use_amp=False, tpu: bool = False):
+    """/root/reference/engine.py:339-430: CE loss + top-1/top-5 accuracy meters over the loader."""
+    if tpu:
+        raise NotImplementedError("tpu=True selects the reference's torch_xla branch; this build targets B200 (CUDA)")
+    criterion = CrossEntropyLoss()
+    metric_logger = utils.MetricLogger(delimiter="  ")
+    model.eval()
+    for images, target in data_loader:
+        images = images.to(device, non_blocking=True)
+        target = target.to(device, non_blocking=True)
+        output = model(images)
+        if isinstance(output, tuple):
+            output = output[0]
+        loss = criterion(output, target)
+        acc1, acc5 = utils.accuracy(output, target, topk=(1, 5))
+        batch_size = images.shape[0]
+        metric_logger.update(loss=loss.item())
+        metric_logger.meters["acc1"].update(acc1.item(), n=batch_size)
+        metric_logger.meters["acc5"].update(acc5.item(), n=batch_size)
+    metric_logger.synchronize_between_processes()
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}

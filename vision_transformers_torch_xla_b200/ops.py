@@ -1,0 +1,517 @@
+"""Fused autograd stages of the ViT hot path, each a fixed sequence of libvitk.so kernel launches.
+
+  EmbedFn  : PatchEmbed + cls/dist tokens + pos_embed          (reference vision_transformer.py:936-937)
+  BlockFn  : one pre-norm transformer Block                     (reference vision_transformer.py:175-178)
+  HeadFn   : pool -> (fc_)norm -> head Linear                   (reference vision_transformer.py:977-990)
+  CEFn     : fused soft-target / label-smoothing / KD loss      (reference main.py:926-968)
+
+Activations between stages are the fp32 residual stream ``[B, N, D]``; everything else is bf16 with
+fp32 accumulation.  Parameter gradients are accumulated by the kernels directly into the flat fp32
+gradient buffer of the ``ParamStore`` (``p.grad`` are views of it), so the autograd graph only carries
+the residual-stream gradient from stage to stage.  A side channel (``store.chain``) hands the bf16,
+DropPath-scaled copy of that gradient — produced for free by the LayerNorm-backward kernel — to the
+next stage's backward so that no separate cast pass is needed.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .store import ParamStore
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _require_f32_cuda(x: torch.Tensor, what: str) -> torch.Tensor:
+    if not x.is_cuda:
+        raise L.VitkError(f"{what}: expected a CUDA tensor (no CPU path)")
+    if x.dtype != torch.float32:
+        raise L.VitkError(f"{what}: expected float32, got {x.dtype}")
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def _bf16_grad(store: ParamStore, g: torch.Tensor, rowscale: Optional[torch.Tensor], elems_per_group: int) -> torch.Tensor:
+    """bf16(rowscale * g): taken from the side channel when the producer already made it."""
+    hit = store.chain.pop(g.data_ptr(), None)
+    if hit is not None and hit.numel() == g.numel():
+        return hit
+    out = _empty(g.shape, torch.bfloat16, g.device)
+    L.rowscale_cast_bf16(g, rowscale, elems_per_group, out)
+    return out
+
+
+# ================================================================================================
+# Patch embedding + prefix tokens + positional embedding
+# ================================================================================================
+class EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, anchor, model, store: ParamStore, save: bool):
+        pe = model.patch_embed
+        B, C, H, W = img.shape
+        ps = pe.patch_size[0]
+        D = model.embed_dim
+        P = pe.num_patches
+        prefix = model.num_prefix_tokens
+        N = P + prefix
+        K = C * ps * ps
+        dev = img.device
+        patches = _empty((B * P, K), torch.bfloat16, dev)
+        L.patchify(img, patches, ps)
+        x = _empty((B, N, D), torch.float32, dev)
+        w = store.shadow_of(pe.proj.weight).view(D, K)
+        pos = model.pos_embed.data.view(N, D)
+        L.gemm(patches, w, x, M=B * P, N=D, K=K, epilogue=L.EPI_PATCH,
+               bias=None if pe.proj.bias is None else pe.proj.bias.data, pos=pos, tokens_per_img=P, prefix=prefix)
+        xf = x.view(-1)
+        posf = pos.view(-1)
+        toks = [model.cls_token] + ([model.dist_token] if prefix == 2 else [])
+        for j, tok in enumerate(toks):
+            L.prefix_rows(xf[j * D:], tok.data.view(1, D), posf[j * D:], B, N, D, 1)
+        if save:
+            ctx.model, ctx.store = model, store
+            ctx.patches = patches
+            ctx.dims = (B, N, D, P, prefix, K)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        model, store = ctx.model, ctx.store
+        B, N, D, P, prefix, K = ctx.dims
+        pe = model.patch_embed
+        g = _require_f32_cuda(g, "EmbedFn.backward grad")
+        store.chain.pop(g.data_ptr(), None)
+        dev = g.device
+        gp = _empty((B * P, D), torch.bfloat16, dev)
+        dpre = torch.zeros((prefix, D), dtype=torch.float32, device=dev)
+        L.embed_bwd(g, gp, store.grad_of(model.pos_embed).view(N, D), dpre, B, N, D, prefix)
+        toks = [model.cls_token] + ([model.dist_token] if prefix == 2 else [])
+        for j, tok in enumerate(toks):
+            if tok.requires_grad:
+                store.grad_of(tok).view(D).add_(dpre[j])
+        L.gemm(gp, ctx.patches, store.grad_of(pe.proj.weight).view(D, K), M=D, N=K, K=B * P,
+               epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+        if pe.proj.bias is not None:
+            L.colsum_bf16(gp, store.grad_of(pe.proj.bias), B * P, D)
+        ctx.patches = None
+        store.fire_grad_ready("embed")
+        return None, None, None, None, None
+
+
+# ================================================================================================
+# Transformer block
+# ================================================================================================
+class BlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, blk, store: ParamStore, rs1, rs2, prev_rs, save: bool, tag: str):
+        x = _require_f32_cuda(x, "Block input")
+        B, N, D = x.shape
+        M = B * N
+        H = blk.attn.num_heads
+        hd = blk.attn.head_dim
+        F = blk.mlp.fc1.out_features
+        dev = x.device
+        eps = blk.norm1.eps
+        sh = store.shadow_of
+        bias = lambda lin: None if lin.bias is None else lin.bias.data  # noqa: E731
+
+        ln1 = _empty((M, D), torch.bfloat16, dev)
+        mean1, rstd1 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
+        L.layernorm_fwd(x, blk.norm1.weight.data, blk.norm1.bias.data, ln1, mean1, rstd1, M, D, eps)
+        qkv = _empty((M, 3 * D), torch.bfloat16, dev)
+        L.gemm(ln1, sh(blk.attn.qkv.weight), qkv, M=M, N=3 * D, K=D, epilogue=L.EPI_BF16, bias=bias(blk.attn.qkv))
+        att = _empty((M, D), torch.bfloat16, dev)
+        lse = _empty((B, H, N), torch.float32, dev)
+        L.attn_fwd(qkv, att, lse, B, N, H, hd, blk.attn.scale)
+        x_mid = _empty((B, N, D), torch.float32, dev)
+        L.gemm(att, sh(blk.attn.proj.weight), x_mid, M=M, N=D, K=D, epilogue=L.EPI_RESID, bias=bias(blk.attn.proj),
+               resid=x, rowscale=rs1, rows_per_group=N)
+        ln2 = _empty((M, D), torch.bfloat16, dev)
+        mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
+        L.layernorm_fwd(x_mid, blk.norm2.weight.data, blk.norm2.bias.data, ln2, mean2, rstd2, M, D, eps)
+        h = _empty((M, F), torch.bfloat16, dev)
+        act = _empty((M, F), torch.bfloat16, dev)
+        L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=L.EPI_GELU, bias=bias(blk.mlp.fc1), aux=h)
+        x_out = _empty((B, N, D), torch.float32, dev)
+        L.gemm(act, sh(blk.mlp.fc2.weight), x_out, M=M, N=D, K=F, epilogue=L.EPI_RESID, bias=bias(blk.mlp.fc2),
+               resid=x_mid, rowscale=rs2, rows_per_group=N)
+        if save:
+            ctx.blk, ctx.store, ctx.tag = blk, store, tag
+            ctx.dims = (B, N, D, H, hd, F)
+            ctx.rs = (rs1, rs2, prev_rs)
+            ctx.saved = (x, ln1, mean1, rstd1, qkv, att, lse, x_mid, ln2, mean2, rstd2, h, act)
+        return x_out
+
+    @staticmethod
+    def backward(ctx, g):
+        blk, store = ctx.blk, ctx.store
+        B, N, D, H, hd, F = ctx.dims
+        M = B * N
+        rs1, rs2, prev_rs = ctx.rs
+        x, ln1, mean1, rstd1, qkv, att, lse, x_mid, ln2, mean2, rstd2, h, act = ctx.saved
+        ctx.saved = None
+        g = _require_f32_cuda(g, "Block.backward grad")
+        dev = g.device
+        sh, gr = store.shadow_of, store.grad_of
+        wgrad = lambda dy, xin, w, m, n: L.gemm(dy, xin, gr(w), M=m, N=n, K=M, epilogue=L.EPI_ATOMIC,  # noqa: E731
+                                                a_mn=True, b_mn=True)
+
+        # ---------------- MLP branch: x_out = x_mid + rs2 * (fc2(gelu(fc1(ln2))) ) ----------------
+        gb2 = _bf16_grad(store, g, rs2, N * D).view(M, D)
+        wgrad(gb2, act, blk.mlp.fc2.weight, D, F)
+        if blk.mlp.fc2.bias is not None:
+            L.colsum_bf16(gb2, gr(blk.mlp.fc2.bias), M, D)
+        dh = act  # reuse: gelu output is dead after the fc2 wgrad above
+        L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
+        del gb2, h
+        wgrad(dh, ln2, blk.mlp.fc1.weight, F, D)
+        if blk.mlp.fc1.bias is not None:
+            L.colsum_bf16(dh, gr(blk.mlp.fc1.bias), M, F)
+        dln2 = ln2  # reuse: ln2 output is dead after the fc1 wgrad above
+        L.gemm(dh, sh(blk.mlp.fc1.weight), dln2, M=M, N=D, K=F, epilogue=L.EPI_BF16, b_mn=True)
+        del dh, act
+        g_mid = _empty((B, N, D), torch.float32, dev)
+        gb1 = _empty((M, D), torch.bfloat16, dev)
+        L.layernorm_bwd(dln2, x_mid, mean2, rstd2, blk.norm2.weight.data, g, g_mid, gb1, rs1, N,
+                        gr(blk.norm2.weight), gr(blk.norm2.bias), M, D)
+        del dln2, ln2, x_mid, g
+
+        # ---------------- attention branch: x_mid = x + rs1 * proj(attn(qkv(ln1))) ----------------
+        wgrad(gb1, att, blk.attn.proj.weight, D, D)
+        if blk.attn.proj.bias is not None:
+            L.colsum_bf16(gb1, gr(blk.attn.proj.bias), M, D)
+        datt = _empty((M, D), torch.bfloat16, dev)
+        L.gemm(gb1, sh(blk.attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
+        dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
+        L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, blk.attn.scale)
+        del gb1, datt, att, qkv, lse
+        wgrad(dqkv, ln1, blk.attn.qkv.weight, 3 * D, D)
+        if blk.attn.qkv.bias is not None:
+            L.colsum_bf16(dqkv, gr(blk.attn.qkv.bias), M, 3 * D)
+        dln1 = ln1
+        L.gemm(dqkv, sh(blk.attn.qkv.weight), dln1, M=M, N=D, K=3 * D, epilogue=L.EPI_BF16, b_mn=True)
+        del dqkv
+        g_in = _empty((B, N, D), torch.float32, dev)
+        gb_prev = _empty((B, N, D), torch.bfloat16, dev)
+        L.layernorm_bwd(dln1, x, mean1, rstd1, blk.norm1.weight.data, g_mid, g_in, gb_prev, prev_rs, N,
+                        gr(blk.norm1.weight), gr(blk.norm1.bias), M, D)
+        store.chain[g_in.data_ptr()] = gb_prev
+        store.fire_grad_ready(ctx.tag)
+        return g_in, None, None, None, None, None, None, None, None
+
+
+# ================================================================================================
+# Pool + norm + classifier head(s)
+# ================================================================================================
+class HeadFn(torch.autograd.Function):
+    """avg:   logits = head(fc_norm(mean_{t>=prefix} x))
+       token: logits = head(norm(x)[:, 0])   (+ head_dist(norm(x)[:, 1]) for the distilled model)"""
+
+    @staticmethod
+    def forward(ctx, x, anchor, model, store: ParamStore, prev_rs, save: bool):
+        x = _require_f32_cuda(x, "head input")
+        B, N, D = x.shape
+        dev = x.device
+        prefix = model.num_prefix_tokens
+        avg = model.global_pool == "avg"
+        norm = model.fc_norm if avg else model.norm
+        has_norm = isinstance(norm, torch.nn.LayerNorm)
+        heads = [model.head] + ([model.head_dist] if getattr(model, "head_dist", None) is not None else [])
+        C = heads[0].out_features
+        sh = store.shadow_of
+        feats, stats, outs = [], [], []
+        pooled = None
+        if avg:
+            pooled = _empty((B, D), torch.float32, dev)
+            L.pool_fwd(x, pooled, B, N, D, prefix, 0)
+        for j, head in enumerate(heads):
+            src, ld = (pooled, D) if avg else (x.view(-1)[j * D:], N * D)
+            f = _empty((B, D), torch.bfloat16, dev)
+            mean, rstd = _empty((B,), torch.float32, dev), _empty((B,), torch.float32, dev)
+            if has_norm:
+                L.layernorm_fwd(src, norm.weight.data, norm.bias.data, f, mean, rstd, B, D, norm.eps, ld_x=ld)
+            else:
+                L.cast_bf16(src.view(B, -1)[:, :D].contiguous(), f)
+            logits = _empty((B, C), torch.float32, dev)
+            L.gemm(f, sh(head.weight), logits, M=B, N=C, K=D, epilogue=L.EPI_F32,
+                   bias=None if head.bias is None else head.bias.data)
+            feats.append(f)
+            stats.append((mean, rstd))
+            outs.append(logits)
+        if save:
+            ctx.model, ctx.store = model, store
+            ctx.dims = (B, N, D, C, prefix, avg, has_norm)
+            ctx.saved = (x, pooled, feats, stats)
+            ctx.prev_rs = prev_rs
+        return tuple(outs) if len(outs) > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, *dlogits):
+        model, store = ctx.model, ctx.store
+        B, N, D, C, prefix, avg, has_norm = ctx.dims
+        x, pooled, feats, stats = ctx.saved
+        ctx.saved = None
+        dev = x.device
+        gr, sh = store.grad_of, store.shadow_of
+        norm = model.fc_norm if avg else model.norm
+        heads = [model.head] + ([model.head_dist] if getattr(model, "head_dist", None) is not None else [])
+        g = _empty((B, N, D), torch.float32, dev) if avg else torch.zeros((B, N, D), dtype=torch.float32, device=dev)
+        for j, head in enumerate(heads):
+            dl = dlogits[j]
+            if dl is None:
+                continue
+            dl = _require_f32_cuda(dl, "dlogits")
+            dlb = _empty((B, C), torch.bfloat16, dev)
+            L.cast_bf16(dl, dlb)
+            L.gemm(dlb, feats[j], gr(head.weight), M=C, N=D, K=B, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+            if head.bias is not None:
+                L.colsum_bf16(dlb, gr(head.bias), B, C)
+            df = _empty((B, D), torch.bfloat16, dev)
+            L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=C, epilogue=L.EPI_BF16, b_mn=True)
+            mean, rstd = stats[j]
+            if not has_norm:
+                raise NotImplementedError("final_norm=False head backward is not built")
+            if avg:
+                dpooled = _empty((B, D), torch.float32, dev)
+                L.layernorm_bwd(df, pooled, mean, rstd, norm.weight.data, None, dpooled, None, None, 1,
+                                gr(norm.weight), gr(norm.bias), B, D)
+                L.pool_bwd(dpooled, g, B, N, D, prefix, 0)
+            else:
+                L.layernorm_bwd(df, x.view(-1)[j * D:], mean, rstd, norm.weight.data, None, g.view(-1)[j * D:], None,
+                                None, 1, gr(norm.weight), gr(norm.bias), B, D, ld_x=N * D, ld_g=N * D)
+        store.fire_grad_ready("head")
+        gb = _empty((B, N, D), torch.bfloat16, dev)
+        L.rowscale_cast_bf16(g, ctx.prev_rs, N * D, gb)
+        store.chain[g.data_ptr()] = gb
+        return g, None, None, None, None, None
+
+
+# ================================================================================================
+# Loss
+# ================================================================================================
+class CEFn(torch.autograd.Function):
+    """loss = (1-alpha) * CE(logits, targets) + alpha * T^2 * KL(softmax(teacher/T) || softmax(logits/T))."""
+
+    @staticmethod
+    def forward(ctx, logits, soft, labels, smoothing: float, teacher, alpha: float, temp: float):
+        logits = _require_f32_cuda(logits, "loss logits")
+        B, C = logits.shape
+        dev = logits.device
+        if soft is not None:
+            soft = _require_f32_cuda(soft.to(torch.float32), "soft targets")
+        if labels is not None:
+            labels = labels.to(torch.int64).contiguous()
+        if teacher is not None:
+            teacher = _require_f32_cuda(teacher.to(torch.float32), "teacher logits")
+        loss = _empty((1,), torch.float32, dev)
+        dl = _empty((B, C), torch.float32, dev)
+        scratch = _empty((B,), torch.float32, dev)
+        L.ce_fwd_bwd(logits, soft, labels, smoothing, teacher, alpha, temp, loss, dl, scratch)
+        ctx.save_for_backward(dl)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        (dl,) = ctx.saved_tensors
+        return dl * gout, None, None, None, None, None, None
+
+
+def drop_path_scale(drop_prob: float, training: bool, B: int, device) -> Optional[torch.Tensor]:
+    """Per-sample DropPath factor mask/keep_prob, same RNG recipe as timm's drop_path."""
+    if drop_prob == 0.0 or not training:
+        return None
+    keep = 1.0 - drop_prob
+    rs = torch.empty(B, dtype=torch.float32, device=device).bernoulli_(keep)
+    if keep > 0.0:
+        rs.div_(keep)
+    return rs
+
+
+# ================================================================================================
+# Stand-alone leaf modules (the reference's own plug points: models/_compat.py:27-172).  The fused
+# stages above bypass these inside a VisionTransformer; they exist so that Attention / Mlp /
+# LayerNorm / PatchEmbed / nn.Linear-shaped heads are usable on their own, on the same kernels.
+# All take and return fp32 (bf16 operands, fp32 accumulation inside).
+# ================================================================================================
+def _to_bf16(x: torch.Tensor) -> torch.Tensor:
+    out = _empty(x.shape, torch.bfloat16, x.device)
+    L.cast_bf16(x, out)
+    return out
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, mod, store: ParamStore, save: bool):
+        x = _require_f32_cuda(x, "LayerNorm input")
+        D = x.shape[-1]
+        rows = x.numel() // D
+        y = _empty(x.shape, torch.bfloat16, x.device)
+        mean, rstd = _empty((rows,), torch.float32, x.device), _empty((rows,), torch.float32, x.device)
+        L.layernorm_fwd(x, mod.weight.data, mod.bias.data, y, mean, rstd, rows, D, mod.eps)
+        if save:
+            ctx.mod, ctx.store, ctx.saved = mod, store, (x, mean, rstd)
+        return y.float()
+
+    @staticmethod
+    def backward(ctx, dy):
+        mod, store = ctx.mod, ctx.store
+        x, mean, rstd = ctx.saved
+        ctx.saved = None
+        D = x.shape[-1]
+        rows = x.numel() // D
+        dyb = _to_bf16(_require_f32_cuda(dy, "LayerNorm grad"))
+        g = _empty(x.shape, torch.float32, x.device)
+        L.layernorm_bwd(dyb, x, mean, rstd, mod.weight.data, None, g, None, None, 1, store.grad_of(mod.weight),
+                        store.grad_of(mod.bias), rows, D)
+        return g, None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, lin, store: ParamStore, save: bool):
+        x = _require_f32_cuda(x, "Linear input")
+        K, N = lin.in_features, lin.out_features
+        M = x.numel() // K
+        xb = _to_bf16(x)
+        out = _empty(x.shape[:-1] + (N,), torch.float32, x.device)
+        L.gemm(xb, store.shadow_of(lin.weight), out, M=M, N=N, K=K, epilogue=L.EPI_F32,
+               bias=None if lin.bias is None else lin.bias.data)
+        if save:
+            ctx.lin, ctx.store, ctx.xb, ctx.shape = lin, store, xb, x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        lin, store, xb = ctx.lin, ctx.store, ctx.xb
+        ctx.xb = None
+        K, N = lin.in_features, lin.out_features
+        M = xb.numel() // K
+        dyb = _to_bf16(_require_f32_cuda(dy, "Linear grad"))
+        L.gemm(dyb, xb, store.grad_of(lin.weight), M=N, N=K, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+        if lin.bias is not None:
+            L.colsum_bf16(dyb, store.grad_of(lin.bias), M, N)
+        dx = _empty(ctx.shape, torch.float32, dy.device)
+        L.gemm(dyb, store.shadow_of(lin.weight), dx, M=M, N=K, K=N, epilogue=L.EPI_F32, b_mn=True)
+        return dx, None, None, None, None
+
+
+class AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, attn, store: ParamStore, save: bool):
+        x = _require_f32_cuda(x, "Attention input")
+        B, N, D = x.shape
+        M, H, hd = B * N, attn.num_heads, attn.head_dim
+        dev = x.device
+        sh = store.shadow_of
+        xb = _to_bf16(x).view(M, D)
+        qkv = _empty((M, 3 * D), torch.bfloat16, dev)
+        L.gemm(xb, sh(attn.qkv.weight), qkv, M=M, N=3 * D, K=D, epilogue=L.EPI_BF16,
+               bias=None if attn.qkv.bias is None else attn.qkv.bias.data)
+        att = _empty((M, D), torch.bfloat16, dev)
+        lse = _empty((B, H, N), torch.float32, dev)
+        L.attn_fwd(qkv, att, lse, B, N, H, hd, attn.scale)
+        out = _empty((B, N, D), torch.float32, dev)
+        L.gemm(att, sh(attn.proj.weight), out, M=M, N=D, K=D, epilogue=L.EPI_F32,
+               bias=None if attn.proj.bias is None else attn.proj.bias.data)
+        if save:
+            ctx.attn, ctx.store, ctx.saved, ctx.dims = attn, store, (xb, qkv, att, lse), (B, N, D, H, hd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        attn, store = ctx.attn, ctx.store
+        xb, qkv, att, lse = ctx.saved
+        ctx.saved = None
+        B, N, D, H, hd = ctx.dims
+        M = B * N
+        dev = dy.device
+        sh, gr = store.shadow_of, store.grad_of
+        dyb = _to_bf16(_require_f32_cuda(dy, "Attention grad")).view(M, D)
+        L.gemm(dyb, att, gr(attn.proj.weight), M=D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+        if attn.proj.bias is not None:
+            L.colsum_bf16(dyb, gr(attn.proj.bias), M, D)
+        datt = _empty((M, D), torch.bfloat16, dev)
+        L.gemm(dyb, sh(attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
+        dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
+        L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, attn.scale)
+        L.gemm(dqkv, xb, gr(attn.qkv.weight), M=3 * D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+        if attn.qkv.bias is not None:
+            L.colsum_bf16(dqkv, gr(attn.qkv.bias), M, 3 * D)
+        dx = _empty((B, N, D), torch.float32, dev)
+        L.gemm(dqkv, sh(attn.qkv.weight), dx, M=M, N=D, K=3 * D, epilogue=L.EPI_F32, b_mn=True)
+        return dx, None, None, None, None
+
+
+class MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, anchor, mlp, store: ParamStore, save: bool):
+        x = _require_f32_cuda(x, "Mlp input")
+        D, F, O = mlp.fc1.in_features, mlp.fc1.out_features, mlp.fc2.out_features
+        M = x.numel() // D
+        dev = x.device
+        sh = store.shadow_of
+        xb = _to_bf16(x).view(M, D)
+        h = _empty((M, F), torch.bfloat16, dev)
+        act = _empty((M, F), torch.bfloat16, dev)
+        L.gemm(xb, sh(mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=L.EPI_GELU,
+               bias=None if mlp.fc1.bias is None else mlp.fc1.bias.data, aux=h)
+        out = _empty(x.shape[:-1] + (O,), torch.float32, dev)
+        L.gemm(act, sh(mlp.fc2.weight), out, M=M, N=O, K=F, epilogue=L.EPI_F32,
+               bias=None if mlp.fc2.bias is None else mlp.fc2.bias.data)
+        if save:
+            ctx.mlp, ctx.store, ctx.saved, ctx.shape = mlp, store, (xb, h, act), x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        mlp, store = ctx.mlp, ctx.store
+        xb, h, act = ctx.saved
+        ctx.saved = None
+        D, F, O = mlp.fc1.in_features, mlp.fc1.out_features, mlp.fc2.out_features
+        M = xb.numel() // D
+        sh, gr = store.shadow_of, store.grad_of
+        dyb = _to_bf16(_require_f32_cuda(dy, "Mlp grad")).view(M, O)
+        L.gemm(dyb, act, gr(mlp.fc2.weight), M=O, N=F, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+        if mlp.fc2.bias is not None:
+            L.colsum_bf16(dyb, gr(mlp.fc2.bias), M, O)
+        dh = act
+        L.gemm(dyb, sh(mlp.fc2.weight), dh, M=M, N=F, K=O, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
+        L.gemm(dh, xb, gr(mlp.fc1.weight), M=F, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+        if mlp.fc1.bias is not None:
+            L.colsum_bf16(dh, gr(mlp.fc1.bias), M, F)
+        dx = _empty(ctx.shape, torch.float32, dy.device)
+        L.gemm(dh, sh(mlp.fc1.weight), dx, M=M, N=D, K=F, epilogue=L.EPI_F32, b_mn=True)
+        return dx, None, None, None, None
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, anchor, pe, store: ParamStore, save: bool):
+        img = _require_f32_cuda(img, "PatchEmbed input")
+        B, C, H, W = img.shape
+        ps = pe.patch_size[0]
+        D = pe.proj.out_channels
+        P, K = pe.num_patches, C * ps * ps
+        patches = _empty((B * P, K), torch.bfloat16, img.device)
+        L.patchify(img, patches, ps)
+        out = _empty((B, P, D), torch.float32, img.device)
+        L.gemm(patches, store.shadow_of(pe.proj.weight).view(D, K), out, M=B * P, N=D, K=K, epilogue=L.EPI_F32,
+               bias=None if pe.proj.bias is None else pe.proj.bias.data)
+        if save:
+            ctx.pe, ctx.store, ctx.patches, ctx.dims = pe, store, patches, (B, P, D, K)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        pe, store, patches = ctx.pe, ctx.store, ctx.patches
+        ctx.patches = None
+        B, P, D, K = ctx.dims
+        dyb = _to_bf16(_require_f32_cuda(dy, "PatchEmbed grad")).view(B * P, D)
+        L.gemm(dyb, patches, store.grad_of(pe.proj.weight).view(D, K), M=D, N=K, K=B * P, epilogue=L.EPI_ATOMIC,
+               a_mn=True, b_mn=True)
+        if pe.proj.bias is not None:
+            L.colsum_bf16(dyb, store.grad_of(pe.proj.bias), B * P, D)
+        return None, None, None, None, None

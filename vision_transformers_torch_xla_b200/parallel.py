@@ -1,0 +1,107 @@
+"""Single-box data parallelism: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+
+Replaces the reference's gradient sync — ``xm.optimizer_step(optimizer, barrier=True)``
+(/root/reference/engine.py:185) on TPU and ``DistributedDataParallel`` (/root/reference/main.py:855-857)
+on GPU — with a bucketed all-reduce driven by the fused backward stages:
+
+  * the flat fp32 gradient buffer is laid out in forward order, so the parameters of ``blocks.i`` (one
+    ~28 MB range for ViT-B) are one bucket;
+  * as soon as a stage's backward has enqueued its last wgrad kernel it fires ``grad_ready``; the bucket is
+    all-reduced (SUM) asynchronously on NCCL's stream while the next block's backward runs;
+  * the optimizer's pre-step hook waits for the outstanding buckets; the 1/world_size of the mean is folded
+    into the AdamW kernel (``grad_scale``), so averaging costs no extra pass over the gradients.
+
+With ``update_freq > 1`` buckets are only reduced on the micro-batch that precedes ``optimizer.step()``
+(``no_sync()`` context, like DDP).
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import List
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .store import get_store
+
+
+class DataParallel(nn.Module):
+    def __init__(self, module: nn.Module, optimizer=None, broadcast: bool = True, bucket_tags=None):
+        super().__init__()
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("DataParallel needs an initialised torch.distributed process group")
+        self.module = module
+        self.world_size = dist.get_world_size()
+        self.require_sync = True
+        self._works: List = []
+        self._pending = False
+        st = get_store(self._find_root(module))
+        self.store = st
+        if broadcast:
+            dist.broadcast(st.flat, src=0)  # identical replicas (DDP does the same at construction)
+            st._sig = None
+        self._ranges = self._make_buckets(st)
+        st.grad_ready_hooks.append(self._on_grad_ready)
+        if optimizer is not None:
+            self.attach_optimizer(optimizer)
+
+    @staticmethod
+    def _find_root(module: nn.Module) -> nn.Module:
+        """The trainable vitk model inside ``module`` (e.g. the student of a StudentWithDistillation wrapper)."""
+        from .models.vision_transformer import VisionTransformer
+
+        roots = [m for m in module.modules()
+                 if isinstance(m, VisionTransformer) and any(p.requires_grad for p in m.parameters())]
+        if len(roots) > 1:
+            raise NotImplementedError("DataParallel: more than one trainable vitk model inside the wrapped module")
+        return roots[0] if roots else module
+
+    @staticmethod
+    def _make_buckets(st):
+        """tag -> [start, end) of the flat buffer: one bucket per block, one for the head, one for the embed."""
+        ranges = {}
+        names = st.names
+        blocks = sorted({n.split(".")[1] for n in names if n.startswith("blocks.")}, key=int)
+        first_block = min((st.name_offsets[n][0] for n in names if n.startswith("blocks.")), default=st.total)
+        last_block_end = 0
+        for b in blocks:
+            lo, hi = st.range_of_prefix(f"blocks.{b}.")
+            ranges[f"blocks.{b}."] = (lo, hi)
+            last_block_end = max(last_block_end, hi)
+        ranges["embed"] = (0, first_block)
+        ranges["head"] = (last_block_end, st.total)
+        return ranges
+
+    def attach_optimizer(self, optimizer):
+        optimizer.grad_scale = 1.0 / self.world_size
+        optimizer.pre_step_hooks.append(lambda opt: self.finish_gradient_sync())
+
+    def _on_grad_ready(self, tag: str):
+        if not self.require_sync or self.world_size == 1:
+            return
+        rng = self._ranges.get(tag)
+        if rng is None or rng[1] <= rng[0]:
+            return
+        lo, hi = rng
+        self._works.append(dist.all_reduce(self.store.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish_gradient_sync(self):
+        for w in self._works:
+            w.wait()
+        self._works.clear()
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        old = self.require_sync
+        self.require_sync = False
+        try:
+            yield
+        finally:
+            self.require_sync = old
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def no_weight_decay(self):
+        return self.module.no_weight_decay() if hasattr(self.module, "no_weight_decay") else set()
