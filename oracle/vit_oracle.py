@@ -212,7 +212,7 @@ class VisionTransformer(nn.Module):
         embed_len = num_patches + self.num_prefix_tokens
         self.pos_embed = nn.Parameter(torch.randn(1, embed_len, embed_dim) * 0.02)  # :566-570
         self.pos_drop = nn.Dropout(p=pos_drop_rate)
-        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]  # :581
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth, device="cpu")]  # :581
         self.blocks = nn.Sequential(*[
             Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, proj_bias=proj_bias,
                   init_values=init_values, proj_drop=proj_drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i],

@@ -42,3 +42,16 @@ def elem_err(a, b):
     b = b.detach().double().flatten()
     rms = b.pow(2).mean().sqrt().clamp_min(1e-30)
     return float(((a - b).abs() / (b.abs() + rms)).max())
+
+
+def rms_err(a, b):
+    """rms(a-b) / rms(b): the typical (not worst-case) relative error of a tensor."""
+    a = a.detach().double().flatten()
+    b = b.detach().double().flatten()
+    return float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30))
+
+
+def cos_sim(a, b):
+    a = a.detach().double().flatten()
+    b = b.detach().double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))

@@ -47,6 +47,7 @@ struct GemmParams {
   const float* pos;
   int tokens_per_img;
   int prefix;
+  int ragged;  // EPI_F32 only: N % 8 != 0 or unaligned rows -> scalar epilogue stores
 };
 
 template <int BLOCK_N>
@@ -69,7 +70,17 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&acc)[32], int row,
                                                int col0, float rs) {
-  // number of valid 8-column groups in this chunk (N % 8 == 0 is a host-side requirement)
+  if constexpr (EPI == EPI_F32) {
+    if (p.ragged) {  // e.g. a 10- or 100-class head: rows are not 16-byte aligned, store scalars
+      if (row >= p.M) return;
+      float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) o[j] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+      return;
+    }
+  }
+  // number of valid 8-column groups in this chunk (N % 8 == 0 is a host-side requirement otherwise)
   const int ngroups = min(4, (p.N - col0) >> 3);
   if (row >= p.M || ngroups <= 0) return;
 
@@ -386,6 +397,7 @@ int launch_gemm(const vitk_gemm_args* a, int splits, cudaStream_t stream) {
   p.colscale = a->colscale;
   p.pos = a->pos; p.tokens_per_img = a->tokens_per_img > 0 ? a->tokens_per_img : 1;
   p.prefix = a->prefix;
+  p.ragged = (EPI == EPI_F32 && (a->N % 8 != 0 || a->ld_out % 4 != 0)) ? 1 : 0;
 
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI>;
   static bool attr_set = false;  // per-instantiation
@@ -454,12 +466,13 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   VITK_REQUIRE(a != nullptr, VITK_ERR_SHAPE, "gemm: null args");
   VITK_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, VITK_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
-  VITK_REQUIRE(a->N % 8 == 0, VITK_ERR_SHAPE, "gemm: N=%d must be a multiple of 8", a->N);
+  VITK_REQUIRE(a->N % 8 == 0 || a->epilogue == EPI_F32, VITK_ERR_SHAPE,
+               "gemm: N=%d must be a multiple of 8 (only the fp32 epilogue handles ragged N)", a->N);
   VITK_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, VITK_ERR_ALIGN, "gemm: lda/ldb must be multiples of 8 elements (16 B)");
   VITK_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
                VITK_ERR_ALIGN, "gemm: A/B must be 16-byte aligned");
   VITK_REQUIRE(a->out != nullptr && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, VITK_ERR_ALIGN, "gemm: out must be 16-byte aligned");
-  VITK_REQUIRE(a->ld_out % 8 == 0, VITK_ERR_ALIGN, "gemm: ld_out must be a multiple of 8");
+  VITK_REQUIRE(a->ld_out % 8 == 0 || a->epilogue == EPI_F32, VITK_ERR_ALIGN, "gemm: ld_out must be a multiple of 8");
   if (a->epilogue == EPI_GELU || a->epilogue == EPI_DGELU)
     VITK_REQUIRE(a->aux != nullptr && a->ld_aux % 8 == 0, VITK_ERR_ALIGN, "gemm: aux pointer/ld required for GELU epilogues");
   if (a->epilogue == EPI_RESID)

@@ -319,7 +319,7 @@ class VisionTransformer(nn.Module):
         self.patch_drop = nn.Identity()
         self.norm_pre = nn.Identity()
 
-        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth)]  # stochastic depth decay rule
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth, device="cpu")]  # stochastic depth decay rule
         self.blocks = nn.Sequential(*[
             block_fn(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, proj_bias=proj_bias,
                      init_values=init_values, drop_path=dpr[i], norm_layer=norm_layer, act_layer=act_layer,

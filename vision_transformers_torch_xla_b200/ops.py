@@ -264,13 +264,20 @@ class HeadFn(torch.autograd.Function):
             if dl is None:
                 continue
             dl = _require_f32_cuda(dl, "dlogits")
-            dlb = _empty((B, C), torch.bfloat16, dev)
+            Cp = (C + 7) // 8 * 8  # TMA needs 16-byte row pitches: pad ragged class counts with zero columns
+            if Cp != C:
+                pad = torch.zeros((B, Cp), dtype=torch.float32, device=dev)
+                pad[:, :C] = dl
+                dl = pad
+            dlb = _empty((B, Cp), torch.bfloat16, dev)
             L.cast_bf16(dl, dlb)
-            L.gemm(dlb, feats[j], gr(head.weight), M=C, N=D, K=B, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
+            L.gemm(dlb, feats[j], gr(head.weight), M=C, N=D, K=B, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, lda=Cp)
             if head.bias is not None:
-                L.colsum_bf16(dlb, gr(head.bias), B, C)
+                # padded columns land in the 64-element alignment gap that follows the bias in the flat buffer
+                L.colsum_bf16(dlb, gr(head.bias), B, Cp)
             df = _empty((B, D), torch.bfloat16, dev)
-            L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=C, epilogue=L.EPI_BF16, b_mn=True)
+            # K = Cp: the extra weight rows read past head.weight are multiplied by the zero pad columns
+            L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=Cp, epilogue=L.EPI_BF16, b_mn=True)
             mean, rstd = stats[j]
             if not has_norm:
                 raise NotImplementedError("final_norm=False head backward is not built")
