@@ -48,10 +48,10 @@ const char* vitk_arch(void);
  * ---------------------------------------------------------------------------------------------- */
 enum vitk_epilogue {
   VITK_EPI_BF16 = 0,   /* out_bf16[m,n]  = rowscale[m/g] * (acc + bias[n])                         */
-  VITK_EPI_GELU = 1,   /* h = acc + bias; aux_bf16 = h; out_bf16 = gelu_erf(h)        (mlp.fc1)    */
+  VITK_EPI_GELU = 1,   /* h = acc + bias; out_bf16 = gelu_erf(h); aux_bf16 = gelu_erf'(h)   (mlp.fc1) */
   VITK_EPI_RESID = 2,  /* out_f32 = resid_f32 + rowscale[m/g]*colscale[n]*(acc+bias)  (proj, fc2)  */
   VITK_EPI_F32 = 3,    /* out_f32 = acc + bias                                        (head)       */
-  VITK_EPI_DGELU = 4,  /* out_bf16 = acc * gelu'(aux_bf16[m,n])                       (fc2 dgrad)  */
+  VITK_EPI_DGELU = 4,  /* out_bf16 = rowscale[m/g] * acc * aux_bf16[m,n], aux = gelu'(h) (fc2 dgrad)  */
   VITK_EPI_ATOMIC = 5, /* out_f32 += acc   via red.global.add (split-K)               (wgrad)      */
   VITK_EPI_PATCH = 6   /* out_f32[b*(P+prefix)+prefix+t, n] = acc + bias[n] + pos[prefix+t, n]     */
 };
@@ -65,7 +65,7 @@ typedef struct vitk_gemm_args {
   int32_t epilogue;    /* enum vitk_epilogue                                                       */
   void* out;           /* bf16 or f32 depending on the epilogue                                    */
   int64_t ld_out;
-  void* aux;           /* GELU: pre-activation output (bf16); DGELU: pre-activation input (bf16)   */
+  void* aux;           /* GELU: activation-derivative output (bf16); DGELU: the same buffer as input */
   int64_t ld_aux;
   const float* bias;   /* [N] or NULL                                                              */
   const float* resid;  /* RESID: fp32 [M, N] residual stream input                                 */

@@ -66,9 +66,11 @@ def test_fprop_gelu_dual(cuda_device):
     out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
     aux = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
     L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_GELU, bias=bias, aux=aux)
-    h = a.float() @ w.float().t() + bias
-    assert elem_err(aux.float(), h) < BF16_TOL
-    assert elem_err(out.float(), torch.nn.functional.gelu(h)) < BF16_TOL
+    h = (a.float() @ w.float().t() + bias).requires_grad_(True)
+    g = torch.nn.functional.gelu(h)
+    g.sum().backward()
+    assert elem_err(out.float(), g) < BF16_TOL
+    assert elem_err(aux.float(), h.grad) < BF16_TOL  # aux = gelu'(h)
 
 
 def test_fprop_resid_scales(cuda_device):
@@ -120,12 +122,10 @@ def test_dgrad_dgelu(cuda_device):
     M, N, K = 394, 3072, 768
     dy = _mk((M, K), cuda_device, seed=1).bfloat16()
     w = _mk((K, N), cuda_device, 0.05, seed=2).bfloat16()
-    h = _mk((M, N), cuda_device, seed=3).bfloat16()
+    d = _mk((M, N), cuda_device, seed=3).bfloat16()  # gelu'(h) as written by the forward EPI_GELU epilogue
     out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
-    L.gemm(dy, w, out, M=M, N=N, K=K, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
-    hf = h.float().requires_grad_(True)
-    torch.nn.functional.gelu(hf).backward(dy.float() @ w.float())
-    assert elem_err(out.float(), hf.grad) < BF16_TOL
+    L.gemm(dy, w, out, M=M, N=N, K=K, epilogue=L.EPI_DGELU, b_mn=True, aux=d)
+    assert elem_err(out.float(), (dy.float() @ w.float()) * d.float()) < BF16_TOL
 
 
 @pytest.mark.parametrize("M,N,K,splits", [(128, 256, 64, 1), (768, 768, 1576, 0), (2304, 768, 4000, 0), (1000, 768, 256, 0),

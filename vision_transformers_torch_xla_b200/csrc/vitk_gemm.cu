@@ -7,11 +7,13 @@
 // /root/reference/models/vision_transformer.py:149-159), fc1/fc2 (Mlp, :164-171), head (:618)
 // and their dgrad/wgrad in autograd.
 //
-// Roles (384 threads, 1 CTA / SM, persistent over output tiles):
-//   warp 0      TMA producer   (global -> 128B-swizzled smem ring, mbarrier tx-count)
-//   warp 1      MMA issuer     (one elected thread: tcgen05.mma 128 x BLOCK_N x 16, cta_group::1)
-//   warp 2      TMEM allocator
-//   warps 4-11  epilogue       (tcgen05.ld accumulator -> fused epilogue -> global)
+// Roles (1 CTA / SM, persistent over output tiles):
+//   warp 0        TMA producer   (global -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1        MMA issuer     (one elected thread: tcgen05.mma 128 x BLOCK_N x 16, cta_group::1)
+//   warp 2        TMEM allocator
+//   warps 4..     epilogue       (tcgen05.ld accumulator -> fused epilogue -> global); 8 warps, or 16
+//                                for the GELU epilogue whose per-element math would otherwise outlast
+//                                the K=768 main loop
 // Accumulators are double-buffered in TMEM so tile i's epilogue overlaps tile i+1's MMAs.
 //
 // Operand layouts: "K-major" = stored [rows][K] (K contiguous), "MN-major" = stored [K][rows].
@@ -28,8 +30,6 @@ using namespace vitk;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 
 struct GemmParams {
   int M, N, K;
@@ -66,152 +66,130 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-// One 32-column chunk of one accumulator row.  `acc` holds the raw fp32 bits.
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&acc)[32], int row,
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]);
+  u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
+
+// One W-column chunk (W = 16 or 32) of one accumulator row.  `acc` holds the raw fp32 bits.
+template <int EPI, int W>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&acc)[W], int row,
                                                int col0, float rs) {
+  constexpr int G = W / 8;
   if constexpr (EPI == EPI_F32) {
     if (p.ragged) {  // e.g. a 10- or 100-class head: rows are not 16-byte aligned, store scalars
       if (row >= p.M) return;
       float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + col0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < W; ++j)
         if (col0 + j < p.N) o[j] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
       return;
     }
   }
   // number of valid 8-column groups in this chunk (N % 8 == 0 is a host-side requirement otherwise)
-  const int ngroups = min(4, (p.N - col0) >> 3);
+  const int ngroups = min(G, (p.N - col0) >> 3);
   if (row >= p.M || ngroups <= 0) return;
 
-  float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  for (int g = 0; g < G; ++g) {
+    if (g >= ngroups) break;
+    const int c = col0 + g * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
 
-  if constexpr (EPI != EPI_ATOMIC && EPI != EPI_DGELU) {
-    if (p.bias != nullptr) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (g < ngroups) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 8));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 8 + 4));
-          v[g * 8 + 0] += b0.x; v[g * 8 + 1] += b0.y; v[g * 8 + 2] += b0.z; v[g * 8 + 3] += b0.w;
-          v[g * 8 + 4] += b1.x; v[g * 8 + 5] += b1.y; v[g * 8 + 6] += b1.z; v[g * 8 + 7] += b1.w;
-        }
+    if constexpr (EPI != EPI_ATOMIC && EPI != EPI_DGELU) {
+      if (p.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
     }
-  }
 
-  if constexpr (EPI == EPI_BF16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + col0;
+    if constexpr (EPI == EPI_BF16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + c;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < ngroups) {
-        uint4 u;
-        u.x = pack_bf16x2(v[g * 8 + 0] * rs, v[g * 8 + 1] * rs);
-        u.y = pack_bf16x2(v[g * 8 + 2] * rs, v[g * 8 + 3] * rs);
-        u.z = pack_bf16x2(v[g * 8 + 4] * rs, v[g * 8 + 5] * rs);
-        u.w = pack_bf16x2(v[g * 8 + 6] * rs, v[g * 8 + 7] * rs);
-        *reinterpret_cast<uint4*>(o + g * 8) = u;
+      for (int j = 0; j < 8; ++j) v[j] *= rs;
+      *reinterpret_cast<uint4*>(o) = pack8(v);
+    } else if constexpr (EPI == EPI_GELU) {
+      // out = gelu(h), aux = gelu'(h): the backward epilogue (EPI_DGELU) is then a plain multiply
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + c;
+      __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + c;
+      float gl[8], gd[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float pdf;
+        const float cdf = gelu_cdf(v[j], &pdf);
+        gl[j] = v[j] * cdf;
+        gd[j] = fmaf(v[j], pdf, cdf);
       }
-    }
-  } else if constexpr (EPI == EPI_GELU) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + col0;
-    __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < ngroups) {
-        uint4 uh, ug;
-        float gl[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gl[j] = gelu_fwd(v[g * 8 + j]);
-        uh.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-        uh.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-        uh.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-        uh.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-        ug.x = pack_bf16x2(gl[0], gl[1]);
-        ug.y = pack_bf16x2(gl[2], gl[3]);
-        ug.z = pack_bf16x2(gl[4], gl[5]);
-        ug.w = pack_bf16x2(gl[6], gl[7]);
-        *reinterpret_cast<uint4*>(a + g * 8) = uh;
-        *reinterpret_cast<uint4*>(o + g * 8) = ug;
+      *reinterpret_cast<uint4*>(a) = pack8(gd);
+      *reinterpret_cast<uint4*>(o) = pack8(gl);
+    } else if constexpr (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_PATCH) {
+      long long orow = row;
+      const float* addp = nullptr;
+      if constexpr (EPI == EPI_RESID) addp = p.resid + (long long)row * p.ld_resid + c;
+      if constexpr (EPI == EPI_PATCH) {
+        // row = b * P + patch  ->  output token row b * (P + prefix) + prefix + patch
+        const int b = row / p.tokens_per_img;
+        const int t = row - b * p.tokens_per_img;
+        orow = (long long)b * (p.tokens_per_img + p.prefix) + p.prefix + t;
+        addp = p.pos + (long long)(p.prefix + t) * p.N + c;
       }
-    }
-  } else if constexpr (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_PATCH) {
-    long long orow = row;
-    const float* addp = nullptr;
-    if constexpr (EPI == EPI_RESID) {
-      addp = p.resid + (long long)row * p.ld_resid + col0;
-    }
-    if constexpr (EPI == EPI_PATCH) {
-      // row = b * P + patch  ->  output token row b * (P + prefix) + prefix + patch
-      const int b = row / p.tokens_per_img;
-      const int t = row - b * p.tokens_per_img;
-      orow = (long long)b * (p.tokens_per_img + p.prefix) + p.prefix + t;
-      addp = p.pos + (long long)(p.prefix + t) * p.N + col0;
-    }
-    float* o = reinterpret_cast<float*>(p.out) + orow * p.ld_out + col0;
+      float* o = reinterpret_cast<float*>(p.out) + orow * p.ld_out + c;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < ngroups) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = g * 8 + h * 4;
-          float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if constexpr (EPI == EPI_RESID) {
-            float4 cs = make_float4(rs, rs, rs, rs);
-            if (p.colscale != nullptr) {
-              const float4 c = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + j));
-              cs.x *= c.x; cs.y *= c.y; cs.z *= c.z; cs.w *= c.w;
-            }
-            const float4 a = *reinterpret_cast<const float4*>(addp + j);
-            r.x = fmaf(r.x, cs.x, a.x); r.y = fmaf(r.y, cs.y, a.y);
-            r.z = fmaf(r.z, cs.z, a.z); r.w = fmaf(r.w, cs.w, a.w);
+      for (int h = 0; h < 2; ++h) {
+        const int j = h * 4;
+        float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if constexpr (EPI == EPI_RESID) {
+          float4 cs = make_float4(rs, rs, rs, rs);
+          if (p.colscale != nullptr) {
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(p.colscale + c + j));
+            cs.x *= cc.x; cs.y *= cc.y; cs.z *= cc.z; cs.w *= cc.w;
           }
-          if constexpr (EPI == EPI_PATCH) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(addp + j));
-            r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
-          }
-          *reinterpret_cast<float4*>(o + j) = r;
+          const float4 a = *reinterpret_cast<const float4*>(addp + j);
+          r.x = fmaf(r.x, cs.x, a.x); r.y = fmaf(r.y, cs.y, a.y);
+          r.z = fmaf(r.z, cs.z, a.z); r.w = fmaf(r.w, cs.w, a.w);
         }
+        if constexpr (EPI == EPI_PATCH) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(addp + j));
+          r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+        }
+        *reinterpret_cast<float4*>(o + j) = r;
       }
-    }
-  } else if constexpr (EPI == EPI_DGELU) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + col0;
-    const __nv_bfloat16* hp =
-        reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + col0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < ngroups) {
-        const uint4 hu = *reinterpret_cast<const uint4*>(hp + g * 8);
-        const float2 h0 = unpack_bf16x2(hu.x), h1 = unpack_bf16x2(hu.y);
-        const float2 h2 = unpack_bf16x2(hu.z), h3 = unpack_bf16x2(hu.w);
-        uint4 u;
-        u.x = pack_bf16x2(v[g * 8 + 0] * gelu_bwd(h0.x), v[g * 8 + 1] * gelu_bwd(h0.y));
-        u.y = pack_bf16x2(v[g * 8 + 2] * gelu_bwd(h1.x), v[g * 8 + 3] * gelu_bwd(h1.y));
-        u.z = pack_bf16x2(v[g * 8 + 4] * gelu_bwd(h2.x), v[g * 8 + 5] * gelu_bwd(h2.y));
-        u.w = pack_bf16x2(v[g * 8 + 6] * gelu_bwd(h3.x), v[g * 8 + 7] * gelu_bwd(h3.y));
-        *reinterpret_cast<uint4*>(o + g * 8) = u;
-      }
-    }
-  } else if constexpr (EPI == EPI_ATOMIC) {
-    float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + col0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g < ngroups) {
-        red_add_v4(o + g * 8, v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
-        red_add_v4(o + g * 8 + 4, v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
-      }
+    } else if constexpr (EPI == EPI_DGELU) {
+      // out = acc * aux, aux = gelu'(h) written by the forward EPI_GELU epilogue
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ld_out + c;
+      const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + c;
+      const uint4 du = *reinterpret_cast<const uint4*>(dp);
+      const float2 d0 = unpack_bf16x2(du.x), d1 = unpack_bf16x2(du.y);
+      const float2 d2 = unpack_bf16x2(du.z), d3 = unpack_bf16x2(du.w);
+      v[0] *= d0.x * rs; v[1] *= d0.y * rs; v[2] *= d1.x * rs; v[3] *= d1.y * rs;
+      v[4] *= d2.x * rs; v[5] *= d2.y * rs; v[6] *= d3.x * rs; v[7] *= d3.y * rs;
+      *reinterpret_cast<uint4*>(o) = pack8(v);
+    } else if constexpr (EPI == EPI_ATOMIC) {
+      float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ld_out + c;
+      red_add_v4(o, v[0], v[1], v[2], v[3]);
+      red_add_v4(o + 4, v[4], v[5], v[6], v[7]);
     }
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int EW>
+__global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmParams p) {
   using Cfg = TileCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int PARTS = EW / 4;             // column partitions of the tile among epilogue warps
+  constexpr int PART_N = BLOCK_N / PARTS;   // columns per epilogue warp
+  constexpr int W = (PART_N % 32 == 0) ? 32 : 16;
+  static_assert(BLOCK_N % PARTS == 0 && PART_N % W == 0, "tile does not split evenly among epilogue warps");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -236,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], EW);
     }
     fence_mbar_init();
   }
@@ -330,8 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ epilogue ------------------------------
     const int ew = warp - 4;
     const int quad = warp & 3;       // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;        // column half of the tile
-    constexpr int HALF_N = BLOCK_N / 2;
+    const int part = ew >> 2;        // column partition of the tile
     int as = 0;
     uint32_t aphase = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
@@ -340,20 +317,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_blk = tile / p.num_n_tiles;
       const int row = m_blk * BLOCK_M + quad * 32 + lane;
       float rs = 1.0f;
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID) {
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID || EPI == EPI_DGELU) {
         if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
       }
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < HALF_N / 32; ++c) {
-        const int col_in_tile = half * HALF_N + c * 32;
+      for (int c = 0; c < PART_N / W; ++c) {
+        const int col_in_tile = part * PART_N + c * W;
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col_in_tile;
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr, acc);
+        uint32_t acc[W];
+        if constexpr (W == 32) tmem_ld_32x32(taddr, acc);
+        else tmem_ld_32x16(taddr, acc);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, acc, row, n_blk * BLOCK_N + col_in_tile, rs);
+        epilogue_chunk<EPI, W>(p, acc, row, n_blk * BLOCK_N + col_in_tile, rs);
       }
       tc_fence_before();
       __syncwarp();
@@ -374,6 +352,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 int launch_gemm(const vitk_gemm_args* a, int splits, cudaStream_t stream) {
   using Cfg = TileCfg<BLOCK_N>;
+  // 16 epilogue warps where the epilogue is heavy: GELU does ~20 instructions per element, RESID / DGELU read a
+  // second operand from global memory (more warps = more loads in flight to hide that latency at K = 768)
+  constexpr int EW = (EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_DGELU) ? 16 : 8;
   CUtensorMap tmA, tmB;
   int rc;
   if (!A_MN) rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, BLOCK_K, BLOCK_M);
@@ -399,7 +380,7 @@ int launch_gemm(const vitk_gemm_args* a, int splits, cudaStream_t stream) {
   p.prefix = a->prefix;
   p.ragged = (EPI == EPI_F32 && (a->N % 8 != 0 || a->ld_out % 4 != 0)) ? 1 : 0;
 
-  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI, EW>;
   static bool attr_set = false;  // per-instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -410,7 +391,7 @@ int launch_gemm(const vitk_gemm_args* a, int splits, cudaStream_t stream) {
   }
   const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int grid = units < vitk_num_sms() ? units : vitk_num_sms();
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, 128 + EW * 32, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   return vitk_check_launch("gemm");
 }
 
@@ -447,7 +428,6 @@ int dispatch(const vitk_gemm_args* a, cudaStream_t stream) {
       case EPI_RESID: return launch_gemm<BLOCK_N, false, false, EPI_RESID>(a, 1, stream);
       case EPI_F32:   return launch_gemm<BLOCK_N, false, false, EPI_F32>(a, 1, stream);
       case EPI_PATCH: return launch_gemm<BLOCK_N, false, false, EPI_PATCH>(a, 1, stream);
-      case EPI_DGELU: return launch_gemm<BLOCK_N, false, false, EPI_DGELU>(a, 1, stream);
     }
   } else if (!amn && bmn) {
     switch (a->epilogue) {

@@ -67,7 +67,10 @@ ln_fwd_kernel(const float* __restrict__ x, long long ld_x, const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// Backward.  VPL = float4 vectors per lane (dim <= 128 * VPL).  Register budget per lane: xhat (4*VPL),
+// packed dy (2*VPL), prefetched g_in (4*VPL), dgamma/dbeta partials (8*VPL) -> 2 CTAs of 8 warps per SM at VPL = 6.
+template <int VPL>
+__global__ void __launch_bounds__(LN_WARPS * 32, (VPL <= 6) ? 2 : 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ x,
               long long ld_x, const float* __restrict__ mean, const float* __restrict__ rstd,
               const float* __restrict__ gamma, const float* __restrict__ g_in,
@@ -80,62 +83,65 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float
   for (int i = threadIdx.x; i < 2 * dim; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
 
-  float4 ag[MAXV], ab[MAXV];
+  float4 ag[VPL], ab[VPL];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
+  for (int i = 0; i < VPL; ++i) {
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  float4 gm[MAXV];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-  }
+  const float4* gm4 = reinterpret_cast<const float4*>(gamma);
   const float inv_dim = 1.0f / (float)dim;
 
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows;
        row += (long long)gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * ld_dy);
     const float4* xr = reinterpret_cast<const float4*>(x + row * ld_x);
-    float4 xh[MAXV], dg[MAXV];
-    float s1 = 0.f, s2 = 0.f;
+    const float4* gir = g_in ? reinterpret_cast<const float4*>(g_in + row * ld_g) : nullptr;
+    // issue every load of the row up front (dy, x, g_in): 3 * VPL independent 8/16-byte requests per lane
+    uint2 dyp[VPL];
+    float4 xh[VPL], gi[VPL];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
-        const uint2 d = dyr[c];
-        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y);
-        const float4 xv = xr[c];
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        dyp[i] = dyr[c];
+        xh[i] = xr[c];
+        gi[i] = gir ? gir[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float2 d0 = unpack_bf16x2(dyp[i].x), d1 = unpack_bf16x2(dyp[i].y);
+        const float4 g = __ldg(gm4 + c);
+        xh[i] = make_float4((xh[i].x - mu) * rs, (xh[i].y - mu) * rs, (xh[i].z - mu) * rs, (xh[i].w - mu) * rs);
         ab[i].x += d0.x; ab[i].y += d0.y; ab[i].z += d1.x; ab[i].w += d1.y;
         ag[i].x = fmaf(d0.x, xh[i].x, ag[i].x); ag[i].y = fmaf(d0.y, xh[i].y, ag[i].y);
         ag[i].z = fmaf(d1.x, xh[i].z, ag[i].z); ag[i].w = fmaf(d1.y, xh[i].w, ag[i].w);
-        dg[i] = make_float4(d0.x * gm[i].x, d0.y * gm[i].y, d1.x * gm[i].z, d1.y * gm[i].w);
-        s1 += (dg[i].x + dg[i].y) + (dg[i].z + dg[i].w);
-        s2 += (dg[i].x * xh[i].x + dg[i].y * xh[i].y) + (dg[i].z * xh[i].z + dg[i].w * xh[i].w);
+        const float a0 = d0.x * g.x, a1 = d0.y * g.y, a2 = d1.x * g.z, a3 = d1.y * g.w;
+        s1 += (a0 + a1) + (a2 + a3);
+        s2 += (a0 * xh[i].x + a1 * xh[i].y) + (a2 * xh[i].z + a3 * xh[i].w);
       }
     }
     const float c1 = warp_sum(s1) * inv_dim;
     const float c2 = warp_sum(s2) * inv_dim;
     const float scale = (rowscale != nullptr) ? __ldg(rowscale + row / rows_per_group) : 1.0f;
     float4* gor = reinterpret_cast<float4*>(g_out + row * ld_g);
-    const float4* gir = g_in ? reinterpret_cast<const float4*>(g_in + row * ld_g) : nullptr;
     uint2* gbr = gb_out ? reinterpret_cast<uint2*>(gb_out + row * (long long)dim) : nullptr;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
       const int c = lane + i * 32;
       if (c < nvec) {
+        const float2 d0 = unpack_bf16x2(dyp[i].x), d1 = unpack_bf16x2(dyp[i].y);
+        const float4 g = __ldg(gm4 + c);
         float4 r;
-        r.x = rs * (dg[i].x - c1 - xh[i].x * c2);
-        r.y = rs * (dg[i].y - c1 - xh[i].y * c2);
-        r.z = rs * (dg[i].z - c1 - xh[i].z * c2);
-        r.w = rs * (dg[i].w - c1 - xh[i].w * c2);
-        if (gir) {
-          const float4 gi = gir[c];
-          r.x += gi.x; r.y += gi.y; r.z += gi.z; r.w += gi.w;
-        }
+        r.x = fmaf(rs, d0.x * g.x - c1 - xh[i].x * c2, gi[i].x);
+        r.y = fmaf(rs, d0.y * g.y - c1 - xh[i].y * c2, gi[i].y);
+        r.z = fmaf(rs, d1.x * g.z - c1 - xh[i].z * c2, gi[i].z);
+        r.w = fmaf(rs, d1.y * g.w - c1 - xh[i].w * c2, gi[i].w);
         gor[c] = r;
         if (gbr) {
           uint2 o;
@@ -148,23 +154,39 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float
   }
 
   // CTA-level reduction of the per-lane column partials, then one atomic per column per CTA.
+  if (dgamma != nullptr || dbeta != nullptr) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) {
-      float* rg = red + c * 4;
-      float* rb = red + dim + c * 4;
-      atomicAdd(rg + 0, ag[i].x); atomicAdd(rg + 1, ag[i].y);
-      atomicAdd(rg + 2, ag[i].z); atomicAdd(rg + 3, ag[i].w);
-      atomicAdd(rb + 0, ab[i].x); atomicAdd(rb + 1, ab[i].y);
-      atomicAdd(rb + 2, ab[i].z); atomicAdd(rb + 3, ab[i].w);
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        float* rg = red + c * 4;
+        float* rb = red + dim + c * 4;
+        atomicAdd(rg + 0, ag[i].x); atomicAdd(rg + 1, ag[i].y);
+        atomicAdd(rg + 2, ag[i].z); atomicAdd(rg + 3, ag[i].w);
+        atomicAdd(rb + 0, ab[i].x); atomicAdd(rb + 1, ab[i].y);
+        atomicAdd(rb + 2, ab[i].z); atomicAdd(rb + 3, ab[i].w);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+      if (dgamma) atomicAdd(dgamma + i, red[i]);
+      if (dbeta) atomicAdd(dbeta + i, red[dim + i]);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, red[i]);
-    if (dbeta) atomicAdd(dbeta + i, red[dim + i]);
-  }
+}
+
+template <int VPL>
+int launch_ln_bwd(const void* dy_bf16, int64_t ld_dy, const float* x, int64_t ld_x, const float* mean,
+                  const float* rstd, const float* gamma, const float* g_in, float* g_out, int64_t ld_g,
+                  void* gb_out_bf16, const float* rowscale, int32_t rows_per_group, float* dgamma, float* dbeta,
+                  int64_t rows, int32_t dim, void* stream) {
+  const long long want = (rows + LN_WARPS - 1) / LN_WARPS;
+  const long long cap = (long long)vitk_num_sms() * ((VPL <= 6) ? 2 : 1);  // exactly one resident wave
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  ln_bwd_kernel<VPL><<<grid, LN_WARPS * 32, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy_bf16, ld_dy, x, ld_x, mean, rstd, gamma, g_in, g_out, ld_g,
+      (__nv_bfloat16*)gb_out_bf16, rowscale, rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, dim);
+  return vitk_check_launch("layernorm_bwd");
 }
 
 }  // namespace
@@ -194,11 +216,14 @@ extern "C" int vitk_layernorm_bwd(const void* dy_bf16, int64_t ld_dy, const floa
   VITK_REQUIRE(ld_x % 4 == 0 && ld_dy % 4 == 0 && ld_g % 4 == 0, VITK_ERR_ALIGN, "layernorm_bwd: row pitches must be multiples of 4 elements");
   VITK_REQUIRE(mean && rstd && g_out, VITK_ERR_SHAPE, "layernorm_bwd: mean/rstd/g_out required");
   if (rows == 0) return VITK_OK;
-  long long want = (rows + LN_WARPS - 1) / LN_WARPS;
-  const long long cap = (long long)vitk_num_sms() * 4;
-  const unsigned grid = (unsigned)(want < cap ? want : cap);
-  ln_bwd_kernel<<<grid, LN_WARPS * 32, 2 * dim * sizeof(float), (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy_bf16, ld_dy, x, ld_x, mean, rstd, gamma, g_in, g_out, ld_g,
-      (__nv_bfloat16*)gb_out_bf16, rowscale, rows_per_group > 0 ? rows_per_group : 1, dgamma, dbeta, rows, dim);
-  return vitk_check_launch("layernorm_bwd");
+#define VITK_LN_BWD(V)                                                                                          \
+  return launch_ln_bwd<V>(dy_bf16, ld_dy, x, ld_x, mean, rstd, gamma, g_in, g_out, ld_g, gb_out_bf16, rowscale, \
+                          rows_per_group, dgamma, dbeta, rows, dim, stream)
+  const int vpl = (dim + 127) / 128;
+  if (vpl <= 2) VITK_LN_BWD(2);
+  if (vpl <= 3) VITK_LN_BWD(3);
+  if (vpl <= 4) VITK_LN_BWD(4);
+  if (vpl <= 6) VITK_LN_BWD(6);
+  VITK_LN_BWD(8);
+#undef VITK_LN_BWD
 }

@@ -132,7 +132,7 @@ class BlockFn(torch.autograd.Function):
         ln2 = _empty((M, D), torch.bfloat16, dev)
         mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
         L.layernorm_fwd(x_mid, blk.norm2.weight.data, blk.norm2.bias.data, ln2, mean2, rstd2, M, D, eps)
-        h = _empty((M, F), torch.bfloat16, dev)
+        h = _empty((M, F), torch.bfloat16, dev)  # receives gelu'(fc1 out): all the backward needs of it
         act = _empty((M, F), torch.bfloat16, dev)
         L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=L.EPI_GELU, bias=bias(blk.mlp.fc1), aux=h)
         x_out = _empty((B, N, D), torch.float32, dev)
