@@ -146,7 +146,10 @@ def test_gemm_rejects_bad_args(cuda_device):
     from vision_transformers_torch_xla_b200 import _lib as L
     a = torch.zeros((128, 64), device=cuda_device, dtype=torch.bfloat16)
     out = torch.zeros((128, 12), device=cuda_device)
+    outb = torch.zeros((128, 12), device=cuda_device, dtype=torch.bfloat16)
     with pytest.raises(L.VitkError):
-        L.gemm(a, a, out, M=128, N=12, K=64, epilogue=L.EPI_F32)  # N % 8 != 0
+        L.gemm(a, a, outb, M=128, N=12, K=64, epilogue=L.EPI_BF16)  # N % 8 != 0 (only the fp32 epilogue is ragged)
+    L.gemm(a, a[:12].contiguous(), out, M=128, N=12, K=64, epilogue=L.EPI_F32)
+    assert float(out.abs().max()) == 0.0
     with pytest.raises(L.VitkError):
         L.gemm(a, a, out, M=0, N=16, K=64, epilogue=L.EPI_F32)  # empty

@@ -22,12 +22,14 @@ ALIGN = 64  # elements; keeps every tensor 256-byte (fp32) / 128-byte (bf16) ali
 
 
 class ParamStore:
-    def __init__(self, root: nn.Module):
+    def __init__(self, root: nn.Module, allow_cpu: bool = False):
+        """``allow_cpu`` exists for the host-logic tests (bucket ranges, gloo all-reduce plumbing); no kernel
+        can run on such a store — every launch wrapper rejects CPU tensors."""
         named = list(root.named_parameters())
         if not named:
             raise L.VitkError("ParamStore: module has no parameters")
         dev = named[0][1].device
-        if dev.type != "cuda":
+        if dev.type != "cuda" and not allow_cpu:
             raise L.VitkError("vitk kernels only run on CUDA (sm_100a); move the model with .cuda() first — "
                               "there is no CPU path")
         self.device = dev
