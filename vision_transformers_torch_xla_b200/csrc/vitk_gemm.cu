@@ -201,19 +201,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&a
 __device__ __forceinline__ uint32_t stg_f32(int r, int u) { return r * 128 + ((u ^ (r & 7)) << 4); }
 __device__ __forceinline__ uint32_t stg_b16(int r, int u) { return r * 64 + ((u ^ ((r >> 1) & 3)) << 4); }
 
-// global (row-contiguous) <-> staging, fp32: 8 instructions, each covering 4 rows x 128 B
+// global (row-contiguous) <-> staging, fp32: 8 instructions, each covering 4 rows x 128 B.  All loads of a panel
+// are issued before the first dependent store (the compiler cannot prove smem/global do not alias).
 template <bool LOAD>
 __device__ __forceinline__ void panel_io_f32(uint8_t* stg, float* g, long long ld, int row0, int col0, int M, int N,
                                              int lane) {
   const int u = lane & 7, c = col0 + u * 4;
+  float4 t[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rr = i * 4 + (lane >> 3);
-    const int row = row0 + rr;
-    if (row < M && c < N) {
-      float4* gp = reinterpret_cast<float4*>(g + (long long)row * ld + c);
-      float4* sp = reinterpret_cast<float4*>(stg + stg_f32(rr, u));
-      if constexpr (LOAD) *sp = *gp; else *gp = *sp;
+    const bool ok = (row0 + rr < M) && (c < N);
+    if constexpr (LOAD) {
+      if (ok) t[i] = __ldcs(reinterpret_cast<const float4*>(g + (long long)(row0 + rr) * ld + c));
+    } else {
+      t[i] = *reinterpret_cast<const float4*>(stg + stg_f32(rr, u));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const bool ok = (row0 + rr < M) && (c < N);
+    if constexpr (LOAD) {
+      if (ok) *reinterpret_cast<float4*>(stg + stg_f32(rr, u)) = t[i];
+    } else {
+      if (ok) *reinterpret_cast<float4*>(g + (long long)(row0 + rr) * ld + c) = t[i];
     }
   }
 }
@@ -222,14 +234,25 @@ template <bool LOAD>
 __device__ __forceinline__ void panel_io_b16(uint8_t* stg, __nv_bfloat16* g, long long ld, int row0, int col0, int M,
                                              int N, int lane) {
   const int u = lane & 3, c = col0 + u * 8;
+  uint4 t[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rr = i * 8 + (lane >> 2);
-    const int row = row0 + rr;
-    if (row < M && c < N) {
-      uint4* gp = reinterpret_cast<uint4*>(g + (long long)row * ld + c);
-      uint4* sp = reinterpret_cast<uint4*>(stg + stg_b16(rr, u));
-      if constexpr (LOAD) *sp = *gp; else *gp = *sp;
+    const bool ok = (row0 + rr < M) && (c < N);
+    if constexpr (LOAD) {
+      if (ok) t[i] = __ldcs(reinterpret_cast<const uint4*>(g + (long long)(row0 + rr) * ld + c));
+    } else {
+      t[i] = *reinterpret_cast<const uint4*>(stg + stg_b16(rr, u));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2);
+    const bool ok = (row0 + rr < M) && (c < N);
+    if constexpr (LOAD) {
+      if (ok) *reinterpret_cast<uint4*>(stg + stg_b16(rr, u)) = t[i];
+    } else {
+      if (ok) *reinterpret_cast<uint4*>(g + (long long)(row0 + rr) * ld + c) = t[i];
     }
   }
 }
@@ -547,7 +570,7 @@ template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
 int launch_gemm(const vitk_gemm_args* a, int splits, cudaStream_t stream) {
   // 16 epilogue warps for the GELU epilogue (~20 instructions per element); 8 elsewhere.  With BLOCK_N = 192 and
   // 16 warps a warp's share is 48 columns, which is not a whole number of 32-column panels -> keep 8 there.
-  constexpr int EW = (EPI == EPI_GELU && BLOCK_N != 192) ? 16 : 8;
+  constexpr int EW = ((EPI == EPI_GELU || EPI == EPI_DGELU) && BLOCK_N != 192) ? 16 : 8;
   using Cfg = TileCfg<BLOCK_N, EW, kStgBytes<EPI>>;
   CUtensorMap tmA, tmB;
   int rc;
