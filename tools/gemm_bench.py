@@ -9,12 +9,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vision_transformers_torch_xla_b200 import _lib as L  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 50432
+ONLY = sys.argv[2] if len(sys.argv) > 2 else ""   # substring filter, e.g. "fc1 fprop"
+ITERS = int(os.environ.get("GB_ITERS", "20"))
 D, F = 768, 3072
 dev = torch.device("cuda")
 torch.manual_seed(0)
 
 
-def bench(name, fn, flops, iters=20):
+def bench(name, fn, flops, iters=None):
+    iters = iters or ITERS
+    if ONLY and ONLY not in name:
+        return
     for _ in range(3):
         fn(0)
     torch.cuda.synchronize()

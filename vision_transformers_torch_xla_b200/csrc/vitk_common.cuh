@@ -317,21 +317,30 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), sharing exp(-x^2) with the caller.
-// Returns Phi(h) = 0.5*(1+erf(h/sqrt2)); *pdf receives exp(-h^2/2)/sqrt(2*pi).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Phi(h) = 0.5*(1+erf(h/sqrt2)) via Abramowitz-Stegun 7.1.26 (|erf err| < 1.5e-7) evaluated as
+//   Phi(-|h|) = 0.5*erfc(|h|/sqrt2) = t*(a1+t*(a2+t*(a3+t*(a4+t*a5))))*exp(-h^2/2),  t = 1/(1 + p*|h|/sqrt2)
+// with the 0.5 folded into the coefficients and one MUFU.RCP + one MUFU.EX2 (~14 instructions).
+// *pdf receives exp(-h^2/2)/sqrt(2*pi), which shares the exponential.
 __device__ __forceinline__ float gelu_cdf(float h, float* pdf) {
-  const float x = fabsf(h) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
-  const float e = __expf(-x * x);
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erf_abs = 1.0f - poly * e;
-  const float erfv = copysignf(erf_abs, h);
+  const float t = rcp_approx(fmaf(fabsf(h), 0.3275911f * 0.70710678118654752f, 1.0f));
+  const float e = ex2_approx(h * h * (-0.5f * 1.4426950408889634f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float q = poly * t * e;
   if (pdf) *pdf = e * 0.3989422804014327f;
-  return 0.5f * (1.0f + erfv);
+  return h > 0.f ? 1.0f - q : q;
 }
 __device__ __forceinline__ float gelu_fwd(float h) { return h * gelu_cdf(h, nullptr); }
 __device__ __forceinline__ float gelu_bwd(float h) {
