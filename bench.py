@@ -283,6 +283,9 @@ def main():
         for fam, (n, tms) in sorted(L.breakdown_end().items(), key=lambda kv: -kv[1][1]):
             print(f"  {fam:24s} {n / 3:7.1f} launches/step {tms / 3:9.3f} ms/step", file=sys.stderr)
 
+    if distributed:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     pk = peaks()

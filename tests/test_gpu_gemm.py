@@ -137,9 +137,12 @@ def test_wgrad_mn_mn_atomic(cuda_device, M, N, K, splits):
     x = _mk((K, N), cuda_device, seed=2).bfloat16()
     init = _mk((M, N), cuda_device, seed=3)
     out = init.clone()
-    L.gemm(dy, x, out, M=M, N=N, K=K, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, splits=splits)
+    bias_g = torch.full((M,), 0.5, device=cuda_device)
+    L.gemm(dy, x, out, M=M, N=N, K=K, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, splits=splits, colsum=bias_g)
     ref = init + dy.float().t() @ x.float()
     assert rel_err(out, ref) < F32_TOL
+    # bias gradient fused into the same kernel: column sums of dy via one extra N=16 MMA against ones
+    assert rel_err(bias_g, 0.5 + dy.float().sum(0)) < F32_TOL
 
 
 def test_gemm_rejects_bad_args(cuda_device):

@@ -39,7 +39,7 @@ class GemmArgs(Structure):
         ("bias", c_void_p), ("resid", c_void_p), ("ld_resid", c_int64),
         ("rowscale", c_void_p), ("rows_per_group", c_int32), ("colscale", c_void_p),
         ("pos", c_void_p), ("tokens_per_img", c_int32), ("prefix", c_int32),
-        ("splits", c_int32), ("block_n", c_int32),
+        ("splits", c_int32), ("block_n", c_int32), ("colsum_out", c_void_p),
     ]
 
 
@@ -190,7 +190,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
          rowscale: Optional[torch.Tensor] = None, rows_per_group: int = 1,
          colscale: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
-         tokens_per_img: int = 0, prefix: int = 0, splits: int = 0, block_n: int = 0) -> None:
+         tokens_per_img: int = 0, prefix: int = 0, splits: int = 0, block_n: int = 0,
+         colsum: Optional[torch.Tensor] = None) -> None:
     """D[M,N] = opA(a) @ opB(b)^T with a fused epilogue; see ``enum vitk_epilogue`` in include/vitk.h."""
     _req(a, torch.bfloat16, "gemm A")
     _req(b, torch.bfloat16, "gemm B")
@@ -208,6 +209,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     args.colscale = _ptr(colscale)
     args.pos, args.tokens_per_img, args.prefix = _ptr(pos), tokens_per_img, prefix
     args.splits, args.block_n = splits, block_n
+    args.colsum_out = _ptr(colsum)
+    if colsum is not None:
+        _req(colsum, torch.float32, "gemm colsum")
     for t, nm in ((bias, "bias"), (resid, "resid"), (rowscale, "rowscale"), (colscale, "colscale"), (pos, "pos")):
         if t is not None:
             _req(t, torch.float32, f"gemm {nm}")

@@ -50,6 +50,7 @@ struct GemmParams {
   int tokens_per_img;
   int prefix;
   int ragged;  // EPI_F32 only: N % 8 != 0 or unaligned rows -> scalar epilogue stores
+  float* colsum_out;  // EPI_ATOMIC only: += column sums of A (bias gradient), or null
 };
 
 // Epilogue staging: every epilogue warp owns a private [32 rows][32 columns] panel in smem (4 KB for fp32
@@ -368,6 +369,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool ROLES_HI = true;
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+  // wgrad (EPI_ATOMIC) runs ~one unit per CTA: a single accumulator stage frees TMEM columns for the bias-gradient
+  // accumulator (16 columns at BLOCK_N) that an extra N=16 MMA against a tile of ones fills.
+  constexpr int ACC_STAGES = (EPI == EPI_ATOMIC) ? 1 : 2;
   static_assert(!CTA2 || (BLOCK_N % 128 == 0), "CTA pairs need BLOCK_N in {128, 256}");
   constexpr int PARTS = EW / 4;             // column partitions of the tile among epilogue warps
   constexpr int PART_N = BLOCK_N / PARTS;   // columns per epilogue warp
@@ -412,6 +416,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
       tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
       tmem_relinquish();
+    }
+  }
+  if constexpr (EPI == EPI_ATOMIC) {
+    // 16 rows x 128 B of bf16 ones (layout-agnostic B operand of the column-sum MMA); lives in the staging area,
+    // which the unstaged red.add epilogue does not use
+    if (warp >= 4) {
+      for (int i = threadIdx.x & (EW * 32 - 1); i < 2048 / 16; i += EW * 32)
+        reinterpret_cast<uint4*>(stg_base)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      fence_proxy_async_smem();
     }
   }
   tc_fence_before();
@@ -501,6 +514,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = unit % p.splits;
         const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        const bool colsum = (EPI == EPI_ATOMIC) && p.colsum_out != nullptr && ((unit / p.splits) % p.num_n_tiles == 0);
+        constexpr uint32_t idesc_cs = umma_idesc(TILE_M, 16, 1, A_MN, false);
+        const uint64_t ones_desc = umma_desc_kmajor(smem_u32(stg_base));
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -513,6 +529,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             if constexpr (CTA2) umma_bf16_ss_2cta(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
             else umma_bf16_ss(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
+            if constexpr (EPI == EPI_ATOMIC) {
+              if (colsum) {
+                if constexpr (CTA2) umma_bf16_ss_2cta(tmem_base + BLOCK_N, adesc0 + soff + k * A_KSTEP, ones_desc, idesc_cs, accum);
+                else umma_bf16_ss(tmem_base + BLOCK_N, adesc0 + soff + k * A_KSTEP, ones_desc, idesc_cs, accum);
+              }
+            }
             accum = 1;
           }
           // frees the smem slot (in both CTAs) once these MMAs retire
@@ -521,8 +543,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         // accumulator complete -> epilogue (of both CTAs)
         if constexpr (CTA2) umma_commit_2cta_mc(&tmem_full[as], 3); else umma_commit(&tmem_full[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -590,14 +611,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           epilogue_chunk<EPI, W>(p, acc, row, n_blk * BLOCK_N + col_in_tile, rs);
         }
       }
+      if constexpr (EPI == EPI_ATOMIC) {
+        if (p.colsum_out != nullptr && n_blk == 0 && part == 0) {
+          uint32_t cs[16];
+          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + BLOCK_N, cs);
+          tmem_ld_wait();
+          if (row < p.M) atomicAdd(p.colsum_out + row, __uint_as_float(cs[0]));
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CTA2 && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0);
         else mbar_arrive(&tmem_empty[as]);
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
   }
 
@@ -669,6 +697,7 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   p.pos = a->pos; p.tokens_per_img = a->tokens_per_img > 0 ? a->tokens_per_img : 1;
   p.prefix = a->prefix;
   p.ragged = (EPI == EPI_F32 && (a->N % 8 != 0 || a->ld_out % 4 != 0)) ? 1 : 0;
+  p.colsum_out = (EPI == EPI_ATOMIC) ? a->colsum_out : nullptr;
 
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI, EW, CTA2>;
   static bool attr_set = false;  // per-instantiation

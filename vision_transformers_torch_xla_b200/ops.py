@@ -93,9 +93,8 @@ class EmbedFn(torch.autograd.Function):
             if tok.requires_grad:
                 store.grad_of(tok).view(D).add_(dpre[j])
         L.gemm(gp, ctx.patches, store.grad_of(pe.proj.weight).view(D, K), M=D, N=K, K=B * P,
-               epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
-        if pe.proj.bias is not None:
-            L.colsum_bf16(gp, store.grad_of(pe.proj.bias), B * P, D)
+               epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+               colsum=None if pe.proj.bias is None else store.grad_of(pe.proj.bias))
         ctx.patches = None
         store.fire_grad_ready("embed")
         return None, None, None, None, None
@@ -156,20 +155,19 @@ class BlockFn(torch.autograd.Function):
         g = _require_f32_cuda(g, "Block.backward grad")
         dev = g.device
         sh, gr = store.shadow_of, store.grad_of
-        wgrad = lambda dy, xin, w, m, n: L.gemm(dy, xin, gr(w), M=m, N=n, K=M, epilogue=L.EPI_ATOMIC,  # noqa: E731
-                                                a_mn=True, b_mn=True)
+        # weight gradient (split-K red.add into the flat grad buffer); the bias gradient (column sums of dy) rides
+        # along as one extra N=16 MMA against a tile of ones inside the same kernel
+        wgrad = lambda dy, xin, lin, m, n: L.gemm(  # noqa: E731
+            dy, xin, gr(lin.weight), M=m, N=n, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+            colsum=None if lin.bias is None else gr(lin.bias))
 
         # ---------------- MLP branch: x_out = x_mid + rs2 * (fc2(gelu(fc1(ln2))) ) ----------------
         gb2 = _bf16_grad(store, g, rs2, N * D).view(M, D)
-        wgrad(gb2, act, blk.mlp.fc2.weight, D, F)
-        if blk.mlp.fc2.bias is not None:
-            L.colsum_bf16(gb2, gr(blk.mlp.fc2.bias), M, D)
+        wgrad(gb2, act, blk.mlp.fc2, D, F)
         dh = act  # reuse: gelu output is dead after the fc2 wgrad above
         L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
         del gb2, h
-        wgrad(dh, ln2, blk.mlp.fc1.weight, F, D)
-        if blk.mlp.fc1.bias is not None:
-            L.colsum_bf16(dh, gr(blk.mlp.fc1.bias), M, F)
+        wgrad(dh, ln2, blk.mlp.fc1, F, D)
         dln2 = ln2  # reuse: ln2 output is dead after the fc1 wgrad above
         L.gemm(dh, sh(blk.mlp.fc1.weight), dln2, M=M, N=D, K=F, epilogue=L.EPI_BF16, b_mn=True)
         del dh, act
@@ -180,17 +178,13 @@ class BlockFn(torch.autograd.Function):
         del dln2, ln2, x_mid, g
 
         # ---------------- attention branch: x_mid = x + rs1 * proj(attn(qkv(ln1))) ----------------
-        wgrad(gb1, att, blk.attn.proj.weight, D, D)
-        if blk.attn.proj.bias is not None:
-            L.colsum_bf16(gb1, gr(blk.attn.proj.bias), M, D)
+        wgrad(gb1, att, blk.attn.proj, D, D)
         datt = _empty((M, D), torch.bfloat16, dev)
         L.gemm(gb1, sh(blk.attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
         dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
         L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, blk.attn.scale)
         del gb1, datt, att, qkv, lse
-        wgrad(dqkv, ln1, blk.attn.qkv.weight, 3 * D, D)
-        if blk.attn.qkv.bias is not None:
-            L.colsum_bf16(dqkv, gr(blk.attn.qkv.bias), M, 3 * D)
+        wgrad(dqkv, ln1, blk.attn.qkv, 3 * D, D)
         dln1 = ln1
         L.gemm(dqkv, sh(blk.attn.qkv.weight), dln1, M=M, N=D, K=3 * D, epilogue=L.EPI_BF16, b_mn=True)
         del dqkv
@@ -271,10 +265,8 @@ class HeadFn(torch.autograd.Function):
                 dl = pad
             dlb = _empty((B, Cp), torch.bfloat16, dev)
             L.cast_bf16(dl, dlb)
-            L.gemm(dlb, feats[j], gr(head.weight), M=C, N=D, K=B, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, lda=Cp)
-            if head.bias is not None:
-                # padded columns land in the 64-element alignment gap that follows the bias in the flat buffer
-                L.colsum_bf16(dlb, gr(head.bias), B, Cp)
+            L.gemm(dlb, feats[j], gr(head.weight), M=C, N=D, K=B, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, lda=Cp,
+                   colsum=None if head.bias is None else gr(head.bias))
             df = _empty((B, D), torch.bfloat16, dev)
             # K = Cp: the extra weight rows read past head.weight are multiplied by the zero pad columns
             L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=Cp, epilogue=L.EPI_BF16, b_mn=True)
@@ -397,9 +389,8 @@ class LinearFn(torch.autograd.Function):
         K, N = lin.in_features, lin.out_features
         M = xb.numel() // K
         dyb = _to_bf16(_require_f32_cuda(dy, "Linear grad"))
-        L.gemm(dyb, xb, store.grad_of(lin.weight), M=N, N=K, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
-        if lin.bias is not None:
-            L.colsum_bf16(dyb, store.grad_of(lin.bias), M, N)
+        L.gemm(dyb, xb, store.grad_of(lin.weight), M=N, N=K, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+               colsum=None if lin.bias is None else store.grad_of(lin.bias))
         dx = _empty(ctx.shape, torch.float32, dy.device)
         L.gemm(dyb, store.shadow_of(lin.weight), dx, M=M, N=K, K=N, epilogue=L.EPI_F32, b_mn=True)
         return dx, None, None, None, None
@@ -437,16 +428,14 @@ class AttentionFn(torch.autograd.Function):
         dev = dy.device
         sh, gr = store.shadow_of, store.grad_of
         dyb = _to_bf16(_require_f32_cuda(dy, "Attention grad")).view(M, D)
-        L.gemm(dyb, att, gr(attn.proj.weight), M=D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
-        if attn.proj.bias is not None:
-            L.colsum_bf16(dyb, gr(attn.proj.bias), M, D)
+        L.gemm(dyb, att, gr(attn.proj.weight), M=D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+               colsum=None if attn.proj.bias is None else gr(attn.proj.bias))
         datt = _empty((M, D), torch.bfloat16, dev)
         L.gemm(dyb, sh(attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
         dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
         L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, attn.scale)
-        L.gemm(dqkv, xb, gr(attn.qkv.weight), M=3 * D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
-        if attn.qkv.bias is not None:
-            L.colsum_bf16(dqkv, gr(attn.qkv.bias), M, 3 * D)
+        L.gemm(dqkv, xb, gr(attn.qkv.weight), M=3 * D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+               colsum=None if attn.qkv.bias is None else gr(attn.qkv.bias))
         dx = _empty((B, N, D), torch.float32, dev)
         L.gemm(dqkv, sh(attn.qkv.weight), dx, M=M, N=D, K=3 * D, epilogue=L.EPI_F32, b_mn=True)
         return dx, None, None, None, None
@@ -481,14 +470,12 @@ class MlpFn(torch.autograd.Function):
         M = xb.numel() // D
         sh, gr = store.shadow_of, store.grad_of
         dyb = _to_bf16(_require_f32_cuda(dy, "Mlp grad")).view(M, O)
-        L.gemm(dyb, act, gr(mlp.fc2.weight), M=O, N=F, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
-        if mlp.fc2.bias is not None:
-            L.colsum_bf16(dyb, gr(mlp.fc2.bias), M, O)
+        L.gemm(dyb, act, gr(mlp.fc2.weight), M=O, N=F, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+               colsum=None if mlp.fc2.bias is None else gr(mlp.fc2.bias))
         dh = act
         L.gemm(dyb, sh(mlp.fc2.weight), dh, M=M, N=F, K=O, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
-        L.gemm(dh, xb, gr(mlp.fc1.weight), M=F, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True)
-        if mlp.fc1.bias is not None:
-            L.colsum_bf16(dh, gr(mlp.fc1.bias), M, F)
+        L.gemm(dh, xb, gr(mlp.fc1.weight), M=F, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
+               colsum=None if mlp.fc1.bias is None else gr(mlp.fc1.bias))
         dx = _empty(ctx.shape, torch.float32, dy.device)
         L.gemm(dh, sh(mlp.fc1.weight), dx, M=M, N=D, K=F, epilogue=L.EPI_F32, b_mn=True)
         return dx, None, None, None, None
@@ -518,7 +505,5 @@ class PatchEmbedFn(torch.autograd.Function):
         B, P, D, K = ctx.dims
         dyb = _to_bf16(_require_f32_cuda(dy, "PatchEmbed grad")).view(B * P, D)
         L.gemm(dyb, patches, store.grad_of(pe.proj.weight).view(D, K), M=D, N=K, K=B * P, epilogue=L.EPI_ATOMIC,
-               a_mn=True, b_mn=True)
-        if pe.proj.bias is not None:
-            L.colsum_bf16(dyb, store.grad_of(pe.proj.bias), B * P, D)
+               a_mn=True, b_mn=True, colsum=None if pe.proj.bias is None else store.grad_of(pe.proj.bias))
         return None, None, None, None, None
