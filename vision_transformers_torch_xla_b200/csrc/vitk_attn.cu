@@ -13,6 +13,8 @@
 // The same smem bytes serve as a K-major operand ([rows][64 contiguous] = rows x K) and as an
 // MN-major operand (K rows x 64 contiguous MN) — only the UMMA descriptor differs — which is how
 // P / dS feed P*V, P^T*dO, dS^T*Q and dS*K without any transposes.
+#include <cstdlib>
+
 #include "vitk_common.cuh"
 #include "vitk_internal.h"
 
@@ -471,6 +473,245 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
+// ================================================================================================
+// Forward, persistent variant for N <= 256 (single-pass softmax: the whole score row lives in TMEM).
+//
+// 192 threads: warps 0-3 = softmax / epilogue (thread r owns row r of the 128-row q tile), warp 4 = TMA producer,
+// warp 5 = MMA issuer.  One CTA per SM loops over work items (b, h, q-tile).  Everything that has latency is
+// overlapped with the thread math of another item:
+//   * Q/K/V tiles of item n+1 are prefetched into the second smem stage while item n is processed,
+//   * S is double-buffered in TMEM (2 x 256 columns): S_{n+1} = Q K^T is issued before the softmax of item n ends,
+//   * O_n = P_n V (written into columns [0,64) of S_n's buffer once S_n has been consumed) is read back while the
+//     tensor core already works on S_{n+1}.
+// smem: 2 stages x (Q 16K + K T*16K + V T*16K) | P [T*2 chunks][128 rows][128 B] | barriers
+// ================================================================================================
+template <int T>
+struct Fwd2Smem {
+  static constexpr uint32_t STAGE = (1 + 2 * T) * TILE_BYTES;
+  static constexpr uint32_t P_OFF = 2 * STAGE;
+  static constexpr uint32_t BAR_OFF = P_OFF + 2 * T * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256;
+};
+
+template <int T>
+__global__ void __launch_bounds__(192, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+                 int B, int N, int H, float scale) {
+  using L = Fwd2Smem<T>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [2] TMA -> MMA
+  uint64_t* stage_empty = stage_full + 2;                                  // [2] MMA -> TMA
+  uint64_t* s_full = stage_empty + 2;                                      // [2] MMA -> softmax (S ready)
+  uint64_t* o_full = s_full + 2;                                           // [2] MMA -> softmax (O ready)
+  uint64_t* tmem_free = o_full + 2;                                        // [2] softmax -> MMA (buffer drained)
+  uint64_t* p_full = tmem_free + 2;                                        // [1] softmax -> MMA (P written)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int QT = (N + TILE - 1) / TILE;
+  const int items = B * H * QT;
+  const uint32_t n_eff = roundup16(N);
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_full[i], 1);
+      mbar_init(&stage_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&tmem_free[i], 128);
+    }
+    mbar_init(p_full, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      int n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int st = n & 1;
+        const int qt = it % QT, bh = it / QT, h = bh % H, b = bh / H;
+        mbar_wait(&stage_empty[st], ((n >> 1) & 1) ^ 1);
+        uint8_t* base = smem + st * L::STAGE;
+        mbar_arrive_expect_tx(&stage_full[st], L::STAGE);
+        tma_load_3d(base, &tm_qkv, &stage_full[st], h * HD, qt * TILE, b);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          tma_load_3d(base + (1 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (H + h) * HD, t * TILE, b);
+          tma_load_3d(base + (1 + T + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (2 * H + h) * HD, t * TILE, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
+      const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
+      const uint32_t sP = smem_u32(smem + L::P_OFF);
+      const int ksteps = (int)n_eff / 16;
+      auto issue_s = [&](int n) {
+        const int st = n & 1;
+        mbar_wait(&stage_full[st], (n >> 1) & 1);
+        mbar_wait(&tmem_free[st], ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sQ = smem_u32(smem + st * L::STAGE), sK = sQ + TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + st * 256, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc_s, k > 0);
+        umma_commit(&s_full[st]);
+      };
+      int count = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x) ++count;
+      if (count > 0) issue_s(0);
+      for (int n = 0; n < count; ++n) {
+        const int st = n & 1;
+        if (n + 1 < count) issue_s(n + 1);
+        mbar_wait(p_full, n & 1);
+        tc_fence_after();
+        const uint32_t sV = smem_u32(smem + st * L::STAGE) + (1 + T) * TILE_BYTES;
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ss(tmem_base + st * 256, umma_desc_kmajor(sP + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                       umma_desc_mnmajor(sV + k * 2048, TILE_BYTES), idesc_o, k > 0);
+        umma_commit(&o_full[st]);
+        umma_commit(&stage_empty[st]);  // Q, K (S done earlier in issue order) and V are free again
+      }
+    }
+  } else {
+    // ------------------------------ softmax / epilogue (128 threads) ------------------------------
+    const int r = threadIdx.x;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    const float c2 = scale * LOG2E;
+    uint8_t* sP = smem + L::P_OFF;
+    const int nchunks = (int)(n_eff + 31) / 32;
+    float prev_l = 1.f, prev_m = 0.f;
+    int prev_it = -1;
+
+    // read O of the previous item out of TMEM, normalise, store; then hand the TMEM buffer back
+    auto finish = [&](int n_prev) {
+      const int st = n_prev & 1;
+      mbar_wait(&o_full[st], (n_prev >> 1) & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(tmem_base + st * 256 + lane_addr, o0);
+      tmem_ld_32x32(tmem_base + st * 256 + lane_addr + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&tmem_free[st]);
+      const int qt = prev_it % QT, bh = prev_it / QT, h = bh % H, b = bh / H;
+      const int q = qt * TILE + r;
+      if (q < N) {
+        const float inv = 1.0f / prev_l;
+        __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * HD) + h * HD;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + g * 8) = u;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + 32 + g * 8) = u;
+        }
+        if (lse) lse[((long long)b * H + h) * N + q] = prev_m * scale + __logf(prev_l);
+      }
+    };
+
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int st = n & 1;
+      const uint32_t tS = tmem_base + st * 256 + lane_addr;
+      mbar_wait(&s_full[st], (n >> 1) & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + c * 32, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      }
+      // O of the previous item (its P*V has long finished): frees the P buffer for this item as a side effect
+      if (n > 0) finish(n - 1);
+      // pass 2: exponentials -> P (bf16, swizzled smem), row sum of the rounded values
+      const float mc = mx * c2;
+      float rowsum = 0.f;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + c * 32, sv);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = ex2_approx(fmaf(__uint_as_float(sv[i]), c2, -mc));
+          p[i] = (c * 32 + i < N) ? e : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+            uint4 u;
+            u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
+            u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+            u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
+            u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+            st_swz(sP, r, c * 4 + g, u);
+            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+            rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+          }
+        }
+      }
+      prev_l = rowsum;
+      prev_m = mx;
+      prev_it = it;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    if (n > 0) finish(n - 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int T>
+int launch_fwd2(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
+  auto kern = attn_fwd2_kernel<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd2Smem<T>::BYTES);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int items = B * H * ((N + TILE - 1) / TILE);
+  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
+  kern<<<grid, 192, Fwd2Smem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, B, N, H, scale);
+  return vitk_check_launch("attn_fwd2");
+}
+
 template <int T>
 int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
   auto kern = attn_fwd_kernel<T>;
@@ -499,6 +740,12 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   if (rc) return rc;
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool persistent = [] {
+    const char* e = getenv("VITK_ATTN_FWD");  // tuning knob: "1" selects the one-CTA-per-tile kernel
+    return !(e && e[0] == '1');
+  }();
+  if (persistent && T == 1) return launch_fwd2<1>(tm, out, lse, B, N, H, scale, s);
+  if (persistent && T == 2) return launch_fwd2<2>(tm, out, lse, B, N, H, scale, s);
   switch (T) {
     case 1: return launch_fwd<1>(tm, out, lse, B, N, H, scale, s);
     case 2: return launch_fwd<2>(tm, out, lse, B, N, H, scale, s);
