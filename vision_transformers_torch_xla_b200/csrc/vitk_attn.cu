@@ -712,6 +712,267 @@ int launch_fwd2(const CUtensorMap& tm, void* out, float* lse, int B, int N, int 
   return vitk_check_launch("attn_fwd2");
 }
 
+// ================================================================================================
+// Backward, two-warpgroup variant (N <= 256): one CTA per (b, h), 288 threads.
+//   warpgroup w (warps 4w..4w+3) owns q tile w: thread r holds row r's probabilities in registers between the
+//   S and dP phases, so S and dP share ONE 128-column TMEM buffer per warpgroup;
+//   warp 8 issues every TMA load and every tcgen05.mma and ping-pongs between the two warpgroups, so the tensor
+//   core runs one warpgroup's GEMMs while the other does its exp / dS math.
+// TMEM: SdP_0 [0,128) | SdP_1 [128,256) | dV_j [256,320) | dK_j [320,384) | dQ_0 [384,448) | dQ_1 [448,512)
+// smem: Q_i, dO_i, K_j, V_j tiles (T*64K) | PdS_0 (32K) | PdS_1 (32K) | barriers.  P_w and dS_w share one buffer:
+//       dS_w overwrites P_w once the dV MMA that reads P_w has retired (covered by the dP commit).
+// ================================================================================================
+struct Bwd2Smem {
+  static constexpr uint32_t QDO_OFF = 0;
+  static constexpr uint32_t KV_OFF = BWD_MAX_T * 2 * TILE_BYTES;
+  static constexpr uint32_t PDS_OFF = KV_OFF + BWD_MAX_T * 2 * TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = PDS_OFF + 2 * 2 * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(288, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                 const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+  using L = Bwd2Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* bar_s = bar_ld + 1;        // [2] MMA -> WG: S_w ready
+  uint64_t* bar_p = bar_s + 2;         // [2] WG -> MMA: P_w written
+  uint64_t* bar_dp = bar_p + 2;        // [2] MMA -> WG: dP_w ready, P_w consumed
+  uint64_t* bar_ds = bar_dp + 2;       // [2] WG -> MMA: dS_w written
+  uint64_t* bar_drain = bar_ds + 2;    // MMA -> WGs: every MMA of kv tile j retired
+  uint64_t* bar_drained = bar_drain + 1;  // WGs -> MMA: dV_j / dK_j read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_drained + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nt = (N + TILE - 1) / TILE;  // q tiles == kv tiles == active warpgroups
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    mbar_init(bar_ld, 1);
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&bar_s[w], 1);
+      mbar_init(&bar_p[w], 128);
+      mbar_init(&bar_dp[w], 1);
+      mbar_init(&bar_ds[w], 128);
+    }
+    mbar_init(bar_drain, 1);
+    mbar_init(bar_drained, 128 * nt);
+    fence_mbar_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
+  const float c2 = scale * LOG2E;
+
+  if (warp == 8) {
+    // ------------------------------ TMA + MMA control ------------------------------
+    if ((threadIdx.x & 31) == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      mbar_arrive_expect_tx(bar_ld, nt * 4 * TILE_BYTES);
+      for (int t = 0; t < nt; ++t) {
+        tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, h * HD, t * TILE, b);
+        tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_do, bar_ld, h * HD, t * TILE, b);
+        tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, (H + h) * HD, t * TILE, b);
+        tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, bar_ld, (2 * H + h) * HD, t * TILE, b);
+      }
+      const uint32_t sQDO = smem_u32(smem + L::QDO_OFF), sKV = smem_u32(smem + L::KV_OFF);
+      const uint32_t sPDS = smem_u32(smem + L::PDS_OFF);
+      auto issue_s = [&](int w, int j) {
+        const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
+        const uint32_t sQ = sQDO + w * 2 * TILE_BYTES, sK = sKV + j * 2 * TILE_BYTES;
+        const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16_ss(tmem_base + w * 128, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc, k > 0);
+        umma_commit(&bar_s[w]);
+      };
+      mbar_wait(bar_ld, 0);
+      tc_fence_after();
+      for (int w = 0; w < nt; ++w) issue_s(w, 0);
+      const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);   // A, B MN-major (P^T dO, dS^T Q)
+      const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);  // dS K
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
+        const uint32_t sK = sKV + j * 2 * TILE_BYTES, sV = sK + TILE_BYTES;
+        if (j > 0) {
+          mbar_wait(bar_drained, (j - 1) & 1);  // dV / dK of the previous kv tile were read out
+          tc_fence_after();
+        }
+        for (int w = 0; w < nt; ++w) {
+          const uint32_t q_eff = roundup16(min(TILE, N - w * TILE));
+          const uint32_t sQ = sQDO + w * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES, sP = sPDS + w * 2 * TILE_BYTES;
+          mbar_wait(&bar_p[w], j & 1);
+          tc_fence_after();
+          // dV_j += P_w^T dO_w
+          for (int k = 0; k < (int)q_eff / 16; ++k)
+            umma_bf16_ss(tm_dv, umma_desc_mnmajor(sP + k * 2048, TILE_BYTES), umma_desc_mnmajor(sDO + k * 2048, TILE_BYTES),
+                         idesc_t, (w > 0 || k > 0));
+          // dP_w = dO_w V_j^T  (overwrites S_w, which warpgroup w has already turned into register-resident P)
+          const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_bf16_ss(tmem_base + w * 128, umma_desc_kmajor(sDO + k * 32), umma_desc_kmajor(sV + k * 32), idesc, k > 0);
+          umma_commit(&bar_dp[w]);
+        }
+        for (int w = 0; w < nt; ++w) {
+          const uint32_t q_eff = roundup16(min(TILE, N - w * TILE));
+          const uint32_t sQ = sQDO + w * 2 * TILE_BYTES, sDS = sPDS + w * 2 * TILE_BYTES;
+          mbar_wait(&bar_ds[w], j & 1);
+          tc_fence_after();
+          // dK_j += dS_w^T Q_w
+          for (int k = 0; k < (int)q_eff / 16; ++k)
+            umma_bf16_ss(tm_dk, umma_desc_mnmajor(sDS + k * 2048, TILE_BYTES), umma_desc_mnmajor(sQ + k * 2048, TILE_BYTES),
+                         idesc_t, (w > 0 || k > 0));
+          // dQ_w += dS_w K_j
+          for (int k = 0; k < (int)n_eff / 16; ++k)
+            umma_bf16_ss(tm_dq + w * HD, umma_desc_kmajor(sDS + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                         umma_desc_mnmajor(sK + k * 2048, TILE_BYTES), idesc_q, (j > 0 || k > 0));
+          if (j + 1 < nt) issue_s(w, j + 1);  // SdP_w is free again: warpgroup w wrote dS_w after reading dP_w
+        }
+        umma_commit(bar_drain);
+      }
+    }
+  } else if (warp < 4 * nt) {
+    // ------------------------------ warpgroup w: rows of q tile w ------------------------------
+    const int w = warp >> 2;
+    const int r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tm_sdp = tmem_base + w * 128 + lane_addr;
+    uint8_t* sPDS = smem + L::PDS_OFF + w * 2 * TILE_BYTES;
+    const int q = w * TILE + r;
+    const int qn = min(TILE, N - w * TILE);
+    const uint32_t q_eff = roundup16(qn);
+    const bool row_ok = r < qn;
+    float my_lse2 = 0.f, my_d = 0.f;
+    if (row_ok) {
+      my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
+      const uint4* op = reinterpret_cast<const uint4*>(out + ((long long)b * N + q) * (H * HD) + h * HD);
+      const uint4* dp = reinterpret_cast<const uint4*>(dout + ((long long)b * N + q) * (H * HD) + h * HD);
+      float acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 a = __ldg(op + g), d = __ldg(dp + g);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+        acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+      }
+      my_d = acc;
+    }
+
+    for (int j = 0; j < nt; ++j) {
+      const int kvn = min(TILE, N - j * TILE);
+      const uint32_t n_eff = roundup16(kvn);
+      const int nchunks = (int)(n_eff + 31) / 32;
+      uint32_t pk[64];  // this row's probabilities of the tile, packed bf16 pairs
+
+      // ---- phase 1: S -> P (registers + smem) ----
+      mbar_wait(&bar_s[w], j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nchunks) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tm_sdp + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const bool ok0 = row_ok && (c * 32 + 2 * k < kvn), ok1 = row_ok && (c * 32 + 2 * k + 1 < kvn);
+            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * k]), c2, -my_lse2));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * k + 1]), c2, -my_lse2));
+            pk[c * 16 + k] = pack_bf16x2(ok0 ? e0 : 0.f, ok1 ? e1 : 0.f);
+          }
+          if ((uint32_t)r < q_eff) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if ((uint32_t)(c * 32 + g * 8) < n_eff)
+                st_swz(sPDS, r, c * 4 + g, make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2],
+                                                      pk[c * 16 + g * 4 + 3]));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar_p[w]);
+
+      // ---- phase 2: dP -> dS (smem, over P) ----
+      mbar_wait(&bar_dp[w], j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nchunks) {
+          uint32_t dv[32];
+          tmem_ld_32x32(tm_sdp + c * 32, dv);
+          tmem_ld_wait();
+          if ((uint32_t)r < q_eff) {
+            uint32_t ds[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float2 pp = unpack_bf16x2(pk[c * 16 + k]);
+              ds[k] = pack_bf16x2(pp.x * (__uint_as_float(dv[2 * k]) - my_d) * scale,
+                                  pp.y * (__uint_as_float(dv[2 * k + 1]) - my_d) * scale);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if ((uint32_t)(c * 32 + g * 8) < n_eff)
+                st_swz(sPDS, r, c * 4 + g, make_uint4(ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&bar_ds[w]);
+
+      // ---- drain dV_j (warpgroup 0) / dK_j (warpgroup 1, or 0 when it is alone) ----
+      mbar_wait(bar_drain, j & 1);
+      tc_fence_after();
+      {
+        const int kv = j * TILE + r;
+        uint32_t a0[32], a1[32];
+        if (w == 0) {
+          tmem_ld_32x32(tm_dv + lane_addr, a0);
+          tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
+          tmem_ld_wait();
+          if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (2 * H + h) * HD, a0, a1);
+        }
+        if (w == nt - 1) {
+          tmem_ld_32x32(tm_dk + lane_addr, a0);
+          tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
+          tmem_ld_wait();
+          if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (H + h) * HD, a0, a1);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_drained);
+    }
+
+    // ---- dQ_w (the last bar_drain wait above covers every MMA) ----
+    {
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(tm_dq + w * HD + lane_addr, a0);
+      tmem_ld_32x32(tm_dq + w * HD + lane_addr + 32, a1);
+      tmem_ld_wait();
+      if (row_ok) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * HD) + h * HD, a0, a1);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int T>
 int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
   auto kern = attn_fwd_kernel<T>;
@@ -772,10 +1033,22 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem::BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd2Smem::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid(H, B);
+  static const bool two_wg = [] {
+    const char* e = getenv("VITK_ATTN_BWD");  // tuning knob: "1" selects the single-warpgroup kernel
+    return !(e && e[0] == '1');
+  }();
+  if (two_wg) {
+    attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, (cudaStream_t)stream>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
+                                                                           (const __nv_bfloat16*)dout, lse,
+                                                                           (__nv_bfloat16*)dqkv, N, H, scale);
+    return vitk_check_launch("attn_bwd2");
+  }
   attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, (cudaStream_t)stream>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
                                                                        (const __nv_bfloat16*)dout, lse,
                                                                        (__nv_bfloat16*)dqkv, N, H, scale);

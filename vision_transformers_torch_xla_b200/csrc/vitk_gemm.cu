@@ -514,9 +514,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = unit % p.splits;
         const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
-        // bias-gradient MMAs are spread over the n-tiles of a row: tile n_blk covers the k-blocks kb % num_n_tiles == n_blk
-        const bool colsum = (EPI == EPI_ATOMIC) && p.colsum_out != nullptr;
-        const int cs_nblk = (unit / p.splits) % p.num_n_tiles;
+        // the n_blk == 0 tile of every row of tiles also accumulates the bias gradient.  (Spreading these MMAs over
+        // all n-tiles was measured 2x slower: every N=16 MMA interleaved into the N=256 stream stalls the pipe.)
+        const bool colsum = (EPI == EPI_ATOMIC) && p.colsum_out != nullptr && ((unit / p.splits) % p.num_n_tiles == 0);
         uint32_t accum_cs = 0;
         constexpr uint32_t idesc_cs = umma_idesc(TILE_M, 16, 1, A_MN, false);
         const uint64_t ones_desc = umma_desc_kmajor(smem_u32(stg_base));
@@ -533,7 +533,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if constexpr (CTA2) umma_bf16_ss_2cta(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
             else umma_bf16_ss(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
             if constexpr (EPI == EPI_ATOMIC) {
-              if (colsum && (kb % p.num_n_tiles) == cs_nblk) {
+              if (colsum) {
                 if constexpr (CTA2) umma_bf16_ss_2cta(tmem_base + BLOCK_N, adesc0 + soff + k * A_KSTEP, ones_desc, idesc_cs, accum_cs);
                 else umma_bf16_ss(tmem_base + BLOCK_N, adesc0 + soff + k * A_KSTEP, ones_desc, idesc_cs, accum_cs);
                 accum_cs = 1;
@@ -616,12 +616,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       if constexpr (EPI == EPI_ATOMIC) {
-        // did this unit run any bias-gradient MMA?  (first k-block >= kb0 with kb % num_n_tiles == n_blk)
-        const int split = unit % p.splits;
-        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
-        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
-        const int first = kb0 + ((n_blk - kb0 % p.num_n_tiles) + p.num_n_tiles) % p.num_n_tiles;
-        if (p.colsum_out != nullptr && first < kb1 && part == 0) {
+        if (p.colsum_out != nullptr && n_blk == 0 && part == 0) {
           uint32_t cs[16];
           tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + BLOCK_N, cs);
           tmem_ld_wait();
