@@ -62,7 +62,7 @@ def test_attn_bwd(cuda_device, B, N, H):
     r = ref.view(B, N, 3, H * hd)
     for i, name in enumerate("qkv"):
         # P and dS are rounded to bf16 before the dV/dK/dQ GEMMs; outputs are bf16
-        assert elem_err(d[:, :, i], r[:, :, i]) < 1.5e-2, f"d{name}"
+        assert elem_err(d[:, :, i], r[:, :, i]) < 2.5e-2, f"d{name}"
         assert rel_err(d[:, :, i], r[:, :, i]) < 6e-2, f"d{name}"
 
 

@@ -476,25 +476,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 // ================================================================================================
 // Forward, persistent variant for N <= 256 (single-pass softmax: the whole score row lives in TMEM).
 //
-// 192 threads: warps 0-3 = softmax / epilogue (thread r owns row r of the 128-row q tile), warp 4 = TMA producer,
-// warp 5 = MMA issuer.  One CTA per SM loops over work items (b, h, q-tile).  Everything that has latency is
-// overlapped with the thread math of another item:
+// 320 threads: warps 0-7 = softmax / epilogue, warp 8 = TMA producer, warp 9 = MMA issuer.  Two threads share a
+// score row (thread (r, half) owns row r and one half of the kv columns; TMEM lane = row, so both warpgroups can
+// read it) and exchange max / sum through smem: with one warp per scheduler the softmax is latency-bound, two warps
+// per scheduler nearly double its throughput.  One CTA per SM loops over work items (b, h, q-tile):
 //   * Q/K/V tiles of item n+1 are prefetched into the second smem stage while item n is processed,
 //   * S is double-buffered in TMEM (2 x 256 columns): S_{n+1} = Q K^T is issued before the softmax of item n ends,
 //   * O_n = P_n V (written into columns [0,64) of S_n's buffer once S_n has been consumed) is read back while the
 //     tensor core already works on S_{n+1}.
-// smem: 2 stages x (Q 16K + K T*16K + V T*16K) | P [T*2 chunks][128 rows][128 B] | barriers
+// smem: 2 stages x (Q 16K + K T*16K + V T*16K) | P [T*2 chunks][128 rows][128 B] | exchange | barriers
 // ================================================================================================
 template <int T>
 struct Fwd2Smem {
   static constexpr uint32_t STAGE = (1 + 2 * T) * TILE_BYTES;
   static constexpr uint32_t P_OFF = 2 * STAGE;
-  static constexpr uint32_t BAR_OFF = P_OFF + 2 * T * TILE_BYTES;
+  static constexpr uint32_t XCH_OFF = P_OFF + 2 * T * TILE_BYTES;     // float [2 parity][2 kind][2 half][128]
+  static constexpr uint32_t BAR_OFF = XCH_OFF + 2 * 2 * 2 * 128 * 4;
   static constexpr uint32_t BYTES = BAR_OFF + 256;
 };
 
 template <int T>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                  int B, int N, int H, float scale) {
   using L = Fwd2Smem<T>;
@@ -506,6 +508,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   uint64_t* tmem_free = o_full + 2;                                        // [2] softmax -> MMA (buffer drained)
   uint64_t* p_full = tmem_free + 2;                                        // [1] softmax -> MMA (P written)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
+  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int QT = (N + TILE - 1) / TILE;
@@ -519,12 +522,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       mbar_init(&stage_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&tmem_free[i], 128);
+      mbar_init(&tmem_free[i], 256);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -533,7 +536,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       tma_prefetch_desc(&tm_qkv);
@@ -552,7 +555,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
@@ -587,50 +590,45 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       }
     }
   } else {
-    // ------------------------------ softmax / epilogue (128 threads) ------------------------------
-    const int r = threadIdx.x;
-    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    // ------------------------------ softmax / epilogue (256 threads, 2 per row) ------------------------------
+    const int r = threadIdx.x & 127;
+    const int half = threadIdx.x >> 7;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float c2 = scale * LOG2E;
     uint8_t* sP = smem + L::P_OFF;
-    const int nchunks = (int)(n_eff + 31) / 32;
-    float prev_l = 1.f, prev_m = 0.f;
+    const int nchunks = (int)(n_eff + 31) / 32;      // 32-column chunks of the score row (<= 8)
+    const int c_lo = half == 0 ? 0 : (nchunks + 1) / 2;
+    const int c_hi = half == 0 ? (nchunks + 1) / 2 : nchunks;
+    float prev_m = 0.f;
     int prev_it = -1;
 
-    // read O of the previous item out of TMEM, normalise, store; then hand the TMEM buffer back
+    // read this thread's 32 columns of O of the previous item, normalise, store; hand the TMEM buffer back
     auto finish = [&](int n_prev) {
       const int st = n_prev & 1;
+      const float* xs = xch + ((n_prev & 1) * 2 + 1) * 256;       // partial row sums of item n_prev
+      const float l = xs[r] + xs[128 + r];
       mbar_wait(&o_full[st], (n_prev >> 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(tmem_base + st * 256 + lane_addr, o0);
-      tmem_ld_32x32(tmem_base + st * 256 + lane_addr + 32, o1);
+      uint32_t o[32];
+      tmem_ld_32x32(tmem_base + st * 256 + lane_addr + half * 32, o);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&tmem_free[st]);
       const int qt = prev_it % QT, bh = prev_it / QT, h = bh % H, b = bh / H;
       const int q = qt * TILE + r;
       if (q < N) {
-        const float inv = 1.0f / prev_l;
-        __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * HD) + h * HD;
+        const float inv = 1.0f / l;
+        __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * HD) + h * HD + half * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o0[g * 8 + 0]) * inv, __uint_as_float(o0[g * 8 + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o0[g * 8 + 2]) * inv, __uint_as_float(o0[g * 8 + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o0[g * 8 + 4]) * inv, __uint_as_float(o0[g * 8 + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o0[g * 8 + 6]) * inv, __uint_as_float(o0[g * 8 + 7]) * inv);
+          u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
           *reinterpret_cast<uint4*>(orow + g * 8) = u;
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o1[g * 8 + 0]) * inv, __uint_as_float(o1[g * 8 + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o1[g * 8 + 2]) * inv, __uint_as_float(o1[g * 8 + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o1[g * 8 + 4]) * inv, __uint_as_float(o1[g * 8 + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o1[g * 8 + 6]) * inv, __uint_as_float(o1[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + 32 + g * 8) = u;
-        }
-        if (lse) lse[((long long)b * H + h) * N + q] = prev_m * scale + __logf(prev_l);
+        if (half == 0 && lse) lse[((long long)b * H + h) * N + q] = prev_m * scale + __logf(l);
       }
     };
 
@@ -638,60 +636,72 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const int st = n & 1;
       const uint32_t tS = tmem_base + st * 256 + lane_addr;
+      float* xm = xch + ((n & 1) * 2 + 0) * 256;   // [half][row] partial maxima of this item
+      float* xs = xch + ((n & 1) * 2 + 1) * 256;   // [half][row] partial sums of this item
       mbar_wait(&s_full[st], (n >> 1) & 1);
       tc_fence_after();
-      // pass 1: row max
+      // this thread's half of the score row -> registers (<= 4 chunks of 32 columns)
+      uint32_t sv[4][32];
       float mx = -INFINITY;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tS + c * 32, sv);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = c_lo + cc;
+        if (c < c_hi) {
+          tmem_ld_32x32(tS + c * 32, sv[cc]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(sv[cc][i]));
+        }
       }
+      xm[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(xm[r], xm[128 + r]);
       // O of the previous item (its P*V has long finished): frees the P buffer for this item as a side effect
       if (n > 0) finish(n - 1);
-      // pass 2: exponentials -> P (bf16, swizzled smem), row sum of the rounded values
       const float mc = mx * c2;
       float rowsum = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tS + c * 32, sv);
-        tmem_ld_wait();
-        float p[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2_approx(fmaf(__uint_as_float(sv[i]), c2, -mc));
-          p[i] = (c * 32 + i < N) ? e : 0.f;
-        }
+      for (int cc = 0; cc < 4; ++cc) {
+        const int c = c_lo + cc;
+        if (c < c_hi) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if ((uint32_t)(c * 32 + g * 8) < n_eff) {
-            uint4 u;
-            u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
-            u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-            u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
-            u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-            st_swz(sP, r, c * 4 + g, u);
-            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-            rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+          for (int g = 0; g < 4; ++g) {
+            if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+              float p[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float e = ex2_approx(fmaf(__uint_as_float(sv[cc][g * 8 + i]), c2, -mc));
+                p[i] = (c * 32 + g * 8 + i < N) ? e : 0.f;
+              }
+              uint4 u;
+              u.x = pack_bf16x2(p[0], p[1]);
+              u.y = pack_bf16x2(p[2], p[3]);
+              u.z = pack_bf16x2(p[4], p[5]);
+              u.w = pack_bf16x2(p[6], p[7]);
+              st_swz(sP, r, c * 4 + g, u);
+              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+              rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+            }
           }
         }
       }
-      prev_l = rowsum;
+      xs[half * 128 + r] = rowsum;   // read by both halves in finish(n), i.e. after the next item's bar.sync
       prev_m = mx;
       prev_it = it;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
     }
-    if (n > 0) finish(n - 1);
+    if (n > 0) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // partial sums of the last item are visible
+      finish(n - 1);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -708,7 +718,7 @@ int launch_fwd2(const CUtensorMap& tm, void* out, float* lse, int B, int N, int 
   }
   const int items = B * H * ((N + TILE - 1) / TILE);
   const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
-  kern<<<grid, 192, Fwd2Smem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, B, N, H, scale);
+  kern<<<grid, 320, Fwd2Smem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, B, N, H, scale);
   return vitk_check_launch("attn_fwd2");
 }
 
