@@ -490,8 +490,8 @@ template <int T>
 struct Fwd2Smem {
   static constexpr uint32_t STAGE = (1 + 2 * T) * TILE_BYTES;
   static constexpr uint32_t P_OFF = 2 * STAGE;
-  static constexpr uint32_t XCH_OFF = P_OFF + 2 * T * TILE_BYTES;     // float [2 parity][2 kind][2 half][128]
-  static constexpr uint32_t BAR_OFF = XCH_OFF + 2 * 2 * 2 * 128 * 4;
+  static constexpr uint32_t XCH_OFF = P_OFF + 2 * T * TILE_BYTES;     // float [2 kind][2 half][128]
+  static constexpr uint32_t BAR_OFF = XCH_OFF + 2 * 2 * 128 * 4;
   static constexpr uint32_t BYTES = BAR_OFF + 256;
 };
 
@@ -603,10 +603,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     int prev_it = -1;
 
     // read this thread's 32 columns of O of the previous item, normalise, store; hand the TMEM buffer back
-    auto finish = [&](int n_prev) {
+    auto finish = [&](int n_prev, float l) {
       const int st = n_prev & 1;
-      const float* xs = xch + ((n_prev & 1) * 2 + 1) * 256;       // partial row sums of item n_prev
-      const float l = xs[r] + xs[128 + r];
       mbar_wait(&o_full[st], (n_prev >> 1) & 1);
       tc_fence_after();
       uint32_t o[32];
@@ -636,8 +634,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
       const int st = n & 1;
       const uint32_t tS = tmem_base + st * 256 + lane_addr;
-      float* xm = xch + ((n & 1) * 2 + 0) * 256;   // [half][row] partial maxima of this item
-      float* xs = xch + ((n & 1) * 2 + 1) * 256;   // [half][row] partial sums of this item
+      float* xm = xch;         // [half][row] partial maxima of this item
+      float* xs = xch + 256;   // [half][row] partial sums (read one item later)
       mbar_wait(&s_full[st], (n >> 1) & 1);
       tc_fence_after();
       // this thread's half of the score row -> registers (<= 4 chunks of 32 columns)
@@ -657,8 +655,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
       xm[half * 128 + r] = mx;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mx = fmaxf(xm[r], xm[128 + r]);
+      const float l_prev = xs[r] + xs[128 + r];          // row sum of the previous item (both halves)
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone has read xm / xs: they may be overwritten
       // O of the previous item (its P*V has long finished): frees the P buffer for this item as a side effect
-      if (n > 0) finish(n - 1);
+      if (n > 0) finish(n - 1, l_prev);
       const float mc = mx * c2;
       float rowsum = 0.f;
 #pragma unroll
@@ -686,7 +686,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
           }
         }
       }
-      xs[half * 128 + r] = rowsum;   // read by both halves in finish(n), i.e. after the next item's bar.sync
+      xs[half * 128 + r] = rowsum;   // read by both halves after the next item's first bar.sync
       prev_m = mx;
       prev_it = it;
       fence_proxy_async_smem();
@@ -695,7 +695,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __re
     }
     if (n > 0) {
       asm volatile("bar.sync 1, 256;" ::: "memory");  // partial sums of the last item are visible
-      finish(n - 1);
+      finish(n - 1, xch[256 + r] + xch[256 + 128 + r]);
     }
   }
 
