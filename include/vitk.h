@@ -78,8 +78,8 @@ typedef struct vitk_gemm_args {
   int32_t prefix;      /* PATCH: number of prefix (cls/dist) tokens                                */
   int32_t splits;      /* ATOMIC: split-K factor, 0 = choose to fill 148 SMs                       */
   int32_t block_n;     /* 0 = auto; otherwise 128, 192 or 256                                      */
-  float* colsum_out;   /* ATOMIC: colsum_out[m] += sum_k A[k, m] (the bias gradient of the same wgrad,
-                          computed by one extra N=16 MMA against a tile of ones), or NULL          */
+  float* colsum_out;   /* ATOMIC with MN-major A: colsum_out[m] += sum_k A[k, m] (the bias gradient of the same
+                          wgrad, summed out of the staged smem tiles by the epilogue warps), or NULL */
 } vitk_gemm_args;
 
 int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);

@@ -369,9 +369,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool ROLES_HI = true;
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
-  // wgrad (EPI_ATOMIC) runs ~one unit per CTA: a single accumulator stage frees TMEM columns for the bias-gradient
-  // accumulator (16 columns at BLOCK_N) that an extra N=16 MMA against a tile of ones fills.
-  constexpr int ACC_STAGES = (EPI == EPI_ATOMIC) ? 1 : 2;
+  constexpr int ACC_STAGES = 2;
+  // wgrad with a fused bias gradient (EPI_ATOMIC, A MN-major): the otherwise idle epilogue warps are a second
+  // consumer of every smem stage.  Once the MMAs of a stage have retired (mma_done) they add up the columns of the
+  // A tile (= dY) straight out of shared memory and only then hand the slot back to the TMA producer.
+  constexpr bool CS = (EPI == EPI_ATOMIC) && A_MN;
   static_assert(!CTA2 || (BLOCK_N % 128 == 0), "CTA pairs need BLOCK_N in {128, 256}");
   constexpr int PARTS = EW / 4;             // column partitions of the tile among epilogue warps
   constexpr int PART_N = BLOCK_N / PARTS;   // columns per epilogue warp
@@ -386,7 +388,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* mma_done = tmem_empty + 2;  // [STAGES], used when CS
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + STAGES);
 
   const int hw_warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -401,7 +404,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int s = 0; s < STAGES; ++s) {
       // CTA2: the leader's barrier collects its own arrive.expect_tx plus the peer producer's remote arrive
       mbar_init(&full_bar[s], CTA2 ? 2 : 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS ? EW : 1);  // CS: the epilogue warps release the slot after their column sums
+      mbar_init(&mma_done[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -418,14 +422,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tmem_relinquish();
     }
   }
-  if constexpr (EPI == EPI_ATOMIC) {
-    // 16 rows x 128 B of bf16 ones (layout-agnostic B operand of the column-sum MMA); lives in the staging area,
-    // which the unstaged red.add epilogue does not use
-    if (warp >= 4) {
-      for (int i = threadIdx.x & (EW * 32 - 1); i < 2048 / 16; i += EW * 32)
-        reinterpret_cast<uint4*>(stg_base)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-      fence_proxy_async_smem();
-    }
+  if constexpr (CS) {
+    for (int i = threadIdx.x; i < BLOCK_M; i += blockDim.x) reinterpret_cast<float*>(stg_base)[i] = 0.f;
   }
   tc_fence_before();
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
@@ -514,12 +512,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int split = unit % p.splits;
         const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
-        // the n_blk == 0 tile of every row of tiles also accumulates the bias gradient.  (Spreading these MMAs over
-        // all n-tiles was measured 2x slower: every N=16 MMA interleaved into the N=256 stream stalls the pipe.)
-        const bool colsum = (EPI == EPI_ATOMIC) && p.colsum_out != nullptr && ((unit / p.splits) % p.num_n_tiles == 0);
-        uint32_t accum_cs = 0;
-        constexpr uint32_t idesc_cs = umma_idesc(TILE_M, 16, 1, A_MN, false);
-        const uint64_t ones_desc = umma_desc_kmajor(smem_u32(stg_base));
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -532,17 +524,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             if constexpr (CTA2) umma_bf16_ss_2cta(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
             else umma_bf16_ss(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
-            if constexpr (EPI == EPI_ATOMIC) {
-              if (colsum) {
-                if constexpr (CTA2) umma_bf16_ss_2cta(tmem_base + BLOCK_N, adesc0 + soff + k * A_KSTEP, ones_desc, idesc_cs, accum_cs);
-                else umma_bf16_ss(tmem_base + BLOCK_N, adesc0 + soff + k * A_KSTEP, ones_desc, idesc_cs, accum_cs);
-                accum_cs = 1;
-              }
-            }
             accum = 1;
           }
-          // frees the smem slot (in both CTAs) once these MMAs retire
-          if constexpr (CTA2) umma_commit_2cta_mc(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+          // once these MMAs retire: free the smem slot (in both CTAs), or (CS) wake the column-sum warps that free it
+          uint64_t* done_bar = CS ? &mma_done[stage] : &empty_bar[stage];
+          if constexpr (CTA2) umma_commit_2cta_mc(done_bar, 3); else umma_commit(done_bar);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
@@ -557,11 +543,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int part = ew >> 2;        // column partition of the tile
     int as = 0;
     uint32_t aphase = 0;
+    int cstage = 0;
+    uint32_t cphase = 0;
     for (int unit = unit0; unit < total_units; unit += ustride) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = tile / p.num_n_tiles;
       const int row = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32 + lane;
+      if constexpr (CS) {
+        // second consumer of the smem ring: per k-block wait for the MMAs, (n_blk == 0 tiles only) add this thread's
+        // 8 columns x 4 k-rows of the swizzled MN-major A tile, then release the slot to the producer
+        const int split = unit % p.splits;
+        const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
+        const bool colsum = p.colsum_out != nullptr && n_blk == 0;
+        const int et = ew * 32 + lane;   // 0..255
+        const int m8 = et & 15;          // 8-column group of the 128 tile rows (MN index)
+        const int kg = et >> 4;          // k rows kg, kg+16, kg+32, kg+48
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&mma_done[cstage], cphase);
+          if (colsum) {
+            const uint8_t* sA = smem + cstage * Cfg::STAGE_BYTES + (m8 >> 3) * (BLOCK_K * 128);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = kg + i * 16;
+              const uint4 u = *reinterpret_cast<const uint4*>(sA + k * 128 + (((m8 & 7) ^ (k & 7)) << 4));
+              const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+              cs[0] += a.x; cs[1] += a.y; cs[2] += b.x; cs[3] += b.y;
+              cs[4] += c.x; cs[5] += c.y; cs[6] += d.x; cs[7] += d.y;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[cstage]);
+          if (++cstage == STAGES) { cstage = 0; cphase ^= 1; }
+        }
+        if (colsum) {
+          float* red = reinterpret_cast<float*>(stg_base);  // [BLOCK_M], zero on entry
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(red + m8 * 8 + j, cs[j]);
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+          if (et < BLOCK_M) {
+            const int r = m_blk * TILE_M + (int)rank * BLOCK_M + et;
+            if (r < p.M) atomicAdd(p.colsum_out + r, red[et]);
+            red[et] = 0.f;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+        }
+      }
       float rs = 1.0f;
       if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID || EPI == EPI_DGELU) {
         if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
@@ -613,14 +642,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           else tmem_ld_32x16(taddr, acc);
           tmem_ld_wait();
           epilogue_chunk<EPI, W>(p, acc, row, n_blk * BLOCK_N + col_in_tile, rs);
-        }
-      }
-      if constexpr (EPI == EPI_ATOMIC) {
-        if (p.colsum_out != nullptr && n_blk == 0 && part == 0) {
-          uint32_t cs[16];
-          tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + BLOCK_N, cs);
-          tmem_ld_wait();
-          if (row < p.M) atomicAdd(p.colsum_out + row, __uint_as_float(cs[0]));
         }
       }
       tc_fence_before();
@@ -701,7 +722,7 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   p.pos = a->pos; p.tokens_per_img = a->tokens_per_img > 0 ? a->tokens_per_img : 1;
   p.prefix = a->prefix;
   p.ragged = (EPI == EPI_F32 && (a->N % 8 != 0 || a->ld_out % 4 != 0)) ? 1 : 0;
-  p.colsum_out = (EPI == EPI_ATOMIC) ? a->colsum_out : nullptr;
+  p.colsum_out = (EPI == EPI_ATOMIC && A_MN) ? a->colsum_out : nullptr;
 
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI, EW, CTA2>;
   static bool attr_set = false;  // per-instantiation
