@@ -45,7 +45,8 @@ def test_attn_fwd(cuda_device, B, N, H):
     assert rel_err(lse, ref_lse) < 5e-3
 
 
-@pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 100, 2)])
+@pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 100, 2),
+                                   (2, 577, 4), (1, 300, 2), (1, 640, 1)])
 def test_attn_bwd(cuda_device, B, N, H):
     from vision_transformers_torch_xla_b200 import _lib as L
     hd = 64

@@ -22,7 +22,7 @@ EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_ATOMIC, EPI_PATCH = range
 #: every symbol include/vitk.h declares (tests check the library exports exactly these)
 EXPORTED_SYMBOLS = (
     "vitk_abi_version", "vitk_last_error", "vitk_arch", "vitk_gemm_bf16", "vitk_layernorm_fwd",
-    "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_patchify", "vitk_prefix_rows",
+    "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_attn_bwd_workspace_bytes", "vitk_patchify", "vitk_prefix_rows",
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
 )
@@ -72,8 +72,10 @@ def load() -> ctypes.CDLL:
                                        c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p,
                                        c_void_p, c_int64, c_int32, c_void_p]
     lib.vitk_attn_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p]
-    lib.vitk_attn_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+    lib.vitk_attn_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                   c_int32, c_float, c_void_p]
+    lib.vitk_attn_bwd_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    lib.vitk_attn_bwd_workspace_bytes.restype = c_int64
     lib.vitk_patchify.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_prefix_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_embed_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
@@ -91,7 +93,7 @@ def load() -> ctypes.CDLL:
     lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version"):
+        if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version", "vitk_attn_bwd_workspace_bytes"):
             fn.restype = c_int32
     _lib = lib
     return lib
@@ -271,9 +273,11 @@ def attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torc
              B: int, N: int, H: int, hd: int, scale: float) -> None:
     for t, nm in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, f"attn_bwd {nm}")
+    ws_bytes = load().vitk_attn_bwd_workspace_bytes(B, N, H, hd)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=qkv.device) if ws_bytes > 0 else None
     with _Timed("attn_bwd"):
         _check(load().vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                    B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
+                                    _ptr(ws), B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
     _count()
 
 

@@ -983,6 +983,233 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   }
 }
 
+// ================================================================================================
+// Backward, streaming variant for 256 < N <= 640 (ViT-L/16 at 384 px: N = 577): one CTA per (b, h, kv tile j).
+// K_j / V_j stay resident, Q_i / dO_i stream through one smem buffer, dV_j / dK_j accumulate in TMEM over the
+// q tiles, and each dQ_ij partial is read out of a TMEM scratch tile and red.add'ed into an fp32 workspace
+// [B, N, H*64] (the q rows are shared by the T CTAs of a head); a small kernel then casts it into dqkv.
+// TMEM: S [0,128) | dP [128,256) | dV_j [256,320) | dK_j [320,384) | dQ_ij [384,448)
+// ================================================================================================
+struct BwdStreamSmem {
+  static constexpr uint32_t KV_OFF = 0;
+  static constexpr uint32_t QDO_OFF = 2 * TILE_BYTES;
+  static constexpr uint32_t P_OFF = 4 * TILE_BYTES;
+  static constexpr uint32_t DS_OFF = 6 * TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = 8 * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 128;
+};
+
+__global__ void __launch_bounds__(128)
+attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                       const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                       const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq32,
+                       int N, int H, float scale) {
+  using L = BwdStreamSmem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* bar_q = bar_kv + 1;
+  uint64_t* bar_sp = bar_q + 1;
+  uint64_t* bar_mma = bar_sp + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nt = (N + TILE - 1) / TILE;
+  const int kvn = min(TILE, N - j * TILE);
+  const uint32_t n_eff = roundup16(kvn);
+  const int nchunks = (int)(n_eff + 31) / 32;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 32) {
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_sp, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320;
+  const uint32_t tm_dq = tmem_base + 384;
+  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const int r = threadIdx.x;
+  const float c2 = scale * LOG2E;
+  uint8_t* sP = smem + L::P_OFF;
+  uint8_t* sDS = smem + L::DS_OFF;
+  const uint32_t sK = smem_u32(smem + L::KV_OFF), sV = sK + TILE_BYTES;
+  const uint32_t sQ = smem_u32(smem + L::QDO_OFF), sDO = sQ + TILE_BYTES;
+  const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_arrive_expect_tx(bar_kv, 2 * TILE_BYTES);
+    tma_load_3d(smem + L::KV_OFF, &tm_qkv, bar_kv, (H + h) * HD, j * TILE, b);
+    tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, (2 * H + h) * HD, j * TILE, b);
+  }
+
+  for (int i = 0; i < nt; ++i) {
+    const int qn = min(TILE, N - i * TILE);
+    const uint32_t q_eff = roundup16(qn);
+    const bool row_ok = r < qn;
+    const int q = i * TILE + r;
+    if (threadIdx.x == 0) {
+      // Q_i / dO_i buffer is free: the previous iteration ended with a CTA-wide sync after its MMAs retired
+      mbar_arrive_expect_tx(bar_q, 2 * TILE_BYTES);
+      tma_load_3d(smem + L::QDO_OFF, &tm_qkv, bar_q, h * HD, i * TILE, b);
+      tma_load_3d(smem + L::QDO_OFF + TILE_BYTES, &tm_do, bar_q, h * HD, i * TILE, b);
+    }
+    float my_lse2 = 0.f, my_d = 0.f;
+    if (row_ok) {
+      my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
+      const uint4* op = reinterpret_cast<const uint4*>(out + ((long long)b * N + q) * (H * HD) + h * HD);
+      const uint4* dp = reinterpret_cast<const uint4*>(dout + ((long long)b * N + q) * (H * HD) + h * HD);
+      float acc = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 a = __ldg(op + g), d = __ldg(dp + g);
+        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+        acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+      }
+      my_d = acc;
+    }
+    if (threadIdx.x == 0) {
+      if (i == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, i & 1);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16_ss(tm_s, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc, k > 0);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16_ss(tm_dp, umma_desc_kmajor(sDO + k * 32), umma_desc_kmajor(sV + k * 32), idesc, k > 0);
+      umma_commit(bar_sp);
+    }
+    mbar_wait(bar_sp, i & 1);
+    tc_fence_after();
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32(tm_s + lane_addr + c * 32, sv);
+      tmem_ld_32x32(tm_dp + lane_addr + c * 32, dv);
+      tmem_ld_wait();
+      if ((uint32_t)r < q_eff) {
+        float p[32], ds[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const bool ok = row_ok && (c * 32 + k < kvn);
+          const float e = ex2_approx(fmaf(__uint_as_float(sv[k]), c2, -my_lse2));
+          p[k] = ok ? e : 0.f;
+          ds[k] = ok ? e * (__uint_as_float(dv[k]) - my_d) * scale : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+            uint4 u, w;
+            u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
+            u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
+            u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
+            u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
+            w.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]);
+            w.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
+            w.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]);
+            w.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
+            st_swz(sP, r, c * 4 + g, u);
+            st_swz(sDS, r, c * 4 + g, w);
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);
+      const int qsteps = (int)q_eff / 16;
+      for (int k = 0; k < qsteps; ++k)
+        umma_bf16_ss(tm_dv, umma_desc_mnmajor(sP_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sDO + k * 2048, TILE_BYTES),
+                     idesc_t, (i > 0 || k > 0));
+      for (int k = 0; k < qsteps; ++k)
+        umma_bf16_ss(tm_dk, umma_desc_mnmajor(sDS_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sQ + k * 2048, TILE_BYTES),
+                     idesc_t, (i > 0 || k > 0));
+      const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);
+      for (int k = 0; k < (int)n_eff / 16; ++k)
+        umma_bf16_ss(tm_dq, umma_desc_kmajor(sDS_u + (k >> 2) * TILE_BYTES + (k & 3) * 32),
+                     umma_desc_mnmajor(sK + k * 2048, TILE_BYTES), idesc_q, k > 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, i & 1);
+    tc_fence_after();
+    {
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(tm_dq + lane_addr, a0);
+      tmem_ld_32x32(tm_dq + lane_addr + 32, a1);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dst = dq32 + ((long long)b * N + q) * (H * HD) + h * HD;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(a0[g * 4])),
+                       "f"(__uint_as_float(a0[g * 4 + 1])), "f"(__uint_as_float(a0[g * 4 + 2])),
+                       "f"(__uint_as_float(a0[g * 4 + 3]))
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 + g * 4), "f"(__uint_as_float(a1[g * 4])),
+                       "f"(__uint_as_float(a1[g * 4 + 1])), "f"(__uint_as_float(a1[g * 4 + 2])),
+                       "f"(__uint_as_float(a1[g * 4 + 3]))
+                       : "memory");
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // Q_i / dO_i / P / dS / dQ scratch may be overwritten by the next q tile
+    tc_fence_after();
+  }
+
+  {
+    uint32_t a0[32], a1[32];
+    const int kv = j * TILE + r;
+    tmem_ld_32x32(tm_dv + lane_addr, a0);
+    tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
+    tmem_ld_wait();
+    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (2 * H + h) * HD, a0, a1);
+    tmem_ld_32x32(tm_dk + lane_addr, a0);
+    tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
+    tmem_ld_wait();
+    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (H + h) * HD, a0, a1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// dqkv[row, 0:D] = bf16(dq32[row, 0:D])  (row pitch of dqkv is 3*D)
+__global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int D) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int dv = D / 8;
+  if (idx >= rows * dv) return;
+  const long long row = idx / dv;
+  const int c = (int)(idx % dv) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(dq32 + row * D + c);
+  const float4 b2 = *reinterpret_cast<const float4*>(dq32 + row * D + c + 4);
+  uint4 u;
+  u.x = pack_bf16x2(a.x, a.y);
+  u.y = pack_bf16x2(a.z, a.w);
+  u.z = pack_bf16x2(b2.x, b2.y);
+  u.w = pack_bf16x2(b2.z, b2.w);
+  *reinterpret_cast<uint4*>(dqkv + row * 3 * D + c) = u;
+}
+
 template <int T>
 int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
   auto kern = attn_fwd_kernel<T>;
@@ -1028,11 +1255,17 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   }
 }
 
-extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int32_t B,
-                             int32_t N, int32_t H, int32_t head_dim, float scale, void* stream) {
+extern "C" int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim) {
+  if (N <= BWD_MAX_T * TILE) return 0;
+  return (int64_t)B * N * H * head_dim * (int64_t)sizeof(float);
+}
+
+extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                             void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
+                             void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_REQUIRE(head_dim == HD, VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (only 64 is built)", head_dim);
-  VITK_REQUIRE(N <= BWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_bwd: N=%d > %d not built yet", N, BWD_MAX_T * TILE);
+  VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_bwd: N=%d > %d", N, FWD_MAX_T * TILE);
   VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
                VITK_ERR_ALIGN, "attn_bwd: unaligned");
   CUtensorMap tm_qkv, tm_do;
@@ -1047,8 +1280,28 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem::BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd2Smem::BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (N > BWD_MAX_T * TILE) {
+    VITK_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, VITK_ERR_ALIGN,
+                 "attn_bwd: N=%d needs a 16-byte aligned workspace of vitk_attn_bwd_workspace_bytes()", N);
+    const long long rows = (long long)B * N;
+    const int D = H * HD;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)rows * D * sizeof(float), st);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: memset: %s", cudaGetErrorString(e));
+    dim3 grid((N + TILE - 1) / TILE, H, B);
+    attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
+                                                                    (const __nv_bfloat16*)dout, lse, (__nv_bfloat16*)dqkv,
+                                                                    (float*)workspace, N, H, scale);
+    rc = vitk_check_launch("attn_bwd_stream");
+    if (rc) return rc;
+    const long long n8 = rows * (D / 8);
+    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>((const float*)workspace, (__nv_bfloat16*)dqkv, rows, D);
+    return vitk_check_launch("attn_bwd_dq_cast");
   }
   dim3 grid(H, B);
   static const bool two_wg = [] {
@@ -1058,13 +1311,11 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     return e && e[0] == '2';
   }();
   if (two_wg) {
-    attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, (cudaStream_t)stream>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
-                                                                           (const __nv_bfloat16*)dout, lse,
-                                                                           (__nv_bfloat16*)dqkv, N, H, scale);
+    attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
+                                                         lse, (__nv_bfloat16*)dqkv, N, H, scale);
     return vitk_check_launch("attn_bwd2");
   }
-  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, (cudaStream_t)stream>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
-                                                                       (const __nv_bfloat16*)dout, lse,
-                                                                       (__nv_bfloat16*)dqkv, N, H, scale);
+  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse,
+                                                     (__nv_bfloat16*)dqkv, N, H, scale);
   return vitk_check_launch("attn_bwd");
 }
