@@ -176,6 +176,10 @@ int vitk_adamw_flat(float* p, float* g, float* m, float* v, void* shadow_bf16, f
                     const float* lr, const float* wd, float beta1, float beta2, float eps,
                     int64_t step, float grad_scale, float ema_decay, int32_t zero_grad,
                     void* stream);
+/* Tuning aid: when non-NULL, the first CTA of the attention kernels stamps clock64() at its phase boundaries into
+ * this device buffer of >= 32 int64 (tools/attn_trace.py prints the timeline).  NULL (default) disables it. */
+void vitk_debug_set_trace(long long* device_buf);
+
 /* out[0] += sum_i x[i]^2 (for clip_grad_norm_) */
 int vitk_sumsq(const float* x, int64_t n, float* out, void* stream);
 

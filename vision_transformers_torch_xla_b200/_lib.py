@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_attn_bwd_workspace_bytes", "vitk_patchify", "vitk_prefix_rows",
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
+    "vitk_debug_set_trace",
 )
 
 
@@ -91,9 +92,12 @@ def load() -> ctypes.CDLL:
                                     c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_float, c_float, c_float,
                                     c_int64, c_float, c_float, c_int32, c_void_p]
     lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.vitk_debug_set_trace.argtypes = [c_void_p]
+    lib.vitk_debug_set_trace.restype = None
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version", "vitk_attn_bwd_workspace_bytes"):
+        if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version", "vitk_attn_bwd_workspace_bytes",
+                        "vitk_debug_set_trace"):
             fn.restype = c_int32
     _lib = lib
     return lib

@@ -30,6 +30,14 @@ constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t roundup16(int v) { return (uint32_t)((v + 15) & ~15); }
 
+// Phase timeline for tuning (vitk_debug_set_trace): the first CTA's thread 0 stamps clock64() into a device buffer.
+long long* g_trace_buf = nullptr;
+#define VITK_STAMP(slot)                                                                    \
+  do {                                                                                      \
+    if (trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) \
+      trace[(slot)] = clock64();                                                            \
+  } while (0)
+
 // Store 8 consecutive bf16 (one 16-byte unit `u8` of row `r`) into a [chunk][128 rows][128 B] swizzled tile.
 __device__ __forceinline__ void st_swz(uint8_t* tile, int r, int col8, uint4 val) {
   const int chunk = col8 >> 3;  // 64-column chunk
@@ -54,7 +62,8 @@ struct FwdSmem {
 template <int T>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                float* __restrict__ lse, int N, int H, float scale) {
+                float* __restrict__ lse, int N, int H, float scale, long long* trace) {
+  VITK_STAMP(0);
   using L = FwdSmem<T>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -85,6 +94,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;         // S: 128 columns
   const uint32_t tmem_o = tmem_base + 128;   // O_j: 64 columns
+  VITK_STAMP(1);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -127,6 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     }
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
+    VITK_STAMP(2 + j * 4);
 
     // ---- online softmax over this kv tile: pass 1 row max, pass 2 exponentials -> P (bf16, smem) ----
     const int nchunks = (int)(n_eff + 31) / 32;
@@ -169,10 +180,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     }
     l_run = l_run * alpha + rowsum;
     m_run = mx;
+    VITK_STAMP(3 + j * 4);
 
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+    VITK_STAMP(4 + j * 4);
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
@@ -185,6 +198,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     }
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
+    VITK_STAMP(5 + j * 4);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t ov[32];
@@ -211,12 +225,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     }
     if (lse) lse[((long long)b * H + h) * N + q] = m_run * scale + __logf(l_run);
   }
+  VITK_STAMP(30);
 
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+  VITK_STAMP(31);
 }
 
 // ================================================================================================
@@ -257,8 +273,10 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+                const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale,
+                long long* trace) {
   using L = BwdSmem;
+  VITK_STAMP(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* bar_sp = bar_ld + 1;
@@ -331,6 +349,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint32_t sp_phase = 0;
 
   // issue S = Q_i K_j^T and dP = dO_i V_j^T
+  VITK_STAMP(1);
   auto issue_s_dp = [&](int j, int i) {
     const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
     const uint32_t sQ = smem_u32(smem + L::QDO_OFF + i * 2 * TILE_BYTES), sDO = sQ + TILE_BYTES;
@@ -348,6 +367,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_wait(bar_ld, 0);
     tc_fence_after();
+    VITK_STAMP(2);
     issue_s_dp(0, 0);
   }
 
@@ -366,6 +386,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_wait(bar_sp, sp_phase);
       sp_phase ^= 1;
       tc_fence_after();
+      VITK_STAMP(3 + (j * 2 + i) * 4);
 
       // every thread executes the (.sync.aligned) TMEM loads; only rows < q_eff compute and store
       for (int c = 0; c < nchunks; ++c) {
@@ -401,9 +422,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
       }
 
+      VITK_STAMP(4 + (j * 2 + i) * 4);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
+      VITK_STAMP(5 + (j * 2 + i) * 4);
       if (threadIdx.x == 0) {
         tc_fence_after();
         const uint32_t sQ = smem_u32(smem + L::QDO_OFF + i * 2 * TILE_BYTES), sDO = sQ + TILE_BYTES;
@@ -430,6 +453,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         int ni = i + 1, nj = j;
         if (ni == nt) { ni = 0; nj = j + 1; }
         if (nj < nt) issue_s_dp(nj, ni);
+        VITK_STAMP(6 + (j * 2 + i) * 4);
       }
     }
 
@@ -437,6 +461,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     // tcgen05 ops retire in issue order, so this also covers every earlier MMA of this kv tile.
     mbar_wait(bar_drain, j & 1);
     tc_fence_after();
+    VITK_STAMP(20 + j * 2);
     {
       uint32_t a0[32], a1[32];
       tmem_ld_32x32(tm_dv + lane_addr, a0);
@@ -452,6 +477,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     // NOTE: the next kv tile's dV/dK MMAs (accumulate = 0) are only issued after the next
     // iteration's __syncthreads, i.e. after every thread finished these TMEM reads.
     tc_fence_before();
+    VITK_STAMP(21 + j * 2);
   }
 
   // ---- drain dQ_i ----
@@ -465,12 +491,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     if (q < N) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * HD) + h * HD, a0, a1);
   }
 
+  VITK_STAMP(30);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  VITK_STAMP(31);
 }
 
 // ================================================================================================
@@ -1220,7 +1248,7 @@ int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H
     attr_set = true;
   }
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  kern<<<grid, 128, FwdSmem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale);
+  kern<<<grid, 128, FwdSmem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale, g_trace_buf);
   return vitk_check_launch("attn_fwd");
 }
 
@@ -1254,6 +1282,8 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
     default: return launch_fwd<5>(tm, out, lse, B, N, H, scale, s);
   }
 }
+
+extern "C" void vitk_debug_set_trace(long long* device_buf) { g_trace_buf = device_buf; }
 
 extern "C" int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim) {
   if (N <= BWD_MAX_T * TILE) return 0;
@@ -1316,6 +1346,6 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     return vitk_check_launch("attn_bwd2");
   }
   attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse,
-                                                     (__nv_bfloat16*)dqkv, N, H, scale);
+                                                     (__nv_bfloat16*)dqkv, N, H, scale, g_trace_buf);
   return vitk_check_launch("attn_bwd");
 }
