@@ -750,6 +750,34 @@ int launch_fwd2(const CUtensorMap& tm, void* out, float* lse, int B, int N, int 
   return vitk_check_launch("attn_fwd2");
 }
 
+// D[b, h, n] = sum_d O[b, n, h, d] * dO[b, n, h, d]: one warp per token row, fully coalesced 16-byte loads.
+// (Computing it inside the backward kernel costs ~10k cycles of exposed, row-strided global loads per CTA.)
+__global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                 float* __restrict__ dsum, long long rows, int N, int H) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const long long b = row / N;
+  const int n = (int)(row - b * N);
+  const uint4* op = reinterpret_cast<const uint4*>(out + row * (long long)(H * HD));
+  const uint4* dp = reinterpret_cast<const uint4*>(dout + row * (long long)(H * HD));
+  const int nchunk = H * HD / 8;  // 16-byte chunks per row; 8 chunks per head
+  for (int c0 = 0; c0 < nchunk; c0 += 32) {
+    const int c = c0 + lane;
+    float s = 0.f;
+    if (c < nchunk) {
+      const uint4 a = __ldg(op + c), d = __ldg(dp + c);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+      s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0 && c < nchunk) dsum[(b * H + (c >> 3)) * N + n] = s;
+  }
+}
+
 // ================================================================================================
 // Backward, two-warpgroup variant (N <= 256): one CTA per (b, h), 288 threads.
 //   warpgroup w (warps 4w..4w+3) owns q tile w: thread r holds row r's probabilities in registers between the
@@ -768,11 +796,12 @@ struct Bwd2Smem {
   static constexpr uint32_t BYTES = BAR_OFF + 256;
 };
 
-__global__ void __launch_bounds__(288, 1)
+__global__ void __maxnreg__(224)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                 const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                 const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale) {
+                 const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                 int N, int H, float scale, long long* trace) {
   using L = Bwd2Smem;
+  VITK_STAMP(0);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* bar_s = bar_ld + 1;        // [2] MMA -> WG: S_w ready
@@ -894,18 +923,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     float my_lse2 = 0.f, my_d = 0.f;
     if (row_ok) {
       my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
-      const uint4* op = reinterpret_cast<const uint4*>(out + ((long long)b * N + q) * (H * HD) + h * HD);
-      const uint4* dp = reinterpret_cast<const uint4*>(dout + ((long long)b * N + q) * (H * HD) + h * HD);
-      float acc = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 a = __ldg(op + g), d = __ldg(dp + g);
-        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
-        acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
-      }
-      my_d = acc;
+      my_d = dsum[((long long)b * H + h) * N + q];
     }
+    VITK_STAMP(1);
 
     for (int j = 0; j < nt; ++j) {
       const int kvn = min(TILE, N - j * TILE);
@@ -916,28 +936,38 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       // ---- phase 1: S -> P (registers + smem) ----
       mbar_wait(&bar_s[w], j & 1);
       tc_fence_after();
+      VITK_STAMP(2 + j * 6);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nchunks) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tm_sdp + c * 32, sv);
+      for (int cb = 0; cb < 4; cb += 2) {
+        if (cb < nchunks) {
+          // two 32-column chunks per TMEM round trip
+          uint32_t sv[2][32];
+          tmem_ld_32x32(tm_sdp + cb * 32, sv[0]);
+          if (cb + 1 < nchunks) tmem_ld_32x32(tm_sdp + (cb + 1) * 32, sv[1]);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const bool ok0 = row_ok && (c * 32 + 2 * k < kvn), ok1 = row_ok && (c * 32 + 2 * k + 1 < kvn);
-            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[2 * k]), c2, -my_lse2));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[2 * k + 1]), c2, -my_lse2));
-            pk[c * 16 + k] = pack_bf16x2(ok0 ? e0 : 0.f, ok1 ? e1 : 0.f);
-          }
-          if ((uint32_t)r < q_eff) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = cb + cc;
+            if (c < nchunks) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if ((uint32_t)(c * 32 + g * 8) < n_eff)
-                st_swz(sPDS, r, c * 4 + g, make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2],
-                                                      pk[c * 16 + g * 4 + 3]));
+              for (int k = 0; k < 16; ++k) {
+                const bool ok0 = row_ok && (c * 32 + 2 * k < kvn), ok1 = row_ok && (c * 32 + 2 * k + 1 < kvn);
+                const float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * k]), c2, -my_lse2));
+                const float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * k + 1]), c2, -my_lse2));
+                pk[c * 16 + k] = pack_bf16x2(ok0 ? e0 : 0.f, ok1 ? e1 : 0.f);
+              }
+              if ((uint32_t)r < q_eff) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if ((uint32_t)(c * 32 + g * 8) < n_eff)
+                    st_swz(sPDS, r, c * 4 + g, make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2],
+                                                          pk[c * 16 + g * 4 + 3]));
+              }
+            }
           }
         }
       }
+      VITK_STAMP(3 + j * 6);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bar_p[w]);
@@ -945,27 +975,34 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       // ---- phase 2: dP -> dS (smem, over P) ----
       mbar_wait(&bar_dp[w], j & 1);
       tc_fence_after();
+      VITK_STAMP(4 + j * 6);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nchunks) {
-          uint32_t dv[32];
-          tmem_ld_32x32(tm_sdp + c * 32, dv);
+      for (int cb = 0; cb < 4; cb += 2) {
+        if (cb < nchunks) {
+          uint32_t dv[2][32];
+          tmem_ld_32x32(tm_sdp + cb * 32, dv[0]);
+          if (cb + 1 < nchunks) tmem_ld_32x32(tm_sdp + (cb + 1) * 32, dv[1]);
           tmem_ld_wait();
-          if ((uint32_t)r < q_eff) {
-            uint32_t ds[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const float2 pp = unpack_bf16x2(pk[c * 16 + k]);
-              ds[k] = pack_bf16x2(pp.x * (__uint_as_float(dv[2 * k]) - my_d) * scale,
-                                  pp.y * (__uint_as_float(dv[2 * k + 1]) - my_d) * scale);
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = cb + cc;
+            if (c < nchunks && (uint32_t)r < q_eff) {
+              uint32_t ds[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float2 pp = unpack_bf16x2(pk[c * 16 + k]);
+                ds[k] = pack_bf16x2(pp.x * (__uint_as_float(dv[cc][2 * k]) - my_d) * scale,
+                                    pp.y * (__uint_as_float(dv[cc][2 * k + 1]) - my_d) * scale);
+              }
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                if ((uint32_t)(c * 32 + g * 8) < n_eff)
+                  st_swz(sPDS, r, c * 4 + g, make_uint4(ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]));
             }
-#pragma unroll
-            for (int g = 0; g < 4; ++g)
-              if ((uint32_t)(c * 32 + g * 8) < n_eff)
-                st_swz(sPDS, r, c * 4 + g, make_uint4(ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]));
           }
         }
       }
+      VITK_STAMP(5 + j * 6);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bar_ds[w]);
@@ -973,6 +1010,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       // ---- drain dV_j (warpgroup 0) / dK_j (warpgroup 1, or 0 when it is alone) ----
       mbar_wait(bar_drain, j & 1);
       tc_fence_after();
+      VITK_STAMP(6 + j * 6);
       {
         const int kv = j * TILE + r;
         uint32_t a0[32], a1[32];
@@ -991,6 +1029,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(bar_drained);
+      VITK_STAMP(7 + j * 6);
     }
 
     // ---- dQ_w (the last bar_drain wait above covers every MMA) ----
@@ -1001,6 +1040,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       tmem_ld_wait();
       if (row_ok) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * HD) + h * HD, a0, a1);
     }
+    VITK_STAMP(30);
   }
 
   tc_fence_before();
@@ -1009,6 +1049,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  VITK_STAMP(31);
 }
 
 // ================================================================================================
@@ -1285,9 +1326,15 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
 
 extern "C" void vitk_debug_set_trace(long long* device_buf) { g_trace_buf = device_buf; }
 
+static int64_t dsum_bytes(int32_t B, int32_t N, int32_t H) {
+  return (((int64_t)B * H * N * (int64_t)sizeof(float)) + 255) / 256 * 256;
+}
+
 extern "C" int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim) {
-  if (N <= BWD_MAX_T * TILE) return 0;
-  return (int64_t)B * N * H * head_dim * (int64_t)sizeof(float);
+  // D = rowsum(O * dO) [B, H, N] fp32, plus (N > 256) the fp32 dQ accumulator [B, N, H*hd]
+  int64_t bytes = dsum_bytes(B, N, H);
+  if (N > BWD_MAX_T * TILE) bytes += (int64_t)B * N * H * head_dim * (int64_t)sizeof(float);
+  return bytes;
 }
 
 extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -1316,21 +1363,30 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     attr_set = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  VITK_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, VITK_ERR_ALIGN,
+               "attn_bwd: needs a 16-byte aligned workspace of vitk_attn_bwd_workspace_bytes()");
+  float* dsum = reinterpret_cast<float*>(workspace);
+  float* dq32 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + dsum_bytes(B, N, H));
+  {
+    const long long rows = (long long)B * N;
+    attn_dsum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, dsum,
+                                                                 rows, N, H);
+    rc = vitk_check_launch("attn_dsum");
+    if (rc) return rc;
+  }
   if (N > BWD_MAX_T * TILE) {
-    VITK_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, VITK_ERR_ALIGN,
-                 "attn_bwd: N=%d needs a 16-byte aligned workspace of vitk_attn_bwd_workspace_bytes()", N);
     const long long rows = (long long)B * N;
     const int D = H * HD;
-    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)rows * D * sizeof(float), st);
+    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * D * sizeof(float), st);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: memset: %s", cudaGetErrorString(e));
     dim3 grid((N + TILE - 1) / TILE, H, B);
     attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
                                                                     (const __nv_bfloat16*)dout, lse, (__nv_bfloat16*)dqkv,
-                                                                    (float*)workspace, N, H, scale);
+                                                                    dq32, N, H, scale);
     rc = vitk_check_launch("attn_bwd_stream");
     if (rc) return rc;
     const long long n8 = rows * (D / 8);
-    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>((const float*)workspace, (__nv_bfloat16*)dqkv, rows, D);
+    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, D);
     return vitk_check_launch("attn_bwd_dq_cast");
   }
   dim3 grid(H, B);
@@ -1341,8 +1397,8 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     return e && e[0] == '2';
   }();
   if (two_wg) {
-    attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout,
-                                                         lse, (__nv_bfloat16*)dqkv, N, H, scale);
+    attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, scale,
+                                                         g_trace_buf);
     return vitk_check_launch("attn_bwd2");
   }
   attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse,
