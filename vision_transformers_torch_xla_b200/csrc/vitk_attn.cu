@@ -272,8 +272,7 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
 
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale,
+                const float* __restrict__ dsum_g, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale,
                 long long* trace) {
   using L = BwdSmem;
   VITK_STAMP(0);
@@ -317,7 +316,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
   }
 
-  // per-row statistics for the (up to) two q tiles this thread owns a row of
+  // per-row statistics for the (up to) two q tiles this thread owns a row of (D comes from attn_dsum_kernel)
   const int r = threadIdx.x;
   float lse2[BWD_MAX_T], dsum[BWD_MAX_T];
 #pragma unroll
@@ -327,17 +326,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int q = i * TILE + r;
     if (i < nt && q < N) {
       lse2[i] = lse[((long long)b * H + h) * N + q] * LOG2E;
-      const uint4* op = reinterpret_cast<const uint4*>(out + ((long long)b * N + q) * (H * HD) + h * HD);
-      const uint4* dp = reinterpret_cast<const uint4*>(dout + ((long long)b * N + q) * (H * HD) + h * HD);
-      float s = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 a = __ldg(op + g), d = __ldg(dp + g);
-        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
-        s += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
-      }
-      dsum[i] = s;
+      dsum[i] = dsum_g[((long long)b * H + h) * N + q];
     }
   }
 
@@ -796,7 +785,7 @@ struct Bwd2Smem {
   static constexpr uint32_t BYTES = BAR_OFF + 256;
 };
 
-__global__ void __maxnreg__(224)
+__global__ void __maxnreg__(208)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                  const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                  int N, int H, float scale, long long* trace) {
@@ -1401,7 +1390,6 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
                                                          g_trace_buf);
     return vitk_check_launch("attn_bwd2");
   }
-  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, lse,
-                                                     (__nv_bfloat16*)dqkv, N, H, scale, g_trace_buf);
+  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, scale, g_trace_buf);
   return vitk_check_launch("attn_bwd");
 }
