@@ -139,42 +139,52 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     tc_fence_after();
     VITK_STAMP(2 + j * 4);
 
-    // ---- online softmax over this kv tile: pass 1 row max, pass 2 exponentials -> P (bf16, smem) ----
+    // ---- online softmax over this kv tile: the row (<= 128 scores) is read from TMEM once, two chunks per round trip ----
     const int nchunks = (int)(n_eff + 31) / 32;
+    uint32_t sv[4][32];
     float mx = m_run;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t sv[32];
-      tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-      tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (c * 32 + i < kvn) mx = fmaxf(mx, __uint_as_float(sv[i]));
+    for (int cb = 0; cb < 4; cb += 2) {
+      if (cb < nchunks) {
+        tmem_ld_32x32(tmem_s + lane_addr + cb * 32, sv[cb]);
+        if (cb + 1 < nchunks) tmem_ld_32x32(tmem_s + lane_addr + (cb + 1) * 32, sv[cb + 1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = cb + cc;
+          if (c < nchunks) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kvn) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+          }
+        }
+      }
     }
-    const float alpha = exp2f((m_run - mx) * c2);  // 0 on the first tile (m_run = -inf)
+    const float alpha = ex2_approx((m_run - mx) * c2);  // 0 on the first tile (m_run = -inf)
     const float mc = mx * c2;
     float rowsum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t sv[32];
-      tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
-      tmem_ld_wait();
-      float p[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float e = exp2f(fmaf(__uint_as_float(sv[i]), c2, -mc));
-        p[i] = (c * 32 + i < kvn) ? e : 0.f;
-      }
+    for (int c = 0; c < 4; ++c) {
+      if (c < nchunks) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if ((uint32_t)(c * 32 + g * 8) < n_eff) {
-          uint4 u;
-          u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
-          u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-          u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
-          u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-          st_swz(sP, r, c * 4 + g, u);
-          // the row sum uses the bf16-rounded probabilities so that P*V and l stay consistent
-          const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-          rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+        for (int g = 0; g < 4; ++g) {
+          if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+            float p[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float e = ex2_approx(fmaf(__uint_as_float(sv[c][g * 8 + i]), c2, -mc));
+              p[i] = (c * 32 + g * 8 + i < kvn) ? e : 0.f;
+            }
+            uint4 u;
+            u.x = pack_bf16x2(p[0], p[1]);
+            u.y = pack_bf16x2(p[2], p[3]);
+            u.z = pack_bf16x2(p[4], p[5]);
+            u.w = pack_bf16x2(p[6], p[7]);
+            st_swz(sP, r, c * 4 + g, u);
+            // the row sum uses the bf16-rounded probabilities so that P*V and l stay consistent
+            const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
+            rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+          }
         }
       }
     }
@@ -190,10 +200,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
       tc_fence_after();
       const uint32_t idesc = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
       const int ksteps = (int)n_eff / 16;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint32_t a_addr = sP_u + (k >> 2) * TILE_BYTES + (k & 3) * 32;
-        umma_bf16_ss(tmem_o, umma_desc_kmajor(a_addr), umma_desc_mnmajor(sV_u + k * 2048, TILE_BYTES), idesc, k > 0);
-      }
+      const uint64_t pdesc = umma_desc_kmajor(sP_u), vdesc = umma_desc_mnmajor(sV_u, TILE_BYTES);
+#pragma unroll 4
+      for (int k = 0; k < ksteps; ++k)
+        umma_bf16_ss(tmem_o, pdesc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), vdesc + (uint64_t)(k * 128), idesc, k > 0);
       umma_commit(bar_o);
     }
     mbar_wait(bar_o, j & 1);
@@ -377,35 +387,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tc_fence_after();
       VITK_STAMP(3 + (j * 2 + i) * 4);
 
-      // every thread executes the (.sync.aligned) TMEM loads; only rows < q_eff compute and store
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tm_s + lane_addr + c * 32, sv);
-        tmem_ld_32x32(tm_dp + lane_addr + c * 32, dv);
+      // every thread executes the (.sync.aligned) TMEM loads; only rows < q_eff compute and store.
+      // Two chunks of S and of dP per TMEM round trip (the round trip, not the math, dominated this loop).
+      for (int cb = 0; cb < nchunks; cb += 2) {
+        uint32_t sv[2][32], dv[2][32];
+        tmem_ld_32x32(tm_s + lane_addr + cb * 32, sv[0]);
+        tmem_ld_32x32(tm_dp + lane_addr + cb * 32, dv[0]);
+        if (cb + 1 < nchunks) {
+          tmem_ld_32x32(tm_s + lane_addr + (cb + 1) * 32, sv[1]);
+          tmem_ld_32x32(tm_dp + lane_addr + (cb + 1) * 32, dv[1]);
+        }
         tmem_ld_wait();
         if ((uint32_t)r < q_eff) {
-          float p[32], ds[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const bool ok = row_ok && (c * 32 + k < kvn);
-            const float e = exp2f(fmaf(__uint_as_float(sv[k]), c2, -my_lse2));
-            p[k] = ok ? e : 0.f;
-            ds[k] = ok ? e * (__uint_as_float(dv[k]) - my_d) * scale : 0.f;
-          }
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c = cb + cc;
+            if (c < nchunks) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if ((uint32_t)(c * 32 + g * 8) < n_eff) {
-              uint4 u, w;
-              u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
-              u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-              u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
-              u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-              w.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]);
-              w.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
-              w.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]);
-              w.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
-              st_swz(sP, r, c * 4 + g, u);
-              st_swz(sDS, r, c * 4 + g, w);
+              for (int g = 0; g < 4; ++g) {
+                if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+                  float p[8], ds[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const bool ok = row_ok && (c * 32 + g * 8 + k < kvn);
+                    const float e = ex2_approx(fmaf(__uint_as_float(sv[cc][g * 8 + k]), c2, -my_lse2));
+                    p[k] = ok ? e : 0.f;
+                    ds[k] = ok ? e * (__uint_as_float(dv[cc][g * 8 + k]) - my_d) * scale : 0.f;
+                  }
+                  uint4 u, w;
+                  u.x = pack_bf16x2(p[0], p[1]);
+                  u.y = pack_bf16x2(p[2], p[3]);
+                  u.z = pack_bf16x2(p[4], p[5]);
+                  u.w = pack_bf16x2(p[6], p[7]);
+                  w.x = pack_bf16x2(ds[0], ds[1]);
+                  w.y = pack_bf16x2(ds[2], ds[3]);
+                  w.z = pack_bf16x2(ds[4], ds[5]);
+                  w.w = pack_bf16x2(ds[6], ds[7]);
+                  st_swz(sP, r, c * 4 + g, u);
+                  st_swz(sDS, r, c * 4 + g, w);
+                }
+              }
             }
           }
         }
@@ -423,20 +444,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         // dV_j += P^T dO_i ; dK_j += dS^T Q_i   (A MN-major [kv chunks][q rows][64], B MN-major)
         const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);
         const int qsteps = (int)q_eff / 16;
+        // descriptors are built once; a k-step only moves the 16-byte-granular start address
+        const uint64_t dP_mn = umma_desc_mnmajor(sP_u, TILE_BYTES), dDO_mn = umma_desc_mnmajor(sDO, TILE_BYTES);
+        const uint64_t dDS_mn = umma_desc_mnmajor(sDS_u, TILE_BYTES), dQ_mn = umma_desc_mnmajor(sQ, TILE_BYTES);
+        const uint64_t dDS_k = umma_desc_kmajor(sDS_u), dK_mn = umma_desc_mnmajor(sK, TILE_BYTES);
+#pragma unroll 4
         for (int k = 0; k < qsteps; ++k)
-          umma_bf16_ss(tm_dv, umma_desc_mnmajor(sP_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sDO + k * 2048, TILE_BYTES),
-                       idesc_t, (i > 0 || k > 0));
+          umma_bf16_ss(tm_dv, dP_mn + (uint64_t)(k * 128), dDO_mn + (uint64_t)(k * 128), idesc_t, (i > 0 || k > 0));
+#pragma unroll 4
         for (int k = 0; k < qsteps; ++k)
-          umma_bf16_ss(tm_dk, umma_desc_mnmajor(sDS_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sQ + k * 2048, TILE_BYTES),
-                       idesc_t, (i > 0 || k > 0));
+          umma_bf16_ss(tm_dk, dDS_mn + (uint64_t)(k * 128), dQ_mn + (uint64_t)(k * 128), idesc_t, (i > 0 || k > 0));
         // dQ_i += dS K_j   (A K-major, B = K_j MN-major)
         const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);
         const int ksteps = (int)n_eff / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint32_t a_addr = sDS_u + (k >> 2) * TILE_BYTES + (k & 3) * 32;
-          umma_bf16_ss(tm_dq + i * HD, umma_desc_kmajor(a_addr), umma_desc_mnmajor(sK + k * 2048, TILE_BYTES), idesc_q,
-                       (j > 0 || k > 0));
-        }
+#pragma unroll 4
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ss(tm_dq + i * HD, dDS_k + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), dK_mn + (uint64_t)(k * 128),
+                       idesc_q, (j > 0 || k > 0));
         if (i == nt - 1) umma_commit(bar_drain);
         // next S/dP pair queues right behind on the tensor pipe
         int ni = i + 1, nj = j;
@@ -785,7 +809,7 @@ struct Bwd2Smem {
   static constexpr uint32_t BYTES = BAR_OFF + 256;
 };
 
-__global__ void __maxnreg__(208)
+__global__ void __launch_bounds__(288, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                  const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                  int N, int H, float scale, long long* trace) {
