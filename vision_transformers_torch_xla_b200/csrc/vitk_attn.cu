@@ -944,7 +944,6 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       const int kvn = min(TILE, N - j * TILE);
       const uint32_t n_eff = roundup16(kvn);
       const int nchunks = (int)(n_eff + 31) / 32;
-      uint32_t pk[64];  // this row's probabilities of the tile, packed bf16 pairs
 
       // ---- phase 1: S -> P (registers + smem) ----
       mbar_wait(&bar_s[w], j & 1);
@@ -961,21 +960,19 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int c = cb + cc;
-            if (c < nchunks) {
+            if (c < nchunks && (uint32_t)r < q_eff) {
+              uint32_t pk[16];
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
                 const bool ok0 = row_ok && (c * 32 + 2 * k < kvn), ok1 = row_ok && (c * 32 + 2 * k + 1 < kvn);
                 const float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * k]), c2, -my_lse2));
                 const float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * k + 1]), c2, -my_lse2));
-                pk[c * 16 + k] = pack_bf16x2(ok0 ? e0 : 0.f, ok1 ? e1 : 0.f);
+                pk[k] = pack_bf16x2(ok0 ? e0 : 0.f, ok1 ? e1 : 0.f);
               }
-              if ((uint32_t)r < q_eff) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                  if ((uint32_t)(c * 32 + g * 8) < n_eff)
-                    st_swz(sPDS, r, c * 4 + g, make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2],
-                                                          pk[c * 16 + g * 4 + 3]));
-              }
+              for (int g = 0; g < 4; ++g)
+                if ((uint32_t)(c * 32 + g * 8) < n_eff)
+                  st_swz(sPDS, r, c * 4 + g, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
             }
           }
         }
@@ -1000,17 +997,23 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           for (int cc = 0; cc < 2; ++cc) {
             const int c = cb + cc;
             if (c < nchunks && (uint32_t)r < q_eff) {
-              uint32_t ds[16];
 #pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const float2 pp = unpack_bf16x2(pk[c * 16 + k]);
-                ds[k] = pack_bf16x2(pp.x * (__uint_as_float(dv[cc][2 * k]) - my_d) * scale,
-                                    pp.y * (__uint_as_float(dv[cc][2 * k + 1]) - my_d) * scale);
+              for (int g = 0; g < 4; ++g) {
+                if ((uint32_t)(c * 32 + g * 8) < n_eff) {
+                  // P of this row is read back from its own smem slot (written in phase 1, consumed by the dV MMA)
+                  uint8_t* slot = sPDS + ((c * 4 + g) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + g) & 7) ^ (r & 7)) << 4);
+                  const uint4 pu = *reinterpret_cast<const uint4*>(slot);
+                  const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+                  uint32_t ds[4];
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 pp = unpack_bf16x2(pw[k]);
+                    ds[k] = pack_bf16x2(pp.x * (__uint_as_float(dv[cc][g * 8 + 2 * k]) - my_d) * scale,
+                                        pp.y * (__uint_as_float(dv[cc][g * 8 + 2 * k + 1]) - my_d) * scale);
+                  }
+                  *reinterpret_cast<uint4*>(slot) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+                }
               }
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                if ((uint32_t)(c * 32 + g * 8) < n_eff)
-                  st_swz(sPDS, r, c * 4 + g, make_uint4(ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]));
             }
           }
         }
