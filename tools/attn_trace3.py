@@ -1,0 +1,48 @@
+"""Timeline (SM cycles) of items 2 and 3 of CTA 0 of the warp-specialised attention forward kernel (attn_fwd3).
+usage: attn_trace3.py [B] [N] [H]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vision_transformers_torch_xla_b200 import _lib as L  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 197
+H = int(sys.argv[3]) if len(sys.argv) > 3 else 12
+dev = torch.device("cuda")
+qkv = torch.randn(B, N, 3 * H * 64, device=dev).bfloat16()
+out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+lse = torch.empty(B, H, N, device=dev)
+trace = torch.zeros(128, dtype=torch.int64, device=dev)
+lib = L.load()
+for _ in range(2):
+    L.attn_fwd(qkv, out, lse, B, N, H, 64, 0.125)
+lib.vitk_debug_set_trace(trace.data_ptr())
+L.attn_fwd(qkv, out, lse, B, N, H, 64, 0.125)
+torch.cuda.synchronize()
+lib.vitk_debug_set_trace(None)
+t = trace.cpu().tolist()
+SM = ["S ready", "max pass done", "max exchanged", "P written", "sum exchanged", "O ready", "O read, slot freed", "O stored"]
+MM = ["stage full", "slot free", "S issued", "P ready", "PV issued"]
+ev = []
+for g in (0, 1):
+    for k in (0, 1):
+        for e, name in enumerate(SM):
+            v = t[16 * g + 8 * k + e]
+            if v:
+                ev.append((v, f"softmax g{g} item {2 + k}: {name}"))
+        for e, name in enumerate(MM):
+            v = t[32 + 16 * g + 8 * k + e]
+            if v:
+                ev.append((v, f"    mma g{g} item {2 + k}: {name}"))
+for g in (0, 1):
+    for u in range(8):
+        v = t[64 + 16 * g + u]
+        if v:
+            ev.append((v, f"softmax g{g} item 2:        exp unit {u} done"))
+ev.sort()
+t0 = ev[0][0] if ev else 0
+for v, name in ev:
+    print(f"{v - t0:8d}  {name}")

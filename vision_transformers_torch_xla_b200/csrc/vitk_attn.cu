@@ -763,6 +763,338 @@ int launch_fwd2(const CUtensorMap& tm, void* out, float* lse, int B, int N, int 
   return vitk_check_launch("attn_fwd2");
 }
 
+// ================================================================================================
+// Forward, warp-specialised persistent kernel for 128 < N <= 256 (224-px ViT / DeiT: N = 197 / 198).
+//
+// The softmax, not the tensor core, bounds attention at head_dim 64 (one MUFU.EX2 per 256 MMA flops; measured
+// 15.6 ex2/clk/SM, tools/ubench_tmem.cu), so the kernel is organised to keep the MUFU pipe fed:
+//   * one CTA per SM loops over (b, h) items; warp 18 prefetches Q/K/V of the next item by TMA (2 smem stages);
+//   * group g (warps 8g..8g+7) owns q tile g and TMEM slot g (256 columns).  Two threads share a score row
+//     (TMEM lane = row, halves split the kv columns at a 16-column boundary), so each scheduler always has
+//     two softmax warps per group;  warp 16+g issues that group's MMAs, so the two groups run out of phase and
+//     one group's exps overlap the other's MMA / TMEM round trips;
+//   * the whole score row (<= 256 columns) is in TMEM, so the softmax is two passes over it (max, then exp) with no
+//     rescaling; P is written back over S in TMEM as packed bf16 and feeds O = P V as the TMEM A operand
+//     (no shared-memory round trip, no proxy fence).
+// Slot layout (columns): S [0, n_eff) | P_lo [0, 8 k0) | P_hi [16 k0, 16 k0 + 8 k1) | O [192, 256)
+// smem: 2 stages x (Q0 Q1 K0 K1 V0 V1) | max / sum exchange | barriers
+// ================================================================================================
+struct Fwd3Smem {
+  static constexpr uint32_t STAGE = 6 * TILE_BYTES;
+  static constexpr uint32_t XCH_OFF = 2 * STAGE;                      // float [2 groups][max, sum][2 halves][128]
+  static constexpr uint32_t BAR_OFF = XCH_OFF + 2 * 2 * 2 * 128 * 4;
+  static constexpr uint32_t BYTES = BAR_OFF + 256;
+};
+constexpr int FWD3_THREADS = 19 * 32;
+
+__global__ void __launch_bounds__(FWD3_THREADS, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
+                 int B, int N, int H, float scale, long long* trace) {
+  using L = Fwd3Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [2] TMA -> MMA warps
+  uint64_t* stage_empty = stage_full + 2;                                  // [2] both MMA warps -> TMA
+  uint64_t* s_full = stage_empty + 2;                                      // [g] MMA -> group: S ready
+  uint64_t* p_full = s_full + 2;                                           // [g] group -> MMA: P written
+  uint64_t* o_full = p_full + 2;                                           // [g] MMA -> group: O ready
+  uint64_t* slot_free = o_full + 2;                                        // [g] group -> MMA: O read out
+  uint64_t* o_staged = slot_free + 2;                                      // [g] group -> MMA: bf16 O tile in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_staged + 2);
+  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
+
+  // timeline of items 2 and 3 of CTA 0 (tools/attn_trace3.py): role base + 8 * (n - 2) + event
+#define FWD3_STAMP(base, ev)                                                       \
+  do {                                                                             \
+    if (trace != nullptr && blockIdx.x == 0 && (n == 2 || n == 3)) trace[(base) + 8 * (n - 2) + (ev)] = clock64(); \
+  } while (0)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = B * H;
+  const uint32_t n_eff = roundup16(N);
+  const int KS = (int)n_eff / 16;  // 16-column units of the score row == k-steps of P V
+  const int k0 = KS / 2, k1 = KS - k0;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_full[i], 1);
+      mbar_init(&stage_empty[i], 4);   // per MMA warp: Q/K/V reads retired + its group's O staging tile stored
+      mbar_init(&o_staged[i], 8);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);        // one arrival per softmax warp
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_free[i], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 18) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 18) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      int n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int st = n & 1;
+        const int h = it % H, b = it / H;
+        mbar_wait(&stage_empty[st], ((n >> 1) & 1) ^ 1);
+        uint8_t* base = smem + st * L::STAGE;
+        mbar_arrive_expect_tx(&stage_full[st], L::STAGE);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_3d(base + t * TILE_BYTES, &tm_qkv, &stage_full[st], h * HD, t * TILE, b);
+          tma_load_3d(base + (2 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (H + h) * HD, t * TILE, b);
+          tma_load_3d(base + (4 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (2 * H + h) * HD, t * TILE, b);
+        }
+      }
+    }
+  } else if (warp >= 16) {
+    // ------------------------------ MMA issuer of group g ------------------------------
+    // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected
+    // lane issues.  Group 1 starts half an item late (it waits for group 0's first P), so that from then on one
+    // group's exps overlap the other group's MMA / TMEM / store phases.
+    {
+      const int g = warp - 16;
+      const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
+      const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P (TMEM, K-major), B = V MN-major
+      const uint32_t slot = tmem_base + g * 256;
+      const uint32_t phi = 16 * k0;  // first TMEM column of the packed P of the upper column half
+      // bf16 O tile of item m (staged by the group in the dead Q_g tile of its stage) -> global, then release the stage
+      auto store_o = [&](int m, int item) {
+        const int st = m & 1;
+        mbar_wait(&o_staged[g], m & 1);
+        if (elect_one()) {
+          tma_store_3d(&tm_out, smem + st * L::STAGE + g * TILE_BYTES, (item % H) * HD, g * TILE, item / H);  // rows >= N clipped
+          tma_store_commit_and_wait_read();
+          mbar_arrive(&stage_empty[st]);
+        }
+        __syncwarp();
+      };
+      int n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int st = n & 1;
+        const uint32_t sbase = smem_u32(smem + st * L::STAGE);
+        const uint32_t sQ = sbase + g * TILE_BYTES, sK = sbase + 2 * TILE_BYTES, sV = sbase + 4 * TILE_BYTES;
+        mbar_wait(&stage_full[st], (n >> 1) & 1);
+        if (lane == 0) FWD3_STAMP(32 + 16 * g, 0);
+        if (n > 0) mbar_wait(&slot_free[g], (n - 1) & 1);
+        else if (g == 1) mbar_wait(&p_full[0], 0);
+        if (lane == 0) FWD3_STAMP(32 + 16 * g, 1);
+        tc_fence_after();
+        const uint64_t qdesc = umma_desc_kmajor(sQ), kdesc = umma_desc_kmajor(sK);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+        if (lane == 0) FWD3_STAMP(32 + 16 * g, 2);
+        if (n > 0) store_o(n - 1, it - (int)gridDim.x);   // nothing else to do until this group's P arrives
+        mbar_wait(&p_full[g], n & 1);
+        if (lane == 0) FWD3_STAMP(32 + 16 * g, 3);
+        tc_fence_after();
+        const uint64_t vdesc = umma_desc_mnmajor(sV, TILE_BYTES);
+        if (elect_one()) {
+          for (int ks = 0; ks < k0; ++ks) umma_bf16_ts(slot + 192, slot + 8 * ks, vdesc + (uint64_t)(ks * 128), idesc_o, ks > 0);
+          for (int ks = 0; ks < k1; ++ks)
+            umma_bf16_ts(slot + 192, slot + phi + 8 * ks, vdesc + (uint64_t)((k0 + ks) * 128), idesc_o, 1);
+          umma_commit(&o_full[g]);
+          umma_commit(&stage_empty[st]);  // this group's reads of Q_g / K / V have retired
+        }
+        __syncwarp();
+        if (lane == 0) FWD3_STAMP(32 + 16 * g, 4);
+      }
+      if (n > 0) {
+        store_o(n - 1, blockIdx.x + (n - 1) * (int)gridDim.x);
+        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the store
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------ softmax group g: 256 threads, 2 per score row ------------------------------
+    const int g = warp >> 3, quarter = warp & 3, half = (warp >> 2) & 1;
+    const int r = quarter * 32 + lane;
+    const uint32_t slot = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int qn = g == 0 ? min(TILE, N) : N - TILE;   // valid rows of this q tile
+    const bool active = quarter * 32 < qn;             // warp-uniform: some row of this warp is real
+    const int my_k = half ? k1 : k0;                   // 16-column units owned by this thread
+    const int c0 = half ? 16 * k0 : 0;                 // first score column (and first packed-P column)
+    float* xm = xch + g * 512;                         // [half][row] partial maxima
+    float* xs = xm + 256;                              // [half][row] partial sums
+    const float c2 = scale * LOG2E;
+    const int q = g * TILE + r;
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const bool tr = (warp & 7) == 0 && lane == 0;
+      mbar_wait(&s_full[g], n & 1);
+      tc_fence_after();
+      if (tr) FWD3_STAMP(16 * g, 0);
+      uint32_t ra[16], rb[16];  // the only TMEM staging registers: shared by both passes and the O read-out
+
+      // ---- pass 1: row maximum over this thread's columns ----
+      float mx = -INFINITY;
+      if (active) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 1
+        for (int u0 = 0; u0 < my_k; u0 += 2) {
+          tmem_ld_32x16(slot + c0 + u0 * 16, ra);
+          if (u0 + 1 < my_k) tmem_ld_32x16(slot + c0 + (u0 + 1) * 16, rb);
+          tmem_ld_wait();
+#pragma unroll
+          for (int uu = 0; uu < 2; ++uu) {
+            if (u0 + uu < my_k) {
+              const uint32_t(&v)[16] = uu ? rb : ra;
+              const int col = c0 + (u0 + uu) * 16;
+              if (col + 16 <= N) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  m0 = fmaxf(m0, __uint_as_float(v[i]));
+                  m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                  m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+                  m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (col + i < N) m0 = fmaxf(m0, __uint_as_float(v[i]));
+              }
+            }
+          }
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      if (tr) FWD3_STAMP(16 * g, 1);
+      xm[half * 128 + r] = mx;
+      named_bar_sync(1 + g, 256);
+      if (tr) FWD3_STAMP(16 * g, 2);
+      mx = fmaxf(xm[r], xm[128 + r]);
+
+      // ---- pass 2: P = exp2(S * c2 - mx * c2) -> packed bf16 written back over S ----
+      float s0 = 0.f, s1 = 0.f;
+      if (active) {
+        const float mc = mx * c2;
+        uint32_t(&cur)[16] = ra;
+        uint32_t(&nxt)[16] = rb;
+        tmem_ld_32x16(slot + c0, cur);
+        tmem_ld_wait();
+#pragma unroll 1
+        for (int u = 0; u < my_k; ++u) {
+          const bool more = u + 1 < my_k;
+          if (more) tmem_ld_32x16(slot + c0 + (u + 1) * 16, nxt);  // in flight while this unit's exps issue
+          const int col = c0 + u * 16;
+          uint32_t pk[8];
+          if (col + 16 <= N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * i]), c2, -mc));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * i + 1]), c2, -mc));
+              s0 += e0;
+              s1 += e1;
+              pk[i] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * i]), c2, -mc));
+              float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * i + 1]), c2, -mc));
+              e0 = (col + 2 * i < N) ? e0 : 0.f;
+              e1 = (col + 2 * i + 1 < N) ? e1 : 0.f;
+              s0 += e0;
+              s1 += e1;
+              pk[i] = pack_bf16x2(e0, e1);
+            }
+          }
+          tmem_st_32x8(slot + c0 + u * 8, pk);
+          if (more) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+          }
+          if (tr && trace != nullptr && blockIdx.x == 0 && n == 2) trace[64 + 16 * g + u] = clock64();
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (tr) FWD3_STAMP(16 * g, 3);
+
+      xs[half * 128 + r] = s0 + s1;
+      named_bar_sync(1 + g, 256);
+      if (tr) FWD3_STAMP(16 * g, 4);
+      const float l = xs[r] + xs[128 + r];
+
+      // ---- O = P V: this thread's 32 of the 64 output columns ----
+      mbar_wait(&o_full[g], n & 1);
+      tc_fence_after();
+      if (tr) FWD3_STAMP(16 * g, 5);
+      if (active) {
+        tmem_ld_32x16(slot + 192 + half * 32, ra);
+        tmem_ld_32x16(slot + 192 + half * 32 + 16, rb);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);
+      if (tr) FWD3_STAMP(16 * g, 6);
+      // normalised bf16 rows -> the (dead) Q_g tile of this item's stage, 128-byte swizzled -> one TMA store per group
+      const int st = n & 1;
+      uint8_t* stg = smem + st * L::STAGE + g * TILE_BYTES;
+      const int h = it % H, b = it / H;
+      if (active) {
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          const uint32_t(&o)[16] = gg < 2 ? ra : rb;
+          const int e = (gg & 1) * 8;
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv, __uint_as_float(o[e + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
+          st_swz(stg, r, half * 4 + gg, u);
+        }
+        if (half == 0 && q < N && lse) lse[((long long)b * H + h) * N + q] = mx * scale + __logf(l);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_staged[g]);   // the group's MMA warp issues the TMA store
+      if (tr) FWD3_STAMP(16 * g, 7);
+    }
+  }
+#undef FWD3_STAMP
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 18) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_fwd3(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
+  CUtensorMap tm_out;
+  int rc = vitk_make_tmap_3d(&tm_out, out, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD, HD,
+                             TILE, 1);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd3Smem::BYTES);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int items = B * H;
+  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
+  attn_fwd3_kernel<<<grid, FWD3_THREADS, Fwd3Smem::BYTES, s>>>(tm, tm_out, lse, B, N, H, scale, g_trace_buf);
+  return vitk_check_launch("attn_fwd3");
+}
+
 // D[b, h, n] = sum_d O[b, n, h, d] * dO[b, n, h, d]: one warp per token row, fully coalesced 16-byte loads.
 // (Computing it inside the backward kernel costs ~10k cycles of exposed, row-strided global loads per CTA.)
 __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -1323,14 +1655,15 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   if (rc) return rc;
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
-  static const bool persistent = [] {
-    // experimental: "2" selects the persistent, double-buffered kernel (measured 316 us vs 212 us per layer at
-    // ViT-B B=256 for the default one-CTA-per-q-tile kernel, whose two resident CTAs per SM hide more latency)
+  // VITK_ATTN_FWD: unset = warp-specialised persistent kernel for 128 < N <= 256, tiled kernel otherwise;
+  // "1" = tiled one-CTA-per-q-tile kernel everywhere; "2" = older persistent kernel (kept for comparison)
+  static const int variant = [] {
     const char* e = getenv("VITK_ATTN_FWD");
-    return e && e[0] == '2';
+    return e ? atoi(e) : 0;
   }();
-  if (persistent && T == 1) return launch_fwd2<1>(tm, out, lse, B, N, H, scale, s);
-  if (persistent && T == 2) return launch_fwd2<2>(tm, out, lse, B, N, H, scale, s);
+  if (variant == 0 && T == 2) return launch_fwd3(tm, out, lse, B, N, H, scale, s);
+  if (variant == 2 && T == 1) return launch_fwd2<1>(tm, out, lse, B, N, H, scale, s);
+  if (variant == 2 && T == 2) return launch_fwd2<2>(tm, out, lse, B, N, H, scale, s);
   switch (T) {
     case 1: return launch_fwd<1>(tm, out, lse, B, N, H, scale, s);
     case 2: return launch_fwd<2>(tm, out, lse, B, N, H, scale, s);
