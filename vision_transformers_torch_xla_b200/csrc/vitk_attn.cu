@@ -1401,6 +1401,341 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 }
 
 // ================================================================================================
+// Backward, warp-specialised persistent kernel for 128 < N <= 256 (224-px ViT / DeiT: N = 197 / 198).
+//
+// One CTA per SM loops over (b, h) items.  320 threads:
+//   warpgroup w (warps 4w..4w+3) owns q tile w, one thread per row (no cross-thread reductions); per kv tile j it turns
+//     S_wj into P (bf16, smem), then dP_wj into dS (bf16, smem, over P) — S and dP share one 128-column TMEM buffer;
+//   warp 8 issues every tcgen05.mma (uniform control flow, one elected lane) and alternates between the two
+//     warpgroups, so one warpgroup's exp / dS math overlaps the other's GEMMs;
+//   warp 9 is the TMA producer: K_0 / V_0 of the next item are prefetched while kv tile 1 is processed, the other
+//     six tiles as soon as the last MMA of the item retires.
+// No masking anywhere in the inner loops: kv rows >= N are zero-filled by TMA (they only reach discarded dK / dV rows
+// and contribute 0 to dQ), q rows >= N have Q = dO = 0 and use lse = D = 0 (finite P, dS = 0).
+// dQ / dK / dV rows leave through a warp-private 4 KB staging tile so that every global store instruction writes
+// whole 128-byte lines (a thread storing its own row costs one L1 line per lane per instruction).
+// TMEM: SdP_0 [0,128) | SdP_1 [128,256) | dV_j [256,320) | dK_j [320,384) | dQ_0 [384,448) | dQ_1 [448,512)
+// smem: Q_w dO_w (64K) | K_j V_j (64K) | PdS_0 PdS_1 (64K) | 8 x 4K store staging | barriers
+// ================================================================================================
+struct Bwd3Smem {
+  static constexpr uint32_t QDO_OFF = 0;                       // [w][Q, dO]
+  static constexpr uint32_t KV_OFF = 4 * TILE_BYTES;           // [j][K, V]
+  static constexpr uint32_t PDS_OFF = 8 * TILE_BYTES;          // [w][2 chunks of 64 kv columns][128 rows][128 B]
+  static constexpr uint32_t STG_OFF = 12 * TILE_BYTES;         // [8 warps][32 rows][128 B]
+  static constexpr uint32_t BAR_OFF = STG_OFF + 8 * 4096;
+  static constexpr uint32_t BYTES = BAR_OFF + 256;
+};
+constexpr int BWD3_THREADS = 10 * 32;
+
+// 32 rows x 64 fp32 (one row per lane, two 32-column halves) -> bf16 -> global rows [row0, row0 + 32) of a tensor with
+// `pitch` elements per row, through a warp-private swizzled 4 KB tile: each store instruction writes 4 full rows.
+__device__ __forceinline__ void store_rows_coalesced(uint8_t* wst, int lane, const uint32_t (&a)[32], const uint32_t (&b)[32],
+                                                     __nv_bfloat16* dst, long long pitch, int rows_valid) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint32_t(&v)[32] = u < 4 ? a : b;
+    const int e = (u & 3) * 8;
+    uint4 q;
+    q.x = pack_bf16x2(__uint_as_float(v[e + 0]), __uint_as_float(v[e + 1]));
+    q.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+    q.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+    q.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+    *reinterpret_cast<uint4*>(wst + lane * 128 + ((u ^ (lane & 7)) << 4)) = q;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3), u = lane & 7;
+    const uint4 q = *reinterpret_cast<const uint4*>(wst + row * 128 + ((u ^ (row & 7)) << 4));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(dst + (long long)row * pitch + u * 8) = q;
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                 int B, int N, int H, float scale) {
+  using L = Bwd3Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [w] TMA -> MMA: Q_w, dO_w landed
+  uint64_t* bar_kv = bar_q + 2;                                       // [j] TMA -> MMA: K_j, V_j landed
+  uint64_t* empty_kv0 = bar_kv + 2;                                   // MMA -> TMA: K_0, V_0 no longer read
+  uint64_t* empty_rest = empty_kv0 + 1;                               // MMA -> TMA: the item's last MMA retired
+  uint64_t* bar_s = empty_rest + 1;                                   // [w] MMA -> WG: S_wj ready
+  uint64_t* bar_p = bar_s + 2;                                        // [w] WG -> MMA: P_wj in smem
+  uint64_t* bar_dp = bar_p + 2;                                       // [w] MMA -> WG: dP_wj ready, P_wj consumed
+  uint64_t* bar_ds = bar_dp + 2;                                      // [w] WG -> MMA: dS_wj in smem
+  uint64_t* bar_drain = bar_ds + 2;                                   // MMA -> WGs: every MMA of kv tile j retired
+  uint64_t* bar_drained = bar_drain + 1;                              // WGs -> MMA: accumulators read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_drained + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = B * H;
+  const uint32_t eff1 = roundup16(N - TILE);   // rows of q tile 1 == columns of kv tile 1, rounded up to the MMA K step
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q[i], 1);
+      mbar_init(&bar_kv[i], 1);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 4);
+      mbar_init(&bar_dp[i], 1);
+      mbar_init(&bar_ds[i], 4);
+    }
+    mbar_init(empty_kv0, 1);
+    mbar_init(empty_rest, 1);
+    mbar_init(bar_drain, 1);
+    mbar_init(bar_drained, 8);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
+
+  if (warp == 9) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      int n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int h = it % H, b = it / H;
+        if (n > 0) mbar_wait(empty_kv0, (n - 1) & 1);
+        mbar_arrive_expect_tx(&bar_kv[0], 2 * TILE_BYTES);
+        tma_load_3d(smem + L::KV_OFF, &tm_qkv, &bar_kv[0], (H + h) * HD, 0, b);
+        tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, &bar_kv[0], (2 * H + h) * HD, 0, b);
+        if (n > 0) mbar_wait(empty_rest, (n - 1) & 1);
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          mbar_arrive_expect_tx(&bar_q[w], 2 * TILE_BYTES);
+          tma_load_3d(smem + L::QDO_OFF + w * 2 * TILE_BYTES, &tm_qkv, &bar_q[w], h * HD, w * TILE, b);
+          tma_load_3d(smem + L::QDO_OFF + w * 2 * TILE_BYTES + TILE_BYTES, &tm_do, &bar_q[w], h * HD, w * TILE, b);
+        }
+        mbar_arrive_expect_tx(&bar_kv[1], 2 * TILE_BYTES);
+        tma_load_3d(smem + L::KV_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_kv[1], (H + h) * HD, TILE, b);
+        tma_load_3d(smem + L::KV_OFF + 3 * TILE_BYTES, &tm_qkv, &bar_kv[1], (2 * H + h) * HD, TILE, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues) ------------------------------
+    const uint32_t sQDO = smem_u32(smem + L::QDO_OFF), sKV = smem_u32(smem + L::KV_OFF), sPDS = smem_u32(smem + L::PDS_OFF);
+    const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);    // A, B MN-major: P^T dO, dS^T Q
+    const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);   // dS K
+    // S_wj = Q_w K_j^T (what == 0) or dP_wj = dO_w V_j^T (what == 1) into SdP_w
+    auto issue_qk = [&](int w, int j, int what, uint64_t* bar) {
+      const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
+      const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+      const uint64_t adesc = umma_desc_kmajor(sQDO + (w * 2 + what) * TILE_BYTES);
+      const uint64_t bdesc = umma_desc_kmajor(sKV + (j * 2 + what) * TILE_BYTES);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + w * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    };
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
+        if (j == 0) {
+          mbar_wait(&bar_kv[0], n & 1);
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&bar_q[w], n & 1);
+            tc_fence_after();
+            issue_qk(w, 0, 0, &bar_s[w]);
+          }
+        }
+        if (n > 0 || j > 0) {
+          mbar_wait(bar_drained, j ^ 1);   // dV / dK (and, across items, dQ) of the previous kv tile were read out
+          tc_fence_after();
+        }
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
+          const uint64_t pdesc = umma_desc_mnmajor(sPDS + w * 2 * TILE_BYTES, TILE_BYTES);
+          const uint64_t dodesc = umma_desc_mnmajor(sQDO + (w * 2 + 1) * TILE_BYTES, TILE_BYTES);
+          mbar_wait(&bar_p[w], j);
+          tc_fence_after();
+          if (elect_one()) {   // dV_j += P_w^T dO_w
+            for (int k = 0; k < (int)q_eff / 16; ++k)
+              umma_bf16_ss(tm_dv, pdesc + (uint64_t)(k * 128), dodesc + (uint64_t)(k * 128), idesc_t, (w > 0 || k > 0));
+          }
+          __syncwarp();
+          issue_qk(w, j, 1, &bar_dp[w]);   // dP_wj over S_wj (warpgroup w has turned S into P)
+        }
+        for (int w = 0; w < 2; ++w) {
+          const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
+          const uint32_t sDS = sPDS + w * 2 * TILE_BYTES;
+          const uint64_t dsdesc_t = umma_desc_mnmajor(sDS, TILE_BYTES);
+          const uint64_t qdesc = umma_desc_mnmajor(sQDO + w * 2 * TILE_BYTES, TILE_BYTES);
+          const uint64_t dsdesc_k = umma_desc_kmajor(sDS);
+          const uint64_t kdesc = umma_desc_mnmajor(sKV + j * 2 * TILE_BYTES, TILE_BYTES);
+          mbar_wait(&bar_ds[w], j);
+          tc_fence_after();
+          if (elect_one()) {
+            for (int k = 0; k < (int)q_eff / 16; ++k)   // dK_j += dS_w^T Q_w
+              umma_bf16_ss(tm_dk, dsdesc_t + (uint64_t)(k * 128), qdesc + (uint64_t)(k * 128), idesc_t, (w > 0 || k > 0));
+            for (int k = 0; k < (int)n_eff / 16; ++k)   // dQ_w += dS_w K_j
+              umma_bf16_ss(tm_dq + w * HD, dsdesc_k + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), kdesc + (uint64_t)(k * 128),
+                           idesc_q, (j > 0 || k > 0));
+          }
+          __syncwarp();
+          if (j == 0) {
+            if (w == 0) mbar_wait(&bar_kv[1], n & 1);
+            issue_qk(w, 1, 0, &bar_s[w]);   // SdP_w is free: warpgroup w read dP before it wrote dS
+          }
+        }
+        if (elect_one()) {
+          umma_commit(bar_drain);
+          if (j == 0) umma_commit(empty_kv0);
+          else umma_commit(empty_rest);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------ warpgroup w: rows of q tile w ------------------------------
+    const int w = warp >> 2, r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tm_sdp = tmem_base + w * 128 + lane_addr;
+    uint8_t* sPDS = smem + L::PDS_OFF + w * 2 * TILE_BYTES;
+    uint8_t* wst = smem + L::STG_OFF + warp * 4096;
+    const int q = w * TILE + r;
+    const bool row_ok = q < N;
+    const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
+    const bool warp_active = (uint32_t)((warp & 3) * 32) < q_eff;   // some row of this warp is read by the dV / dK MMAs
+    const float c2 = scale * LOG2E;
+    const int D = H * HD;
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int h = it % H, b = it / H;
+      float my_lse2 = 0.f, my_ds = 0.f;   // rows >= N: P = 2^S stays finite, dS = 0
+      if (row_ok) {
+        my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
+        my_ds = dsum[((long long)b * H + h) * N + q] * scale;
+      }
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
+        const int nch = (int)(n_eff + 31) / 32;   // 32-column chunks (the last one may be half)
+
+        // ---- S -> P ----
+        mbar_wait(&bar_s[w], j);
+        tc_fence_after();
+        if (warp_active) {
+          uint32_t cur[32], nxt[32];
+          tmem_ld_32x32(tm_sdp, cur);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < nch) {
+              if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, nxt);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  pk[i] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(cur[g * 8 + 2 * i]), c2, -my_lse2)),
+                                      ex2_approx(fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), c2, -my_lse2)));
+                st_swz(sPDS, r, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+              }
+              if (c + 1 < nch) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[w]);
+
+        // ---- dP -> dS (over P) ----
+        mbar_wait(&bar_dp[w], j);
+        tc_fence_after();
+        if (warp_active) {
+          uint32_t cur[32], nxt[32];
+          tmem_ld_32x32(tm_sdp, cur);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < nch) {
+              if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, nxt);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint8_t* slot = sPDS + ((c * 4 + g) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + g) & 7) ^ (r & 7)) << 4);
+                const uint4 pu = *reinterpret_cast<const uint4*>(slot);
+                const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+                uint32_t ds[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 pp = unpack_bf16x2(pw[i]);
+                  ds[i] = pack_bf16x2(pp.x * fmaf(__uint_as_float(cur[g * 8 + 2 * i]), scale, -my_ds),
+                                      pp.y * fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), scale, -my_ds));
+                }
+                *reinterpret_cast<uint4*>(slot) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+              }
+              if (c + 1 < nch) {
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_ds[w]);
+
+        // ---- drain dV_j (warpgroup 0) / dK_j (warpgroup 1), and dQ_w after the last kv tile ----
+        mbar_wait(bar_drain, j);
+        tc_fence_after();
+        {
+          const int kv0 = j * TILE + (warp & 3) * 32;   // first kv row of this warp
+          if (kv0 < N) {
+            uint32_t a0[32], a1[32];
+            const uint32_t src = (w == 0 ? tm_dv : tm_dk) + lane_addr;
+            tmem_ld_32x32(src, a0);
+            tmem_ld_32x32(src + 32, a1);
+            tmem_ld_wait();
+            store_rows_coalesced(wst, lane, a0, a1, dqkv + ((long long)b * N + kv0) * (3 * D) + ((w == 0 ? 2 : 1) * H + h) * HD,
+                                 3 * D, N - kv0);
+          }
+          const int q0 = w * TILE + (warp & 3) * 32;
+          if (j == 1 && q0 < N) {
+            uint32_t a0[32], a1[32];
+            tmem_ld_32x32(tm_dq + w * HD + lane_addr, a0);
+            tmem_ld_32x32(tm_dq + w * HD + lane_addr + 32, a1);
+            tmem_ld_wait();
+            store_rows_coalesced(wst, lane, a0, a1, dqkv + ((long long)b * N + q0) * (3 * D) + h * HD, 3 * D, N - q0);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_drained);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
 // Backward, streaming variant for 256 < N <= 640 (ViT-L/16 at 384 px: N = 577): one CTA per (b, h, kv tile j).
 // K_j / V_j stay resident, Q_i / dO_i stream through one smem buffer, dV_j / dK_j accumulate in TMEM over the
 // q tiles, and each dQ_ij partial is read out of a TMEM scratch tile and red.add'ed into an fp32 workspace
@@ -1707,6 +2042,8 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd2Smem::BYTES);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -1739,13 +2076,19 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     return vitk_check_launch("attn_bwd_dq_cast");
   }
   dim3 grid(H, B);
-  static const bool two_wg = [] {
-    // experimental: "2" selects the two-warpgroup ping-pong kernel (measured 550 us vs 500 us per layer at ViT-B
-    // B=256 for the default single-warpgroup kernel)
+  // VITK_ATTN_BWD: unset = warp-specialised persistent kernel for 128 < N <= 256, single-warpgroup kernel otherwise;
+  // "1" = single-warpgroup kernel everywhere; "2" = older two-warpgroup kernel (kept for comparison)
+  static const int variant = [] {
     const char* e = getenv("VITK_ATTN_BWD");
-    return e && e[0] == '2';
+    return e ? atoi(e) : 0;
   }();
-  if (two_wg) {
+  if (variant == 0 && N > TILE) {
+    const int items = B * H;
+    const int g3 = items < vitk_num_sms() ? items : vitk_num_sms();
+    attn_bwd3_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, B, N, H, scale);
+    return vitk_check_launch("attn_bwd3");
+  }
+  if (variant == 2) {
     attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, scale,
                                                          g_trace_buf);
     return vitk_check_launch("attn_bwd2");
