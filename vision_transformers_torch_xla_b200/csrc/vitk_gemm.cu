@@ -22,6 +22,8 @@
 //   wgrad  dW = dY^T X   : A MN-major, B MN-major  (split-K, fp32 red.add into the grad buffer)
 #include <cstdlib>
 
+#include <cstring>
+
 #include "vitk_common.cuh"
 #include "vitk_internal.h"
 
@@ -57,7 +59,11 @@ struct GemmParams {
 // columns, 2 KB for bf16) through which accumulator rows (thread = row) are transposed into row-contiguous
 // order, so that every global load/store instruction touches whole 64/128-byte row segments.
 template <int EPI>
-constexpr uint32_t kStgBytes = (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_DGELU) ? 2048u : 4096u;
+constexpr uint32_t kStgBytes = (EPI == EPI_BF16) ? 2048u : 4096u;
+// GELU / x GELU' epilogues with 64 columns per epilogue warp leave (and, for the aux operand, enter) through TMA:
+// two [32 rows][64 B] panels per warp in the 64-byte-swizzle layout (see the epilogue branch of gemm_kernel).
+template <int EPI, int PART_N>
+constexpr bool kTmaEpi = (EPI == EPI_GELU || EPI == EPI_DGELU) && PART_N == 64;
 
 // CTA2: a pair of CTAs (cluster of 2, one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2.
 // Each CTA stages its own 128 rows of A but only HALF of the B tile, so per-SM operand traffic from L2 (and smem
@@ -70,10 +76,10 @@ struct TileCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t STG_TOTAL = EW * STG_BYTES;
   static constexpr uint32_t SMEM_MAX = 232448;  // 227 KB
-  static constexpr int STAGES_FIT = (SMEM_MAX - 1024 - 256 - STG_TOTAL) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_MAX - 1024 - 512 - STG_TOTAL) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 256) ? 256 : 512;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + STG_TOTAL + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
 };
 
@@ -139,12 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&a
       __nv_bfloat16* a = reinterpret_cast<__nv_bfloat16*>(p.aux) + (long long)row * p.ld_aux + c;
       float gl[8], gd[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float pdf;
-        const float cdf = gelu_cdf(v[j], &pdf);
-        gl[j] = v[j] * cdf;
-        gd[j] = fmaf(v[j], pdf, cdf);
-      }
+      for (int j = 0; j < 8; ++j) gelu_fwd_bwd(v[j], gl[j], gd[j]);
       *reinterpret_cast<uint4*>(a) = pack8(gd);
       *reinterpret_cast<uint4*>(o) = pack8(gl);
     } else if constexpr (EPI == EPI_RESID || EPI == EPI_F32 || EPI == EPI_PATCH) {
@@ -300,12 +301,7 @@ __device__ __forceinline__ void epilogue_panel(const GemmParams& p, uint32_t (&a
     // out = gelu(h), aux = gelu'(h): the backward epilogue (EPI_DGELU) is then a plain multiply
     float gd[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float pdf;
-      const float cdf = gelu_cdf(v[j], &pdf);
-      gd[j] = fmaf(v[j], pdf, cdf);
-      v[j] *= cdf;
-    }
+    for (int j = 0; j < 32; ++j) gelu_fwd_bwd(v[j], v[j], gd[j]);
     row_put_b16(stg, lane, v);
     __syncwarp();
     panel_io_b16<false>(stg, reinterpret_cast<__nv_bfloat16*>(p.out), p.ld_out, row0, col0, p.M, p.N, lane);
@@ -363,7 +359,7 @@ constexpr bool kStaged = (EPI == EPI_BF16 || EPI == EPI_GELU || EPI == EPI_F32 |
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int EW, bool CTA2>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   constexpr uint32_t STG_BYTES = kStgBytes<EPI>;
   using Cfg = TileCfg<BLOCK_N, EW, STG_BYTES, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
@@ -390,6 +386,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* mma_done = tmem_empty + 2;  // [STAGES], used when CS
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + STAGES);
+  uint64_t* aux_bar = mma_done + STAGES + 1;  // [EW] kTmaEpi x GELU': aux panels of the epilogue warp have landed
 
   const int hw_warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -407,6 +404,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&empty_bar[s], CS ? EW : 1);  // CS: the epilogue warps release the slot after their column sums
       mbar_init(&mma_done[s], 1);
     }
+    for (int s = 0; s < EW; ++s) mbar_init(&aux_bar[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CTA2 ? 2 * EW : EW);  // CTA2: epilogue warps of BOTH CTAs release the leader
@@ -437,7 +435,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    // the whole warp runs the loops (uniform control flow keeps addresses / coordinates in uniform registers);
+    // one elected lane issues the copies
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < total_units; unit += ustride) {
@@ -449,6 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int kb1 = (int)(((long long)(split + 1) * p.num_k_blocks) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
           const int a_row = m_blk * TILE_M + (int)rank * BLOCK_M;
@@ -489,13 +490,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], b_row + c * 64, kb * BLOCK_K);
             }
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0 && rank == 0) {  // CTA2: only the leader CTA issues (for both CTAs)
+    if (rank == 0) {  // CTA2: only the leader CTA issues (for both CTAs); whole warp loops, one elected lane issues
       constexpr uint32_t idesc = umma_idesc(TILE_M, BLOCK_N, 1 /*bf16*/, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
@@ -520,19 +523,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t soff = (uint64_t)(stage * (Cfg::STAGE_BYTES >> 4));
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            if constexpr (CTA2) umma_bf16_ss_2cta(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
-            else umma_bf16_ss(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, accum);
-            accum = 1;
-          }
           // once these MMAs retire: free the smem slot (in both CTAs), or (CS) wake the column-sum warps that free it
           uint64_t* done_bar = CS ? &mma_done[stage] : &empty_bar[stage];
-          if constexpr (CTA2) umma_commit_2cta_mc(done_bar, 3); else umma_commit(done_bar);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if constexpr (CTA2) umma_bf16_ss_2cta(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, (k > 0) ? 1u : accum);
+              else umma_bf16_ss(d_tmem, adesc0 + soff + k * A_KSTEP, bdesc0 + soff + k * B_KSTEP, idesc, (k > 0) ? 1u : accum);
+            }
+            if constexpr (CTA2) umma_commit_2cta_mc(done_bar, 3); else umma_commit(done_bar);
+          }
+          __syncwarp();
+          accum = 1;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs)
-        if constexpr (CTA2) umma_commit_2cta_mc(&tmem_full[as], 3); else umma_commit(&tmem_full[as]);
+        if (elect_one()) {
+          if constexpr (CTA2) umma_commit_2cta_mc(&tmem_full[as], 3); else umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
         if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
       }
     }
@@ -545,6 +554,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t aphase = 0;
     int cstage = 0;
     uint32_t cphase = 0;
+    [[maybe_unused]] uint32_t tphase = 0;   // kTmaEpi x GELU': parity of this warp's aux barrier
     for (int unit = unit0; unit < total_units; unit += ustride) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.num_n_tiles;
@@ -595,7 +605,104 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID || EPI == EPI_DGELU) {
         if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
       }
-      if constexpr (kStaged<EPI> && W == 32) {
+      if constexpr (kTmaEpi<EPI, PART_N>) {
+        // ---- TMA-staged epilogue: no global loads / stores, no bounds predicates (the tensor maps clip) ----
+        uint8_t* buf0 = stg_base + ew * STG_BYTES;   // [32 rows][64 B], unit u of row r at u ^ ((r >> 1) & 3)
+        uint8_t* buf1 = buf0 + 2048;
+        const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
+        const int colp = n_blk * BLOCK_N + part * PART_N;
+        const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + part * PART_N;
+        if constexpr (EPI == EPI_DGELU) {
+          // aux = gelu'(h) panels of this tile are fetched while the tile's MMAs still run
+          if (elect_one()) {
+            tma_store_wait_read();   // the previous tile's output panels have left buf0 / buf1
+            mbar_arrive_expect_tx(&aux_bar[ew], 4096);
+            tma_load_2d(buf0, &tmAux, &aux_bar[ew], colp, row0);
+            tma_load_2d(buf1, &tmAux, &aux_bar[ew], colp + 32, row0);
+          }
+          __syncwarp();
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+          uint32_t acc0[32], acc1[32];
+          tmem_ld_32x32(tacc, acc0);
+          tmem_ld_32x32(tacc + 32, acc1);
+          mbar_wait(&aux_bar[ew], tphase);
+          tmem_ld_wait();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint8_t* buf = hf ? buf1 : buf0;
+            const uint32_t(&acc)[32] = hf ? acc1 : acc0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint4* slot = reinterpret_cast<uint4*>(buf + stg_b16(lane, u));
+              const uint4 du = *slot;
+              const float2 d0 = unpack_bf16x2(du.x), d1 = unpack_bf16x2(du.y), d2 = unpack_bf16x2(du.z), d3 = unpack_bf16x2(du.w);
+              const uint32_t* a = acc + u * 8;
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(a[0]) * (d0.x * rs), __uint_as_float(a[1]) * (d0.y * rs));
+              o.y = pack_bf16x2(__uint_as_float(a[2]) * (d1.x * rs), __uint_as_float(a[3]) * (d1.y * rs));
+              o.z = pack_bf16x2(__uint_as_float(a[4]) * (d2.x * rs), __uint_as_float(a[5]) * (d2.y * rs));
+              o.w = pack_bf16x2(__uint_as_float(a[6]) * (d3.x * rs), __uint_as_float(a[7]) * (d3.y * rs));
+              *slot = o;   // in place: every thread rewrites exactly the 64 bytes it read
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d(&tmOut, buf0, colp, row0);
+            tma_store_2d(&tmOut, buf1, colp + 32, row0);
+            tma_store_commit();
+          }
+          __syncwarp();
+          tphase ^= 1;
+        } else {
+          // bias of this warp's 64 columns -> L1 while the MMAs run
+          if (p.bias != nullptr && lane < 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + colp + lane * 32));
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            const int col0 = colp + hf * 32;
+            uint32_t acc[32];
+            tmem_ld_32x32(tacc + hf * 32, acc);
+            float4 bb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              bb[j] = (p.bias != nullptr && col0 + j * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            tmem_ld_wait();
+            uint32_t act[16], der[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a0, a1, a2, a3, g0, g1, g2, g3;
+              gelu_fwd_bwd(__uint_as_float(acc[j * 4 + 0]) + bb[j].x, a0, g0);
+              gelu_fwd_bwd(__uint_as_float(acc[j * 4 + 1]) + bb[j].y, a1, g1);
+              gelu_fwd_bwd(__uint_as_float(acc[j * 4 + 2]) + bb[j].z, a2, g2);
+              gelu_fwd_bwd(__uint_as_float(acc[j * 4 + 3]) + bb[j].w, a3, g3);
+              act[j * 2] = pack_bf16x2(a0, a1);
+              act[j * 2 + 1] = pack_bf16x2(a2, a3);
+              der[j * 2] = pack_bf16x2(g0, g1);
+              der[j * 2 + 1] = pack_bf16x2(g2, g3);
+            }
+            // the panels of the previous half (or tile) must have been read by the TMA unit before they are overwritten
+            if (elect_one()) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              *reinterpret_cast<uint4*>(buf0 + stg_b16(lane, u)) = make_uint4(act[u * 4], act[u * 4 + 1], act[u * 4 + 2], act[u * 4 + 3]);
+              *reinterpret_cast<uint4*>(buf1 + stg_b16(lane, u)) = make_uint4(der[u * 4], der[u * 4 + 1], der[u * 4 + 2], der[u * 4 + 3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              tma_store_2d(&tmOut, buf0, col0, row0);
+              tma_store_2d(&tmAux, buf1, col0, row0);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
+        }
+      } else if constexpr (kStaged<EPI> && W == 32) {
         uint8_t* stg = stg_base + ew * STG_BYTES;
         const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
         const bool ragged = (EPI == EPI_F32) && p.ragged;
@@ -652,6 +759,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
+    if constexpr (kTmaEpi<EPI, PART_N>) {
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the bulk stores
+      __syncwarp();
+    }
   }
 
   tc_fence_before();
@@ -701,6 +812,16 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   else       rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, 64, BLOCK_K);
   if (rc) return rc;
 
+  CUtensorMap tmOut, tmAux;
+  memset(&tmOut, 0, sizeof(tmOut));
+  memset(&tmAux, 0, sizeof(tmAux));
+  if (kTmaEpi<EPI, BLOCK_N / (EW / 4)>) {
+    rc = vitk_make_tmap_2d_sw64(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 32, 32);
+    if (rc) return rc;
+    rc = vitk_make_tmap_2d_sw64(&tmAux, a->aux, 2, a->N, a->M, a->ld_aux, 32, 32);
+    if (rc) return rc;
+  }
+
   const int sms = vitk_num_sms();
   const int slots = CTA2 ? sms / 2 : sms;
   GemmParams p;
@@ -745,7 +866,7 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, p);
   if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "gemm: launch failed: %s", cudaGetErrorString(e));
   return vitk_check_launch("gemm");
 }

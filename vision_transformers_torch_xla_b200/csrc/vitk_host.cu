@@ -57,13 +57,14 @@ int vitk_num_sms() {
 }
 
 static int encode(CUtensorMap* out, const void* base, int elem_bytes, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                  const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode();
   if (!fn) return vitk_set_error(VITK_ERR_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return vitk_set_error(VITK_ERR_DRIVER,
@@ -80,6 +81,15 @@ int vitk_make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64
   cuuint64_t strides[1] = {ld_elems * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   return encode(out, base, elem_bytes, 2, dims, strides, box);
+}
+
+// 64-byte swizzle (box rows of 32 bf16): the layout of the GEMM epilogue's [32 rows][64 B] staging panels
+int vitk_make_tmap_2d_sw64(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                           uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  return encode(out, base, elem_bytes, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 int vitk_make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
