@@ -390,7 +390,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
 //   |h Phi(h) - gelu(h)| <= 3.4e-5   and   |d/dh [h Phi(h)] - gelu'(h)| <= 9.3e-5   (before the 2^-11 relative error of
 // tanh.approx), i.e. two orders of magnitude below the bf16 rounding of the outputs.  The derivative is the analytic
 // derivative of the approximant:  gelu'(h) ~= Phi + 0.5 h (1 - T^2) (c0 + 3 c1 s + 5 c2 s^2).
-__device__ __forceinline__ void gelu_fwd_bwd(float h, float& act, float& deriv) {
+__device__ __forceinline__ void gelu_fwd_bwd_fast(float h, float& act, float& deriv) {
   constexpr float c0 = 0.79745014f, c1 = 0.0369949746f, c2 = -0.00034728153f;
   const float s = fminf(h * h, 49.0f);
   const float P = fmaf(fmaf(c2, s, c1), s, c0);
@@ -399,6 +399,28 @@ __device__ __forceinline__ void gelu_fwd_bwd(float h, float& act, float& deriv) 
   const float gp = fmaf(fmaf(2.5f * c2, s, 1.5f * c1), s, 0.5f * c0);   // 0.5 * d/dh [h P(h^2)]
   act = h * cdf;
   deriv = fmaf(h * fmaf(-T, T, 1.0f), gp, cdf);
+}
+// Phi(h) = 0.5*(1+erf(h/sqrt2)) via Abramowitz-Stegun 7.1.26 (|erf err| < 1.5e-7) evaluated as
+//   Phi(-|h|) = 0.5*erfc(|h|/sqrt2) = t*(a1+t*(a2+t*(a3+t*(a4+t*a5))))*exp(-h^2/2),  t = 1/(1 + p*|h|/sqrt2)
+// with the 0.5 folded into the coefficients, one MUFU.RCP + one MUFU.EX2; exp(-h^2/2) is shared with the density.
+__device__ __forceinline__ void gelu_fwd_bwd_exact(float h, float& act, float& deriv) {
+  const float t = rcp_approx(fmaf(fabsf(h), 0.3275911f * 0.70710678118654752f, 1.0f));
+  const float e = ex2_approx(h * h * (-0.5f * 1.4426950408889634f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float q = poly * t * e;
+  const float cdf = h > 0.f ? 1.0f - q : q;
+  act = h * cdf;
+  deriv = fmaf(h, e * 0.3989422804014327f, cdf);
+}
+__device__ __forceinline__ void gelu_fwd_bwd(float h, float& act, float& deriv) {
+#ifdef VITK_GELU_FAST
+  gelu_fwd_bwd_fast(h, act, deriv);
+#else
+  gelu_fwd_bwd_exact(h, act, deriv);
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
