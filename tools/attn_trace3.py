@@ -46,3 +46,38 @@ ev.sort()
 t0 = ev[0][0] if ev else 0
 for v, name in ev:
     print(f"{v - t0:8d}  {name}")
+
+# ---- backward (attn_bwd3): item 2 of CTA 0 ----
+dout = torch.randn(B, N, H * 64, device=dev).bfloat16()
+dqkv = torch.empty_like(qkv)
+for _ in range(2):
+    L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, 64, 0.125)
+trace.zero_()
+lib.vitk_debug_set_trace(trace.data_ptr())
+L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, 64, 0.125)
+torch.cuda.synchronize()
+lib.vitk_debug_set_trace(None)
+t = trace.cpu().tolist()
+MMA = ["S_00 issued", "S_10 issued"]
+for j in (0, 1):
+    for w in (0, 1):
+        MMA += [f"P_{w}{j} ready", f"dV+dP_{w}{j} issued"]
+    for w in (0, 1):
+        MMA += [f"dS_{w}{j} ready", f"dK+dQ{'+S' if j == 0 else ''}_{w}{j} issued"]
+GRP = []
+for j in (0, 1):
+    GRP += [f"S_{j} ready", f"P_{j} written", f"dP_{j} ready", f"dS_{j} written", f"drain_{j} may start", f"drain_{j} done"]
+ev = []
+for i, name in enumerate(MMA):
+    if t[i]:
+        ev.append((t[i], f"        mma: {name}"))
+for w in (0, 1):
+    for i, name in enumerate(GRP):
+        v = t[32 + 16 * w + i]
+        if v:
+            ev.append((v, f"group {w}: {name}"))
+ev.sort()
+print("== attn_bwd3")
+t0 = ev[0][0] if ev else 0
+for v, name in ev:
+    print(f"{v - t0:8d}  {name}")

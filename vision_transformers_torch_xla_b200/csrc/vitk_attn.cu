@@ -1455,8 +1455,11 @@ __device__ __forceinline__ void store_rows_coalesced(uint8_t* wst, int lane, con
 __global__ void __launch_bounds__(BWD3_THREADS, 1)
 attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                  const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                 int B, int N, int H, float scale) {
+                 int B, int N, int H, float scale, long long* trace) {
   using L = Bwd3Smem;
+  // timeline of item 2 of CTA 0 (tools/attn_trace3.py bwd): each role appends clock64() stamps to its own slot range
+  int tslot = 0;
+#define BWD3_STAMP(base) do { if (trace != nullptr && blockIdx.x == 0 && n == 2 && lane == 0 && tslot < 32) trace[(base) + tslot++] = clock64(); } while (0)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [w] TMA -> MMA: Q_w, dO_w landed
   uint64_t* bar_kv = bar_q + 2;                                       // [j] TMA -> MMA: K_j, V_j landed
@@ -1552,6 +1555,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
             mbar_wait(&bar_q[w], n & 1);
             tc_fence_after();
             issue_qk(w, 0, 0, &bar_s[w]);
+            BWD3_STAMP(0);
           }
         }
         if (n > 0 || j > 0) {
@@ -1563,6 +1567,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           const uint64_t pdesc = umma_desc_mnmajor(sPDS + w * 2 * TILE_BYTES, TILE_BYTES);
           const uint64_t dodesc = umma_desc_mnmajor(sQDO + (w * 2 + 1) * TILE_BYTES, TILE_BYTES);
           mbar_wait(&bar_p[w], j);
+          BWD3_STAMP(0);
           tc_fence_after();
           if (elect_one()) {   // dV_j += P_w^T dO_w
             for (int k = 0; k < (int)q_eff / 16; ++k)
@@ -1570,6 +1575,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           }
           __syncwarp();
           issue_qk(w, j, 1, &bar_dp[w]);   // dP_wj over S_wj (warpgroup w has turned S into P)
+          BWD3_STAMP(0);
         }
         for (int w = 0; w < 2; ++w) {
           const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
@@ -1579,6 +1585,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           const uint64_t dsdesc_k = umma_desc_kmajor(sDS);
           const uint64_t kdesc = umma_desc_mnmajor(sKV + j * 2 * TILE_BYTES, TILE_BYTES);
           mbar_wait(&bar_ds[w], j);
+          BWD3_STAMP(0);
           tc_fence_after();
           if (elect_one()) {
             for (int k = 0; k < (int)q_eff / 16; ++k)   // dK_j += dS_w^T Q_w
@@ -1592,6 +1599,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
             if (w == 0) mbar_wait(&bar_kv[1], n & 1);
             issue_qk(w, 1, 0, &bar_s[w]);   // SdP_w is free: warpgroup w read dP before it wrote dS
           }
+          BWD3_STAMP(0);
         }
         if (elect_one()) {
           umma_commit(bar_drain);
@@ -1629,6 +1637,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         // ---- S -> P ----
         mbar_wait(&bar_s[w], j);
         tc_fence_after();
+        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
         if (warp_active) {
           uint32_t cur[32], nxt[32];
           tmem_ld_32x32(tm_sdp, cur);
@@ -1658,10 +1667,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_p[w]);
+        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
 
         // ---- dP -> dS (over P) ----
         mbar_wait(&bar_dp[w], j);
         tc_fence_after();
+        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
         if (warp_active) {
           uint32_t cur[32], nxt[32];
           tmem_ld_32x32(tm_sdp, cur);
@@ -1696,10 +1707,12 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_ds[w]);
+        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
 
         // ---- drain dV_j (warpgroup 0) / dK_j (warpgroup 1), and dQ_w after the last kv tile ----
         mbar_wait(bar_drain, j);
         tc_fence_after();
+        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
         {
           const int kv0 = j * TILE + (warp & 3) * 32;   // first kv row of this warp
           if (kv0 < N) {
@@ -1723,9 +1736,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_drained);
+        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
       }
     }
   }
+#undef BWD3_STAMP
 
   tc_fence_before();
   __syncthreads();
@@ -2085,7 +2100,7 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
   if (variant == 0 && N > TILE) {
     const int items = B * H;
     const int g3 = items < vitk_num_sms() ? items : vitk_num_sms();
-    attn_bwd3_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, B, N, H, scale);
+    attn_bwd3_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, B, N, H, scale, g_trace_buf);
     return vitk_check_launch("attn_bwd3");
   }
   if (variant == 2) {

@@ -235,6 +235,26 @@ __device__ __forceinline__ void panel_io_f32(uint8_t* stg, float* g, long long l
     }
   }
 }
+// The same transfer split in two, so that the residual panel of the NEXT iteration is in flight (in registers) while
+// the current panel is processed: global -> registers (issue), registers -> staging (once the buffer is free).
+__device__ __forceinline__ void panel_ldg_f32(float4 (&t)[8], const float* g, long long ld, int row0, int col0, int M, int N,
+                                              int lane) {
+  const int u = lane & 7, c = col0 + u * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((row0 + rr < M) && (c < N)) t[i] = __ldcs(reinterpret_cast<const float4*>(g + (long long)(row0 + rr) * ld + c));
+  }
+}
+__device__ __forceinline__ void panel_sts_f32(uint8_t* stg, const float4 (&t)[8], int lane) {
+  const int u = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    *reinterpret_cast<float4*>(stg + stg_f32(rr, u)) = t[i];
+  }
+}
 // global <-> staging, bf16: 4 instructions, each covering 8 rows x 64 B
 template <bool LOAD>
 __device__ __forceinline__ void panel_io_b16(uint8_t* stg, __nv_bfloat16* g, long long ld, int row0, int col0, int M,
@@ -706,9 +726,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* stg = stg_base + ew * STG_BYTES;
         const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
         const bool ragged = (EPI == EPI_F32) && p.ragged;
-        // second operand of the first panel goes to the staging buffer while the MMAs are still running
+        // second operand of the first panel is fetched while the MMAs are still running; for the residual epilogue
+        // panel c + 1 is in flight (registers) while panel c is processed
+        [[maybe_unused]] float4 rnext[8];
         if constexpr (EPI == EPI_RESID)
-          panel_io_f32<true>(stg, const_cast<float*>(p.resid), p.ld_resid, row0, n_blk * BLOCK_N + part * PART_N, p.M, p.N, lane);
+          panel_ldg_f32(rnext, p.resid, p.ld_resid, row0, n_blk * BLOCK_N + part * PART_N, p.M, p.N, lane);
         if constexpr (EPI == EPI_DGELU)
           panel_io_b16<true>(stg, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ld_aux, row0, n_blk * BLOCK_N + part * PART_N, p.M, p.N, lane);
         mbar_wait(&tmem_full[as], aphase);
@@ -720,15 +742,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col_in_tile;
           uint32_t acc[32];
           tmem_ld_32x32(taddr, acc);
+          if constexpr (EPI == EPI_RESID) {
+            if (!ragged) {
+              panel_sts_f32(stg, rnext, lane);
+              if (c + 1 < PART_N / 32) panel_ldg_f32(rnext, p.resid, p.ld_resid, row0, col0 + 32, p.M, p.N, lane);
+            }
+          }
           tmem_ld_wait();
           if (ragged) {
             epilogue_chunk<EPI, 32>(p, acc, row, col0, rs);
           } else {
             if constexpr (EPI == EPI_RESID || EPI == EPI_DGELU) {
-              if (c > 0) {
-                if constexpr (EPI == EPI_RESID)
-                  panel_io_f32<true>(stg, const_cast<float*>(p.resid), p.ld_resid, row0, col0, p.M, p.N, lane);
-                else
+              if constexpr (EPI == EPI_DGELU) {
+                if (c > 0)
                   panel_io_b16<true>(stg, reinterpret_cast<__nv_bfloat16*>(p.aux), p.ld_aux, row0, col0, p.M, p.N, lane);
               }
               __syncwarp();
