@@ -272,8 +272,8 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         h2d = sum(v.numel() * v.element_size() for v in host[0])
         e2e = {"value": world * args.batch * args.steps / (float(t.item()) / 1e3), "unit": "img/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "api": "engine.train_one_epoch(model, SoftTargetCrossEntropy, pinned-host loader, FusedAdamW, log_freq=1)"}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+               "api": "engine.train_one_epoch(model, SoftTargetCrossEntropy, pinned-host loader -> side-stream H2D prefetch, FusedAdamW, log_freq=1: loss+metric read back every step, one step deferred)"}
 
     if args.breakdown and rank == 0:
         L.breakdown_begin()

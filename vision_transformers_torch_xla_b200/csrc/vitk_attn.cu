@@ -1751,6 +1751,424 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 }
 
 // ================================================================================================
+// Backward, ping-pong variant of attn_bwd3 (same roles, same smem / TMEM layout; 128 < N <= 256).
+//
+// attn_bwd3 keeps the two warpgroups in lockstep (both do P, then both wait for the MMAs, then both do dS ...), so
+// the tensor core idles while the CUDA cores work and vice versa.  Here warpgroup 1 runs half a step behind
+// warpgroup 0: while one warpgroup turns S into P (MUFU), the other turns dP into dS (FP32 pipe), and the MMA
+// warp serves them alternately in the fixed event order E1..E8 below.  What makes that possible with single
+// dV / dK accumulators (TMEM is full) is WHEN they are read out:
+//   * warpgroup 0 drains dV_j (and, after kv tile 1, dQ_0) only after its NEXT P phase, just before it hands P over —
+//     by then dV_j is final (warpgroup 1's P of the same kv tile came half a step later);
+//   * warpgroup 1 drains dK_j (and dQ_1) right after its dS phase, while it waits for its next S anyway.
+// Event order of the MMA warp for item n  (X' = item n+1, "final" = tcgen05.commit on the named barrier):
+//   E1  P_00  -> dV_0  = P_00^T dO_0,  dP_00                      E5  P_01 -> dV_1  = P_01^T dO_0, dP_01
+//   E2a dS_11 of item n-1 -> dK_1 +=, dQ_1 += (final), frees Q_1 dO_1 K_1 V_1      E6  dS_10 -> dK_0 += (final), dQ_1 =, S_11, frees K_0 V_0
+//   E2b S_10                                                       E7  dS_01 -> dK_1 =, dQ_0 += (final), frees Q_0 dO_0
+//   E3  dS_00 -> dK_0 =, dQ_0 =, S_01                              E8  P_11 -> dV_1 += (final), dP_11;  then S_00'
+//   E4  P_10  -> dV_0 += (final), dP_10
+// ================================================================================================
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
+attn_bwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const __grid_constant__ CUtensorMap tm_dqkv, const float* __restrict__ dsum, const float* __restrict__ lse,
+                 int B, int N, int H, float scale, long long* trace) {
+  using L = Bwd3Smem;
+  int tslot = 0;
+#define BWD4_STAMP(base) do { if (trace != nullptr && blockIdx.x == 0 && n == 2 && lane == 0 && tslot < 32) trace[(base) + tslot++] = clock64(); } while (0)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [w] TMA -> MMA: Q_w, dO_w landed
+  uint64_t* bar_kv = bar_q + 2;                                       // [j] TMA -> MMA: K_j, V_j landed
+  uint64_t* empty_kv0 = bar_kv + 2;                                   // MMA -> TMA: K_0, V_0 free
+  uint64_t* empty_q0 = empty_kv0 + 1;                                 // MMA -> TMA: Q_0, dO_0 free
+  uint64_t* empty_rest = empty_q0 + 1;                                // MMA -> TMA: Q_1, dO_1, K_1, V_1 free
+  uint64_t* bar_s = empty_rest + 1;                                   // [w] MMA -> WG: S_wj ready
+  uint64_t* bar_p = bar_s + 2;                                        // [w] WG -> MMA: P_wj in smem
+  uint64_t* bar_dp = bar_p + 2;                                       // [w] MMA -> WG: dP_wj ready, P_wj consumed
+  uint64_t* bar_ds = bar_dp + 2;                                      // [w] WG -> MMA: dS_wj in smem
+  uint64_t* bar_dvf = bar_ds + 2;                                     // MMA -> WG0: dV_j final
+  uint64_t* bar_dkf = bar_dvf + 1;                                    // MMA -> WG1: dK_j final (j = 1: dQ_1 too)
+  uint64_t* bar_dq0f = bar_dkf + 1;                                   // MMA -> WG0: dQ_0 final
+  uint64_t* drained_dk = bar_dq0f + 1;                                // WG1 -> MMA: dK_j (and dQ_1) read out
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained_dk + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = B * H;
+  const int G = (int)gridDim.x;
+  const uint32_t eff1 = roundup16(N - TILE);   // rows of q tile 1 == columns of kv tile 1, rounded up to the MMA K step
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_q[i], 1);
+      mbar_init(&bar_kv[i], 1);
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 4);
+      mbar_init(&bar_dp[i], 1);
+      mbar_init(&bar_ds[i], 4);
+    }
+    mbar_init(empty_kv0, 1);
+    mbar_init(empty_q0, 1);
+    mbar_init(empty_rest, 1);
+    mbar_init(bar_dvf, 1);
+    mbar_init(bar_dkf, 1);
+    mbar_init(bar_dq0f, 1);
+    mbar_init(drained_dk, 4);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
+
+  if (warp == 9) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      int n = 0;
+      for (int it = blockIdx.x; it < items; it += G, ++n) {
+        const int h = it % H, b = it / H;
+        if (n > 0) mbar_wait(empty_kv0, (n - 1) & 1);
+        mbar_arrive_expect_tx(&bar_kv[0], 2 * TILE_BYTES);
+        tma_load_3d(smem + L::KV_OFF, &tm_qkv, &bar_kv[0], (H + h) * HD, 0, b);
+        tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, &bar_kv[0], (2 * H + h) * HD, 0, b);
+        if (n > 0) mbar_wait(empty_q0, (n - 1) & 1);
+        mbar_arrive_expect_tx(&bar_q[0], 2 * TILE_BYTES);
+        tma_load_3d(smem + L::QDO_OFF, &tm_qkv, &bar_q[0], h * HD, 0, b);
+        tma_load_3d(smem + L::QDO_OFF + TILE_BYTES, &tm_do, &bar_q[0], h * HD, 0, b);
+        if (n > 0) mbar_wait(empty_rest, (n - 1) & 1);
+        mbar_arrive_expect_tx(&bar_q[1], 2 * TILE_BYTES);
+        tma_load_3d(smem + L::QDO_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_q[1], h * HD, TILE, b);
+        tma_load_3d(smem + L::QDO_OFF + 3 * TILE_BYTES, &tm_do, &bar_q[1], h * HD, TILE, b);
+        mbar_arrive_expect_tx(&bar_kv[1], 2 * TILE_BYTES);
+        tma_load_3d(smem + L::KV_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_kv[1], (H + h) * HD, TILE, b);
+        tma_load_3d(smem + L::KV_OFF + 3 * TILE_BYTES, &tm_qkv, &bar_kv[1], (2 * H + h) * HD, TILE, b);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer (whole warp runs the program, one elected lane issues) ------------------------------
+    const uint32_t sQDO = smem_u32(smem + L::QDO_OFF), sKV = smem_u32(smem + L::KV_OFF), sPDS = smem_u32(smem + L::PDS_OFF);
+    const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);    // A, B MN-major: P^T dO, dS^T Q
+    const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);   // dS K
+    // S_wj = Q_w K_j^T (what == 0) or dP_wj = dO_w V_j^T (what == 1) into SdP_w
+    auto issue_qk = [&](int w, int j, int what, uint64_t* bar) {
+      const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
+      const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+      const uint64_t adesc = umma_desc_kmajor(sQDO + (w * 2 + what) * TILE_BYTES);
+      const uint64_t bdesc = umma_desc_kmajor(sKV + (j * 2 + what) * TILE_BYTES);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + w * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
+        umma_commit(bar);
+      }
+      __syncwarp();
+    };
+    // dV_j (+)= P_w^T dO_w  (fin: commit bar_dvf), then dP_wj
+    auto issue_dv_dp = [&](int w, int j, bool fin) {
+      const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
+      const uint64_t pdesc = umma_desc_mnmajor(sPDS + w * 2 * TILE_BYTES, TILE_BYTES);
+      const uint64_t dodesc = umma_desc_mnmajor(sQDO + (w * 2 + 1) * TILE_BYTES, TILE_BYTES);
+      if (elect_one()) {
+        for (int k = 0; k < (int)q_eff / 16; ++k)
+          umma_bf16_ss(tm_dv, pdesc + (uint64_t)(k * 128), dodesc + (uint64_t)(k * 128), idesc_t, (w > 0 || k > 0));
+        if (fin) umma_commit(bar_dvf);
+      }
+      __syncwarp();
+      issue_qk(w, j, 1, &bar_dp[w]);
+    };
+    // dK_j (+)= dS_w^T Q_w ; dQ_w (+)= dS_w K_j
+    auto issue_dk_dq = [&](int w, int j) {
+      const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
+      const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
+      const uint32_t sDS = sPDS + w * 2 * TILE_BYTES;
+      const uint64_t dsdesc_t = umma_desc_mnmajor(sDS, TILE_BYTES);
+      const uint64_t qdesc = umma_desc_mnmajor(sQDO + w * 2 * TILE_BYTES, TILE_BYTES);
+      const uint64_t dsdesc_k = umma_desc_kmajor(sDS);
+      const uint64_t kdesc = umma_desc_mnmajor(sKV + j * 2 * TILE_BYTES, TILE_BYTES);
+      if (elect_one()) {
+        for (int k = 0; k < (int)q_eff / 16; ++k)
+          umma_bf16_ss(tm_dk, dsdesc_t + (uint64_t)(k * 128), qdesc + (uint64_t)(k * 128), idesc_t, (w > 0 || k > 0));
+        for (int k = 0; k < (int)n_eff / 16; ++k)
+          umma_bf16_ss(tm_dq + w * HD, dsdesc_k + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), kdesc + (uint64_t)(k * 128),
+                       idesc_q, (j > 0 || k > 0));
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    // Two in-order event queues, one per warpgroup, served in arrival order (non-blocking barrier tests): warpgroup 0's
+    // queue is  S_00 | E1 | E3 | E5 | E7,  warpgroup 1's is  E2b (S_10) | E4 | E6 | E8 | E2a (of the same item).
+    // Warpgroup 1's accumulating MMAs may only follow warpgroup 0's initialising ones (E4 after E1, E6 after E3, E8 after
+    // E5, E2a after E7); everything else the two queues need from each other travels through the mbarriers tested here.
+    const int nitems = (int)blockIdx.x < items ? (items - (int)blockIdx.x + G - 1) / G : 0;
+    int n0 = 0, k0 = 0, n1 = 0, k1 = 0;
+    [[maybe_unused]] const int n = 0;
+    while (n1 < nitems) {
+      if (n0 < nitems) {
+        const uint32_t par = n0 & 1;
+        bool ready = false;
+        switch (k0) {
+          case 0: ready = mbar_test(&bar_kv[0], par) && mbar_test(&bar_q[0], par); break;
+          case 1: ready = mbar_test(&bar_p[0], 0); break;
+          case 2: ready = mbar_test(&bar_ds[0], 0) && (n0 == 0 || mbar_test(drained_dk, 1)) && mbar_test(&bar_kv[1], par); break;
+          case 3: ready = mbar_test(&bar_p[0], 1); break;
+          default: ready = mbar_test(&bar_ds[0], 1) && mbar_test(drained_dk, 0); break;
+        }
+        if (ready) {
+          tc_fence_after();
+          switch (k0) {
+            case 0: issue_qk(0, 0, 0, &bar_s[0]); break;
+            case 1: issue_dv_dp(0, 0, false); break;
+            case 2:
+              issue_dk_dq(0, 0);
+              issue_qk(0, 1, 0, &bar_s[0]);
+              break;
+            case 3: issue_dv_dp(0, 1, false); break;
+            default:
+              issue_dk_dq(0, 1);
+              commit(bar_dq0f);
+              commit(empty_q0);
+              break;
+          }
+          if (++k0 == 5) { k0 = 0; ++n0; }
+        }
+      }
+      {
+        const uint32_t par = n1 & 1;
+        const bool ahead = n0 > n1;   // warpgroup 0's queue has finished this item
+        bool ready = false;
+        switch (k1) {
+          case 0: ready = mbar_test(&bar_q[1], par) && mbar_test(&bar_kv[0], par); break;
+          case 1: ready = (ahead || k0 > 1) && mbar_test(&bar_p[1], 0); break;
+          case 2: ready = (ahead || k0 > 2) && mbar_test(&bar_ds[1], 0); break;
+          case 3: ready = (ahead || k0 > 3) && mbar_test(&bar_p[1], 1); break;
+          default: ready = ahead && mbar_test(&bar_ds[1], 1); break;
+        }
+        if (ready) {
+          tc_fence_after();
+          switch (k1) {
+            case 0: issue_qk(1, 0, 0, &bar_s[1]); break;
+            case 1: issue_dv_dp(1, 0, true); break;
+            case 2:
+              issue_dk_dq(1, 0);
+              commit(bar_dkf);
+              commit(empty_kv0);
+              issue_qk(1, 1, 0, &bar_s[1]);
+              break;
+            case 3: issue_dv_dp(1, 1, true); break;
+            default:
+              issue_dk_dq(1, 1);
+              commit(bar_dkf);
+              commit(empty_rest);
+              break;
+          }
+          if (++k1 == 5) { k1 = 0; ++n1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ warpgroup w: rows of q tile w ------------------------------
+    const int w = warp >> 2, r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tm_sdp = tmem_base + w * 128 + lane_addr;
+    uint8_t* sPDS = smem + L::PDS_OFF + w * 2 * TILE_BYTES;
+    uint8_t* wst = smem + L::STG_OFF + warp * 4096;
+    const int q = w * TILE + r;
+    const bool row_ok = q < N;
+    const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
+    const bool warp_active = (uint32_t)((warp & 3) * 32) < q_eff;   // some row of this warp is read by the dV / dK MMAs
+    const float c2 = scale * LOG2E;
+    // this warp's 32 accumulator rows (64 fp32 columns at TMEM column `tcol`) -> rows [row_first, ...) of part `which`
+    // (0 = dQ, 1 = dK, 2 = dV) of head h of image b: bf16 into the warp's swizzled 4 KB tile, one TMA store (rows >= N
+    // are clipped by the tensor map).  The previous store of this warp has long been read when the next one starts.
+    auto drain = [&](uint32_t tcol, int which, int b, int h, int row_first) {
+      if (row_first < N) {
+        uint32_t a0[32], a1[32];
+        tmem_ld_32x32(tcol + lane_addr, a0);
+        tmem_ld_32x32(tcol + lane_addr + 32, a1);
+        if (elect_one()) tma_store_wait_read();
+        __syncwarp();
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t(&v)[32] = u < 4 ? a0 : a1;
+          const int e = (u & 3) * 8;
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[e + 0]), __uint_as_float(v[e + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+          *reinterpret_cast<uint4*>(wst + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_3d(&tm_dqkv, wst, (which * H + h) * HD, row_first, b);
+          tma_store_commit();
+        }
+        __syncwarp();
+      }
+    };
+    int n = 0;
+    int pb = 0, ph = 0;   // previous item (warpgroup 0 drains it one P phase late)
+    for (int it = blockIdx.x; it < items; it += G, ++n) {
+      const int h = it % H, b = it / H;
+      float my_lse2 = 0.f, my_ds = 0.f;   // rows >= N: P = 2^S stays finite, dS = 0
+      if (row_ok) {
+        my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
+        my_ds = dsum[((long long)b * H + h) * N + q] * scale;
+      }
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
+        const int nch = (int)(n_eff + 31) / 32;   // 32-column chunks (the last one may be half)
+
+        // ---- S -> P ----
+        mbar_wait(&bar_s[w], j);
+        tc_fence_after();
+        if ((warp & 3) == 0) BWD4_STAMP(32 + 16 * w);
+        if (warp_active) {
+          uint32_t ra[32], rb[32];
+          auto p_chunk = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                pk[i] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * i]), c2, -my_lse2)),
+                                    ex2_approx(fmaf(__uint_as_float(v[g * 8 + 2 * i + 1]), c2, -my_lse2)));
+              st_swz(sPDS, r, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            }
+          };
+          tmem_ld_32x32(tm_sdp, ra);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; c += 2) {
+            if (c < nch) {
+              if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, rb);
+              p_chunk(ra, c);
+              if (c + 1 < nch) {
+                tmem_ld_wait();
+                if (c + 2 < nch) tmem_ld_32x32(tm_sdp + (c + 2) * 32, ra);
+                p_chunk(rb, c + 1);
+                if (c + 2 < nch) tmem_ld_wait();
+              }
+            }
+          }
+        }
+        if (w == 0) {
+          // deferred read-out: dV of the previous kv tile (and dQ_0 of the previous item) are final by now
+          if (j == 1) {
+            mbar_wait(bar_dvf, 0);
+            tc_fence_after();
+            drain(tm_dv, 2, b, h, (warp & 3) * 32);
+          } else if (n > 0) {
+            mbar_wait(bar_dvf, 1);
+            tc_fence_after();
+            drain(tm_dv, 2, pb, ph, TILE + (warp & 3) * 32);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_p[w]);
+        if ((warp & 3) == 0) BWD4_STAMP(32 + 16 * w);
+
+        // ---- dP -> dS (over P) ----
+        mbar_wait(&bar_dp[w], j);
+        tc_fence_after();
+        if ((warp & 3) == 0) BWD4_STAMP(32 + 16 * w);
+        if (warp_active) {
+          uint32_t ra[32], rb[32];
+          auto ds_chunk = [&](const uint32_t (&v)[32], int c) {
+            uint4 pall[4];   // all four loads first: the compiler cannot hoist them above the (possibly aliasing) stores
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              pall[g] = *reinterpret_cast<const uint4*>(sPDS + ((c * 4 + g) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + g) & 7) ^ (r & 7)) << 4));
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint8_t* slot = sPDS + ((c * 4 + g) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + g) & 7) ^ (r & 7)) << 4);
+              const uint4 pu = pall[g];
+              const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
+              uint32_t ds[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 pp = unpack_bf16x2(pw[i]);
+                ds[i] = pack_bf16x2(pp.x * fmaf(__uint_as_float(v[g * 8 + 2 * i]), scale, -my_ds),
+                                    pp.y * fmaf(__uint_as_float(v[g * 8 + 2 * i + 1]), scale, -my_ds));
+              }
+              *reinterpret_cast<uint4*>(slot) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
+            }
+          };
+          tmem_ld_32x32(tm_sdp, ra);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 4; c += 2) {
+            if (c < nch) {
+              if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, rb);
+              ds_chunk(ra, c);
+              if (c + 1 < nch) {
+                tmem_ld_wait();
+                if (c + 2 < nch) tmem_ld_32x32(tm_sdp + (c + 2) * 32, ra);
+                ds_chunk(rb, c + 1);
+                if (c + 2 < nch) tmem_ld_wait();
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_ds[w]);
+        if ((warp & 3) == 0) BWD4_STAMP(32 + 16 * w);
+
+        if (w == 0 && j == 1) {
+          // dQ_0 is final once the MMAs fed by this dS retire; read it out while the next item's Q_0 is still loading
+          mbar_wait(bar_dq0f, n & 1);
+          tc_fence_after();
+          drain(tm_dq, 0, b, h, (warp & 3) * 32);
+        }
+        if (w == 1) {
+          // dK_j is final half a step after this warpgroup's dS (it is the second contributor); read it out while
+          // waiting for the next S anyway.  After kv tile 1 the same holds for dQ_1.
+          mbar_wait(bar_dkf, j);
+          tc_fence_after();
+          drain(tm_dk, 1, b, h, j * TILE + (warp & 3) * 32);
+          if (j == 1) drain(tm_dq + HD, 0, b, h, TILE + (warp & 3) * 32);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained_dk);
+          if ((warp & 3) == 0) BWD4_STAMP(32 + 16 * w);
+        }
+      }
+      pb = b;
+      ph = h;
+    }
+    if (w == 0 && n > 0) {   // the last item's deferred read-out
+      mbar_wait(bar_dvf, 1);
+      tc_fence_after();
+      drain(tm_dv, 2, pb, ph, TILE + (warp & 3) * 32);
+    }
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // smem must outlive the bulk stores
+    __syncwarp();
+  }
+#undef BWD4_STAMP
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
 // Backward, streaming variant for 256 < N <= 640 (ViT-L/16 at 384 px: N = 577): one CTA per (b, h, kv tile j).
 // K_j / V_j stay resident, Q_i / dO_i stream through one smem buffer, dV_j / dK_j accumulate in TMEM over the
 // q tiles, and each dQ_ij partial is read out of a TMEM scratch tile and red.add'ed into an fp32 workspace
@@ -2059,6 +2477,8 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -2097,11 +2517,19 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     const char* e = getenv("VITK_ATTN_BWD");
     return e ? atoi(e) : 0;
   }();
-  if (variant == 0 && N > TILE) {
+  if ((variant == 0 || variant == 3) && N > TILE) {
     const int items = B * H;
     const int g3 = items < vitk_num_sms() ? items : vitk_num_sms();
-    attn_bwd3_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, B, N, H, scale, g_trace_buf);
-    return vitk_check_launch("attn_bwd3");
+    if (variant == 3) {   // lockstep predecessor, kept for comparison
+      attn_bwd3_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, B, N, H, scale, g_trace_buf);
+      return vitk_check_launch("attn_bwd3");
+    }
+    CUtensorMap tm_dqkv;   // 32-row boxes: one per warp-level read-out of dQ / dK / dV
+    rc = vitk_make_tmap_3d(&tm_dqkv, dqkv, 2, (uint64_t)3 * H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)3 * H * HD,
+                           (uint64_t)N * 3 * H * HD, HD, 32, 1);
+    if (rc) return rc;
+    attn_bwd4_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, tm_dqkv, dsum, lse, B, N, H, scale, g_trace_buf);
+    return vitk_check_launch("attn_bwd4");
   }
   if (variant == 2) {
     attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, scale,

@@ -40,6 +40,35 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
         log_writer.set_step(epoch * num_training_steps_per_epoch * update_freq)
     optimizer.zero_grad()
     last_loss = None
+    on_gpu = torch.device(device).type == "cuda"
+    pinned = [torch.empty(2, dtype=torch.float32, pin_memory=on_gpu) for _ in range(2)]
+    pending = None
+
+    def _enqueue_read(loss_t, acc_t, nsamp, lr_now, buf):
+        vals = torch.stack([loss_t.detach().float().reshape(()), (acc_t if acc_t is not None else loss_t.detach()).float().reshape(())])
+        buf.copy_(vals, non_blocking=True)
+        ev = None
+        if on_gpu:
+            ev = torch.cuda.Event()
+            ev.record()
+        return ev, buf, acc_t is not None, nsamp, lr_now
+
+    def _consume(p):
+        ev, buf, has_acc, nsamp, lr_now = p
+        if ev is not None:
+            ev.synchronize()
+        metric_logger.update(loss=float(buf[0]))
+        if has_acc:
+            metric_logger.meters["class_acc"].update(float(buf[1]), n=nsamp)
+        metric_logger.update(lr=lr_now)
+        if log_writer is not None:
+            log_writer.update(loss=metric_logger.meters["loss"].value, lr=lr_now)
+        if wandb_logger is not None:
+            wandb_logger._wandb.log({"train/loss": metric_logger.meters["loss"].value, "train/learning_rate": lr_now,
+                                     "train/epoch": epoch})
+
+    if on_gpu:
+        data_loader = utils.DevicePrefetcher(data_loader, torch.device(device))   # H2D of batch i+1 overlaps step i
     for data_iter_step, (samples, targets) in enumerate(metric_logger.log_every(data_loader, 10, header, quiet=quiet)):
         step = data_iter_step // update_freq
         if num_training_steps_per_epoch is not None and step >= num_training_steps_per_epoch:
@@ -77,15 +106,14 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
             class_acc = None
         lr = optimizer.param_groups[0]["lr"]
         if data_iter_step % log_freq == 0 or data_iter_step < 5:
-            metric_logger.update(loss=loss.item())  # the only host<->device sync of the step
-            if class_acc is not None:
-                metric_logger.meters["class_acc"].update(class_acc.item(), n=samples.size(0))
-            metric_logger.update(lr=lr)
-            if log_writer is not None:
-                log_writer.update(loss=metric_logger.meters["loss"].value, lr=lr)
-            if wandb_logger is not None:
-                wandb_logger._wandb.log({"train/loss": metric_logger.meters["loss"].value, "train/learning_rate": lr,
-                                         "train/epoch": epoch, "train/step": start_steps + data_iter_step})
+            # The device -> host read of this step's loss is asynchronous (pinned buffer + event) and consumed one step
+            # later, so the host keeps enqueuing the next step while the GPU finishes this one; the reference blocks on
+            # loss.item() after every step (/root/reference/engine.py:278-299).
+            if pending is not None:
+                _consume(pending)
+            pending = _enqueue_read(loss, class_acc, samples.size(0), lr, pinned[data_iter_step & 1])
+    if pending is not None:
+        _consume(pending)
     if last_loss is not None and "loss" not in metric_logger.meters:
         metric_logger.update(loss=last_loss.item())
     metric_logger.synchronize_between_processes()

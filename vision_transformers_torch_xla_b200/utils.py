@@ -151,6 +151,41 @@ class MetricLogger:
             i += 1
 
 
+class DevicePrefetcher:
+    """Host -> device input path of the training loop (replaces torch_xla's MpDeviceLoader, /root/reference/main.py:1017):
+    batch i+1 is copied from (pinned) host memory on a side stream while batch i is being trained on, so the H2D
+    copy (155 MB per 256 x 3 x 224 x 224 fp32 batch) never sits on the compute stream's critical path."""
+
+    def __init__(self, loader, device: torch.device):
+        self.loader = loader
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _fetch(self, it):
+        try:
+            batch = next(it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self.stream):
+            return tuple(t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        nxt = self._fetch(it)
+        while nxt is not None:
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_stream(self.stream)          # batch i has landed
+            for t in nxt:
+                if torch.is_tensor(t):
+                    t.record_stream(cur)          # keep its memory until the compute stream is done with it
+            batch = nxt
+            nxt = self._fetch(it)                 # batch i+1 starts copying now, overlapping the step on batch i
+            yield batch
+
+
 def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1,)):
     """timm.utils.accuracy: top-k accuracy in percent."""
     maxk = min(max(topk), output.size(1))
