@@ -147,7 +147,19 @@ def gemm_timing_end():
     global _gemm_timing
     rec, _gemm_timing = _gemm_timing or [], None
     torch.cuda.synchronize()
-    return (sum(f for f, _, _ in rec), sum(a.elapsed_time(b) for _, a, b in rec), len(rec))
+    return (sum(r[0] for r in rec), sum(r[1].elapsed_time(r[2]) for r in rec), len(rec))
+
+
+def gemm_timing_end_by_shape():
+    """Like gemm_timing_end(), plus {family: (flops, ms, launches)} per GEMM role / shape."""
+    global _gemm_timing
+    rec, _gemm_timing = _gemm_timing or [], None
+    torch.cuda.synchronize()
+    by = {}
+    for f, a, b, fam in rec:
+        fl, ms, n = by.get(fam, (0.0, 0.0, 0))
+        by[fam] = (fl + f, ms + a.elapsed_time(b), n + 1)
+    return (sum(v[0] for v in by.values()), sum(v[1] for v in by.values()), len(rec)), by
 
 
 def breakdown_begin() -> None:
@@ -181,7 +193,7 @@ class _Timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             if _gemm_timing is not None and self.flops:
-                _gemm_timing.append((self.flops, self.e0, e1))
+                _gemm_timing.append((self.flops, self.e0, e1, self.family))
             if _breakdown is not None:
                 _breakdown.setdefault(self.family, []).append((self.e0, e1))
         return False
