@@ -20,6 +20,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
