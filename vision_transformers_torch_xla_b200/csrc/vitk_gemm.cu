@@ -580,6 +580,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = tile / p.num_n_tiles;
       const int row = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32 + lane;
+      // The accumulator stage goes back to the MMA warp as soon as this warp has READ its last column out of TMEM:
+      // the rest of the epilogue (math, staging, stores) then overlaps the MMAs of the tile after next.
+      bool released = false;
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CTA2 && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0);
+          else mbar_arrive(&tmem_empty[as]);
+        }
+        released = true;
+      };
       if constexpr (CS) {
         // second consumer of the smem ring: per k-block wait for the MMAs, (n_blk == 0 tiles only) add this thread's
         // 8 columns x 4 k-rows of the swizzled MN-major A tile, then release the slot to the producer
@@ -648,6 +660,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_32x32(tacc + 32, acc1);
           mbar_wait(&aux_bar[ew], tphase);
           tmem_ld_wait();
+          release_acc();
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             uint8_t* buf = hf ? buf1 : buf0;
@@ -691,6 +704,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               bb[j] = (p.bias != nullptr && col0 + j * 4 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j)
                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
+            if (hf == 1) release_acc();
             uint32_t act[16], der[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -749,6 +763,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           tmem_ld_wait();
+          if (c + 1 == PART_N / 32) release_acc();
           if (ragged) {
             epilogue_chunk<EPI, 32>(p, acc, row, col0, rs);
           } else {
@@ -774,15 +789,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if constexpr (W == 32) tmem_ld_32x32(taddr, acc);
           else tmem_ld_32x16(taddr, acc);
           tmem_ld_wait();
+          if (c + 1 == PART_N / W) release_acc();
           epilogue_chunk<EPI, W>(p, acc, row, n_blk * BLOCK_N + col_in_tile, rs);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTA2 && rank != 0) mbar_arrive_remote(&tmem_empty[as], 0);
-        else mbar_arrive(&tmem_empty[as]);
-      }
+      if (!released) release_acc();
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
     if constexpr (kTmaEpi<EPI, PART_N>) {
