@@ -168,9 +168,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
-      if (dgamma) atomicAdd(dgamma + i, red[i]);
-      if (dbeta) atomicAdd(dbeta + i, red[dim + i]);
+    // one 16-byte reduction per 4 columns (every CTA of the grid hits the same 2*dim addresses at the end of the kernel)
+    for (int i = threadIdx.x; i < (dim >> 2); i += blockDim.x) {
+      const float4 a = *reinterpret_cast<const float4*>(red + i * 4);
+      const float4 b = *reinterpret_cast<const float4*>(red + dim + i * 4);
+      if (dgamma)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dgamma + i * 4), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+      if (dbeta)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbeta + i * 4), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
     }
   }
 }
@@ -215,6 +220,8 @@ extern "C" int vitk_layernorm_bwd(const void* dy_bf16, int64_t ld_dy, const floa
   VITK_REQUIRE(dim % 4 == 0 && dim <= MAXV * 128, VITK_ERR_SHAPE, "layernorm_bwd: dim=%d must be a multiple of 4 and <= %d", dim, MAXV * 128);
   VITK_REQUIRE(ld_x % 4 == 0 && ld_dy % 4 == 0 && ld_g % 4 == 0, VITK_ERR_ALIGN, "layernorm_bwd: row pitches must be multiples of 4 elements");
   VITK_REQUIRE(mean && rstd && g_out, VITK_ERR_SHAPE, "layernorm_bwd: mean/rstd/g_out required");
+  VITK_REQUIRE(((uintptr_t)dgamma & 15) == 0 && ((uintptr_t)dbeta & 15) == 0, VITK_ERR_ALIGN,
+               "layernorm_bwd: dgamma / dbeta must be 16-byte aligned (vector reductions)");
   if (rows == 0) return VITK_OK;
 #define VITK_LN_BWD(V)                                                                                          \
   return launch_ln_bwd<V>(dy_bf16, ld_dy, x, ld_x, mean, rstd, gamma, g_in, g_out, ld_g, gb_out_bf16, rowscale, \
