@@ -1095,6 +1095,302 @@ int launch_fwd3(const CUtensorMap& tm, void* out, float* lse, int B, int N, int 
   return vitk_check_launch("attn_fwd3");
 }
 
+// ================================================================================================
+// Forward, one-thread-per-row variant of attn_fwd3 (same smem stages, barriers, TMEM slots and TMA-stored O).
+// 11 warps: group g = warps 4g..4g+3 (thread = score row of q tile g), warp 8 + g issues group g's MMAs, warp 10 is
+// the TMA producer.  With 168 registers per thread the score row is processed in 32-column chunks that are
+// double-buffered in registers and fully unrolled (the structure of the backward's P phase, which sustains ~10 cycles
+// per exp per warp; attn_fwd3's 16-column rolled loop with two threads per row needed ~29), there is no max / sum
+// exchange and no named barrier, and P is one contiguous run of packed columns [0, n_eff / 2) written in place
+// behind the read pointer.
+// ================================================================================================
+constexpr int FWD4_THREADS = 11 * 32;
+
+__global__ void __launch_bounds__(FWD4_THREADS, 1)
+attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
+                 int B, int N, int H, float scale, long long* trace) {
+  using L = Fwd3Smem;
+#define FWD4_STAMP(base, ev) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && (n == 2 || n == 3)) trace[(base) + 8 * (n - 2) + (ev)] = clock64(); } while (0)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [2] TMA -> MMA warps
+  uint64_t* stage_empty = stage_full + 2;                                  // [2] MMA warps -> TMA
+  uint64_t* s_full = stage_empty + 2;                                      // [g] MMA -> group: S ready
+  uint64_t* p_full = s_full + 2;                                           // [g] group -> MMA: P written
+  uint64_t* o_full = p_full + 2;                                           // [g] MMA -> group: O ready
+  uint64_t* slot_free = o_full + 2;                                        // [g] group -> MMA: O read out
+  uint64_t* o_staged = slot_free + 2;                                      // [g] group -> MMA: bf16 O tile in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_staged + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = B * H;
+  const uint32_t n_eff = roundup16(N);
+  const int KS = (int)n_eff / 16;           // k-steps of P V
+  const int nch = ((int)n_eff + 31) / 32;   // 32-column chunks of the score row (the last one may be half)
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_full[i], 1);
+      mbar_init(&stage_empty[i], 4);   // per MMA warp: Q/K/V reads retired + its group's O staging tile stored
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);        // one arrival per softmax warp
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_free[i], 4);
+      mbar_init(&o_staged[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 10) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 10) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      int n = 0;
+      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int st = n & 1;
+        const int h = it % H, b = it / H;
+        mbar_wait(&stage_empty[st], ((n >> 1) & 1) ^ 1);
+        uint8_t* base = smem + st * L::STAGE;
+        mbar_arrive_expect_tx(&stage_full[st], L::STAGE);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          tma_load_3d(base + t * TILE_BYTES, &tm_qkv, &stage_full[st], h * HD, t * TILE, b);
+          tma_load_3d(base + (2 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (H + h) * HD, t * TILE, b);
+          tma_load_3d(base + (4 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (2 * H + h) * HD, t * TILE, b);
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------ MMA issuer of group g (uniform control flow, one elected lane issues) ------------------------------
+    const int g = warp - 8;
+    const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
+    const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P (TMEM, K-major), B = V MN-major
+    const uint32_t slot = tmem_base + g * 256;
+    auto store_o = [&](int m, int item) {
+      const int st = m & 1;
+      mbar_wait(&o_staged[g], m & 1);
+      if (elect_one()) {
+        tma_store_3d(&tm_out, smem + st * L::STAGE + g * TILE_BYTES, (item % H) * HD, g * TILE, item / H);  // rows >= N clipped
+        tma_store_commit_and_wait_read();
+        mbar_arrive(&stage_empty[st]);
+      }
+      __syncwarp();
+    };
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int st = n & 1;
+      const uint32_t sbase = smem_u32(smem + st * L::STAGE);
+      const uint32_t sQ = sbase + g * TILE_BYTES, sK = sbase + 2 * TILE_BYTES, sV = sbase + 4 * TILE_BYTES;
+      mbar_wait(&stage_full[st], (n >> 1) & 1);
+      FWD4_STAMP(32 + 16 * g, 0);
+      if (n > 0) mbar_wait(&slot_free[g], (n - 1) & 1);
+      else if (g == 1) mbar_wait(&p_full[0], 0);   // group 1 starts half an item late
+      FWD4_STAMP(32 + 16 * g, 1);
+      tc_fence_after();
+      const uint64_t qdesc = umma_desc_kmajor(sQ), kdesc = umma_desc_kmajor(sK);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+      FWD4_STAMP(32 + 16 * g, 2);
+      if (n > 0) store_o(n - 1, it - (int)gridDim.x);   // nothing else to do until this group's P arrives
+      mbar_wait(&p_full[g], n & 1);
+      FWD4_STAMP(32 + 16 * g, 3);
+      tc_fence_after();
+      const uint64_t vdesc = umma_desc_mnmajor(sV, TILE_BYTES);
+      if (elect_one()) {
+        for (int ks = 0; ks < KS; ++ks) umma_bf16_ts(slot + 192, slot + 8 * ks, vdesc + (uint64_t)(ks * 128), idesc_o, ks > 0);
+        umma_commit(&o_full[g]);
+        umma_commit(&stage_empty[st]);  // this group's reads of Q_g / K / V have retired
+      }
+      __syncwarp();
+      FWD4_STAMP(32 + 16 * g, 4);
+    }
+    if (n > 0) {
+      store_o(n - 1, blockIdx.x + (n - 1) * (int)gridDim.x);
+      if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the store
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------ softmax group g: 128 threads, thread = score row ------------------------------
+    const int g = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t slot = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int qn = g == 0 ? min(TILE, N) : N - TILE;   // valid rows of this q tile
+    const bool active = quarter * 32 < qn;             // warp-uniform: some row of this warp is real
+    const float c2 = scale * LOG2E;
+    const int q = g * TILE + r;
+    int n = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      mbar_wait(&s_full[g], n & 1);
+      tc_fence_after();
+      if (quarter == 0) FWD4_STAMP(16 * g, 0);
+      uint32_t ra[32], rb[32];
+      float mx = 0.f, l = 1.f;
+      if (active) {
+        // ---- pass 1: row maximum ----
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        auto mx_chunk = [&](const uint32_t (&v)[32], int c) {
+          if (c * 32 + 32 <= N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < N) m0 = fmaxf(m0, __uint_as_float(v[i]));
+          }
+        };
+        // (four chunks in flight per round trip do not help: with the other group's exps queued in the same MIO
+        // pipe a tcgen05.ld takes ~700 cycles here against ~40 on an idle SM, and the extra registers cost more)
+        tmem_ld_32x32(slot, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          if (c < nch) {
+            if (c + 1 < nch) tmem_ld_32x32(slot + (c + 1) * 32, rb);
+            mx_chunk(ra, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32(slot + (c + 2) * 32, ra);
+              mx_chunk(rb, c + 1);
+              if (c + 2 < nch) tmem_ld_wait();
+            }
+          }
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        if (quarter == 0) FWD4_STAMP(16 * g, 1);
+
+        // ---- pass 2: P = exp2(S * c2 - mx * c2) -> packed bf16, written back over S behind the read pointer ----
+        const float mc = mx * c2;
+        float s0 = 0.f, s1 = 0.f;
+        auto p_chunk = [&](const uint32_t (&v)[32], int c) {
+          uint32_t pk[16];
+          if (c * 32 + 32 <= N) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c2, -mc));
+              const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c2, -mc));
+              s0 += e0;
+              s1 += e1;
+              pk[i] = pack_bf16x2(e0, e1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c2, -mc));
+              float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c2, -mc));
+              e0 = (c * 32 + 2 * i < N) ? e0 : 0.f;
+              e1 = (c * 32 + 2 * i + 1 < N) ? e1 : 0.f;
+              s0 += e0;
+              s1 += e1;
+              pk[i] = pack_bf16x2(e0, e1);
+            }
+          }
+          tmem_st_32x16(slot + c * 16, pk);
+        };
+        tmem_ld_32x32(slot, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+          if (c < nch) {
+            if (c + 1 < nch) tmem_ld_32x32(slot + (c + 1) * 32, rb);
+            p_chunk(ra, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32(slot + (c + 2) * 32, ra);
+              p_chunk(rb, c + 1);
+              if (c + 2 < nch) tmem_ld_wait();
+            }
+          }
+        }
+        tmem_st_wait();
+        l = s0 + s1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (quarter == 0) FWD4_STAMP(16 * g, 3);
+
+      // ---- O = P V ----
+      mbar_wait(&o_full[g], n & 1);
+      tc_fence_after();
+      if (quarter == 0) FWD4_STAMP(16 * g, 5);
+      if (active) {
+        tmem_ld_32x32(slot + 192, ra);
+        tmem_ld_32x32(slot + 224, rb);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slot_free[g]);
+      if (quarter == 0) FWD4_STAMP(16 * g, 6);
+      // normalised bf16 row -> the (dead) Q_g tile of this item's stage, 128-byte swizzled -> TMA store by the MMA warp
+      const int st = n & 1;
+      uint8_t* stg = smem + st * L::STAGE + g * TILE_BYTES;
+      if (active) {
+        const int h = it % H, b = it / H;
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t(&o)[32] = u < 4 ? ra : rb;
+          const int e = (u & 3) * 8;
+          uint4 v4;
+          v4.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv, __uint_as_float(o[e + 1]) * inv);
+          v4.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
+          v4.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
+          v4.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
+          st_swz(stg, r, u, v4);
+        }
+        if (q < N && lse) lse[((long long)b * H + h) * N + q] = mx * scale + __logf(l);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_staged[g]);
+      if (quarter == 0) FWD4_STAMP(16 * g, 7);
+    }
+  }
+#undef FWD4_STAMP
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_fwd4(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
+  CUtensorMap tm_out;
+  int rc = vitk_make_tmap_3d(&tm_out, out, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD, HD,
+                             TILE, 1);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd3Smem::BYTES);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd4: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int items = B * H;
+  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
+  attn_fwd4_kernel<<<grid, FWD4_THREADS, Fwd3Smem::BYTES, s>>>(tm, tm_out, lse, B, N, H, scale, g_trace_buf);
+  return vitk_check_launch("attn_fwd4");
+}
+
 // D[b, h, n] = sum_d O[b, n, h, d] * dO[b, n, h, d]: one warp per token row, fully coalesced 16-byte loads.
 // (Computing it inside the backward kernel costs ~10k cycles of exposed, row-strided global loads per CTA.)
 __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -2423,13 +2719,14 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   if (rc) return rc;
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
-  // VITK_ATTN_FWD: unset = warp-specialised persistent kernel for 128 < N <= 256, tiled kernel otherwise;
-  // "1" = tiled one-CTA-per-q-tile kernel everywhere; "2" = older persistent kernel (kept for comparison)
+  // VITK_ATTN_FWD: unset = warp-specialised persistent kernel (one thread per row) for 128 < N <= 256, tiled kernel
+  // otherwise; "1" = tiled one-CTA-per-q-tile kernel everywhere; "2" / "3" = older persistent kernels (for comparison)
   static const int variant = [] {
     const char* e = getenv("VITK_ATTN_FWD");
     return e ? atoi(e) : 0;
   }();
-  if (variant == 0 && T == 2) return launch_fwd3(tm, out, lse, B, N, H, scale, s);
+  if (variant == 0 && T == 2) return launch_fwd4(tm, out, lse, B, N, H, scale, s);
+  if (variant == 3 && T == 2) return launch_fwd3(tm, out, lse, B, N, H, scale, s);
   if (variant == 2 && T == 1) return launch_fwd2<1>(tm, out, lse, B, N, H, scale, s);
   if (variant == 2 && T == 2) return launch_fwd2<2>(tm, out, lse, B, N, H, scale, s);
   switch (T) {
