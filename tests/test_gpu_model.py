@@ -255,6 +255,74 @@ def test_engine_train_one_epoch_and_evaluate(cuda_device):
     assert set(ev) == {"loss", "acc1", "acc5"} and math.isfinite(ev["loss"])
 
 
+def test_checkpoint_save_resume(cuda_device, tmp_path):
+    """Reference format (/root/reference/utils/__init__.py:686-770): {'model','optimizer','epoch','scaler','args',
+    'model_ema'}; resuming restores weights, Adam moments, step count and the fused EMA (the split-K wgrad
+    reductions are fp32 atomics, so two runs agree to rounding, not bitwise; a lost moment or step count shows up at 1e-3)."""
+    import argparse
+
+    from vision_transformers_torch_xla_b200 import optim_factory, utils
+    from vision_transformers_torch_xla_b200.losses import SoftTargetCrossEntropy
+    from vision_transformers_torch_xla_b200.models import create_model
+    from oracle import vit_oracle as O
+
+    class OptArgs:
+        opt, lr, weight_decay, opt_eps, opt_betas = "adamw", 1e-3, 0.05, 1e-8, None
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 3, 224, 224, generator=g).to(cuda_device)
+    y = O.mixup_soft_targets(torch.randint(0, 1000, (4,), generator=g)).to(cuda_device)
+    crit = SoftTargetCrossEntropy()
+
+    def make():
+        torch.manual_seed(0)
+        m = create_model("vit_tiny_patch16_224", num_classes=1000, global_pool="avg").to(cuda_device)
+        o = optim_factory.create_optimizer(OptArgs, m)
+        return m, o
+
+    def steps(m, o, n):
+        for _ in range(n):
+            crit(m(x), y).backward()
+            o.step()
+            o.zero_grad()
+
+    a, oa = make()
+    crit(a(x), y).backward()   # the flat store (and with it the optimizer plan) exists after the first forward
+    oa.zero_grad()
+    oa.enable_ema(0.9)
+    steps(a, oa, 2)
+    args = argparse.Namespace(output_dir=str(tmp_path), save_ckpt_num=3, save_ckpt_freq=1, auto_resume=True, resume="",
+                              start_epoch=0)
+    path = utils.save_model(args, 0, a, a, oa, None, model_ema=True)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "epoch", "scaler", "args", "model_ema"} and ck["epoch"] == 0
+    assert set(ck["model"]) == set(a.state_dict()) == set(ck["model_ema"])
+    assert set(ck["optimizer"]) == {"state", "param_groups"}
+    steps(a, oa, 2)
+
+    b, ob = make()
+    crit(b(x), y).backward()
+    ob.zero_grad()
+    ob.enable_ema(0.9)
+    utils.auto_load_model(args, b, b, ob, None, model_ema=True)
+    assert args.start_epoch == 1
+    # the restored state is exactly the saved one: weights, both Adam moments, step count, EMA
+    for n2, p2 in b.named_parameters():
+        assert torch.equal(p2.detach().cpu(), ck["model"][n2]), n2
+    saved = ck["optimizer"]["state"]
+    for i, p2 in enumerate(pp for gp in ob.param_groups for pp in gp["params"]):
+        assert torch.equal(ob.state[p2]["exp_avg"].cpu(), saved[i]["exp_avg"]) and \
+            torch.equal(ob.state[p2]["exp_avg_sq"].cpu(), saved[i]["exp_avg_sq"]), i
+    assert ob._step == 2
+    assert torch.equal(utils.ema_state_dict(b, ob)["blocks.3.mlp.fc1.weight"], ck["model_ema"]["blocks.3.mlp.fc1.weight"])
+    # and training continues from there (elements with ~zero gradient move by up to lr under the atomics' rounding noise)
+    steps(b, ob, 2)
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        # (the key bias has an exactly-zero true gradient: Adam turns its rounding noise into +-lr steps)
+        assert (p1 - p2).abs().max().item() < 2.5e-3 and (p1 - p2).abs().mean().item() < 2e-4, n1
+    assert int(float(next(iter(ob.state.values()))["step"])) == 4
+
+
 def test_standalone_modules(cuda_device):
     """Attention / Mlp / LayerNorm / PatchEmbed / Block are usable on their own (reference plug points)."""
     from oracle import vit_oracle as O

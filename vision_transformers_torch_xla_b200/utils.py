@@ -9,6 +9,8 @@ import time
 from collections import defaultdict, deque
 
 import numpy as np
+from typing import Optional
+
 import torch
 import torch.distributed as dist
 
@@ -184,6 +186,113 @@ class DevicePrefetcher:
             batch = nxt
             nxt = self._fetch(it)                 # batch i+1 starts copying now, overlapping the step on batch i
             yield batch
+
+
+# ------------------------------------------------------------------------------------------------
+# checkpoint save / resume with the reference's on-disk format (/root/reference/utils/__init__.py:686-770):
+# {'model', 'optimizer', 'epoch', 'scaler', 'args'[, 'model_ema']} in <output_dir>/checkpoint-<epoch>.pth
+# ------------------------------------------------------------------------------------------------
+def save_on_master(*args, **kwargs):
+    if is_main_process():
+        torch.save(*args, **kwargs)
+
+
+def ema_state_dict(model: torch.nn.Module, optimizer) -> Optional[dict]:
+    """EMA weights kept by ``FusedAdamW.enable_ema`` (one flat fp32 buffer updated inside the AdamW launch) as a
+    state_dict with the model's own keys, i.e. what ``timm.utils.get_state_dict(model_ema)`` returns in the reference."""
+    ema = getattr(optimizer, "ema", None)
+    if ema is None or getattr(optimizer, "_plan", None) is None:
+        return None
+    st = optimizer._plan[0]["store"]
+    out = {}
+    for name, p in model.named_parameters():
+        if id(p) in st.offsets:
+            o, n = st.offsets[id(p)]
+            out[name] = ema[o:o + n].view(p.shape).detach().cpu().clone()
+    for name, b in model.named_buffers():
+        out[name] = b.detach().cpu().clone()
+    return out
+
+
+def load_ema_state_dict(model: torch.nn.Module, optimizer, state: dict) -> None:
+    ema = getattr(optimizer, "ema", None)
+    if ema is None:
+        raise RuntimeError("call optimizer.enable_ema(decay) before loading EMA weights")
+    st = optimizer._plan[0]["store"]
+    for name, p in model.named_parameters():
+        if name in state and id(p) in st.offsets:
+            o, n = st.offsets[id(p)]
+            ema[o:o + n].copy_(state[name].reshape(-1).to(ema.device, ema.dtype))
+
+
+def save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler, model_ema=None):
+    """Same call and same file as the reference.  ``model_ema`` may be a timm-style object with ``.ema`` / ``.module``,
+    or ``True`` / the optimizer itself to save the fused EMA buffer."""
+    from pathlib import Path
+    output_dir = Path(args.output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    checkpoint_path = output_dir / ("checkpoint-%s.pth" % str(epoch))
+    to_save = {
+        "model": {k: v.detach().cpu().clone() for k, v in model_without_ddp.state_dict().items()},
+        "optimizer": optimizer.state_dict(),
+        "epoch": epoch,
+        "scaler": loss_scaler.state_dict() if loss_scaler is not None else None,
+        "args": args,
+    }
+    if model_ema is not None and model_ema is not False:
+        inner = getattr(model_ema, "ema", None)
+        if isinstance(inner, torch.nn.Module):
+            to_save["model_ema"] = {k: v.detach().cpu().clone() for k, v in inner.state_dict().items()}
+        elif isinstance(getattr(model_ema, "module", None), torch.nn.Module):
+            to_save["model_ema"] = {k: v.detach().cpu().clone() for k, v in model_ema.module.state_dict().items()}
+        else:
+            sd = ema_state_dict(model_without_ddp, optimizer)
+            if sd is not None:
+                to_save["model_ema"] = sd
+    save_on_master(to_save, checkpoint_path)
+    if is_main_process() and isinstance(epoch, int) and hasattr(args, "save_ckpt_num") and hasattr(args, "save_ckpt_freq"):
+        to_del = epoch - args.save_ckpt_num * args.save_ckpt_freq
+        old_ckpt = output_dir / ("checkpoint-%s.pth" % to_del)
+        if os.path.exists(old_ckpt):
+            os.remove(old_ckpt)
+    return checkpoint_path
+
+
+def auto_load_model(args, model, model_without_ddp, optimizer, loss_scaler, model_ema=None):
+    """Resume from ``args.resume`` or (``args.auto_resume``) the newest ``checkpoint-<int>.pth`` in ``args.output_dir``;
+    sets ``args.start_epoch`` like the reference."""
+    import glob
+    output_dir = str(args.output_dir)
+    if getattr(args, "auto_resume", False) and len(getattr(args, "resume", "") or "") == 0:
+        latest = -1
+        for ckpt in glob.glob(os.path.join(output_dir, "checkpoint-*.pth")):
+            t = ckpt.split("-")[-1].split(".")[0]
+            if t.isdigit():
+                latest = max(int(t), latest)
+        if latest >= 0:
+            args.resume = os.path.join(output_dir, "checkpoint-%d.pth" % latest)
+    if not getattr(args, "resume", ""):
+        return None
+    if str(args.resume).startswith("https"):
+        raise NotImplementedError("remote checkpoints are not fetched (no network dependency on the training path)")
+    checkpoint = torch.load(args.resume, map_location="cpu", weights_only=False)
+    model_without_ddp.load_state_dict(checkpoint["model"])
+    if "optimizer" in checkpoint and "epoch" in checkpoint:
+        optimizer.load_state_dict(checkpoint["optimizer"])
+        if not isinstance(checkpoint["epoch"], str):
+            args.start_epoch = checkpoint["epoch"] + 1
+        else:
+            assert getattr(args, "eval", False), "Does not support resuming with checkpoint-best"
+        if model_ema is not None and model_ema is not False:
+            ema_sd = checkpoint.get("model_ema", checkpoint["model"])
+            inner = getattr(model_ema, "ema", None)
+            if isinstance(inner, torch.nn.Module):
+                inner.load_state_dict(ema_sd)
+            elif getattr(optimizer, "ema", None) is not None:
+                load_ema_state_dict(model_without_ddp, optimizer, ema_sd)
+        if "scaler" in checkpoint and loss_scaler is not None and checkpoint["scaler"] is not None:
+            loss_scaler.load_state_dict(checkpoint["scaler"])
+    return checkpoint
 
 
 def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1,)):
