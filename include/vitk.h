@@ -183,6 +183,16 @@ void vitk_debug_set_trace(long long* device_buf);
 /* out[0] += sum_i x[i]^2 (for clip_grad_norm_) */
 int vitk_sumsq(const float* x, int64_t n, float* out, void* stream);
 
+/* Mixup / CutMix, batch mode, in place on fp32 NCHW images (image b mixes with image B-1-b); replaces
+ * timm.data.Mixup._mix_batch as constructed at /root/reference/main.py:622-629 and applied at engine.py:259-262.
+ * lam and the CutMix box are drawn on the host exactly as timm does (no device sync); lam is a double so that
+ * (float)lam and (float)(1 - lam) round exactly like the reference's Python scalars. */
+int vitk_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, double lam, int32_t use_cutmix,
+                     int32_t yl, int32_t yh, int32_t xl, int32_t xh, void* stream);
+/* out[b, c] = onehot_smooth(labels[b])[c] * lam + onehot_smooth(labels[B-1-b])[c] * (1 - lam)   (timm mixup_target) */
+int vitk_mixup_target(const int64_t* labels, float* out, int32_t B, int32_t C, double lam, double smoothing,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

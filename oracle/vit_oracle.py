@@ -500,3 +500,58 @@ def mixup_soft_targets(labels: torch.Tensor, num_classes: int = 1000, lam: float
         return torch.full((y.shape[0], num_classes), off).scatter_(1, y.view(-1, 1), on)
 
     return lam * one_hot(labels) + (1.0 - lam) * one_hot(labels.flip(0))
+
+
+class Mixup:
+    """Restatement of ``timm.data.Mixup`` 1.0.15, batch mode, as the reference constructs and calls it
+    (/root/reference/main.py:622-629; engine.py:259-262).  Pure torch on whatever device ``x`` lives on; draws
+    ``np.random`` numbers in timm's order: rand() for prob, [rand() for the cutmix switch,] beta() for lam,
+    [randint() twice for the box centre]."""
+
+    def __init__(self, mixup_alpha=1.0, cutmix_alpha=0.0, cutmix_minmax=None, prob=1.0, switch_prob=0.5, mode="batch",
+                 correct_lam=True, label_smoothing=0.1, num_classes=1000):
+        assert cutmix_minmax is None and mode == "batch"
+        self.mixup_alpha, self.cutmix_alpha, self.mix_prob, self.switch_prob = mixup_alpha, cutmix_alpha, prob, switch_prob
+        self.label_smoothing, self.num_classes, self.correct_lam = label_smoothing, num_classes, correct_lam
+
+    def _params_per_batch(self):
+        import numpy as np
+        lam, use_cutmix = 1.0, False
+        if np.random.rand() < self.mix_prob:
+            if self.mixup_alpha > 0.0 and self.cutmix_alpha > 0.0:
+                use_cutmix = np.random.rand() < self.switch_prob
+                lam_mix = np.random.beta(self.cutmix_alpha, self.cutmix_alpha) if use_cutmix else \
+                    np.random.beta(self.mixup_alpha, self.mixup_alpha)
+            elif self.mixup_alpha > 0.0:
+                lam_mix = np.random.beta(self.mixup_alpha, self.mixup_alpha)
+            else:
+                use_cutmix = True
+                lam_mix = np.random.beta(self.cutmix_alpha, self.cutmix_alpha)
+            lam = float(lam_mix)
+        return lam, use_cutmix
+
+    def __call__(self, x, target):
+        import numpy as np
+        assert len(x) % 2 == 0
+        lam, use_cutmix = self._params_per_batch()
+        if lam != 1.0:
+            if use_cutmix:
+                img_h, img_w = x.shape[-2:]
+                ratio = np.sqrt(1 - lam)
+                cut_h, cut_w = int(img_h * ratio), int(img_w * ratio)
+                cy = np.random.randint(0, img_h)
+                cx = np.random.randint(0, img_w)
+                yl, yh = np.clip(cy - cut_h // 2, 0, img_h), np.clip(cy + cut_h // 2, 0, img_h)
+                xl, xh = np.clip(cx - cut_w // 2, 0, img_w), np.clip(cx + cut_w // 2, 0, img_w)
+                if self.correct_lam:
+                    lam = 1.0 - (yh - yl) * (xh - xl) / float(img_h * img_w)
+                x[:, :, yl:yh, xl:xh] = x.flip(0)[:, :, yl:yh, xl:xh]
+            else:
+                x_flipped = x.flip(0).mul_(1.0 - lam)
+                x.mul_(lam).add_(x_flipped)
+        off = self.label_smoothing / self.num_classes
+        on = 1.0 - self.label_smoothing + off
+        t = target.long().view(-1, 1)
+        y1 = torch.full((t.shape[0], self.num_classes), off, device=x.device).scatter_(1, t.to(x.device), on)
+        y2 = torch.full((t.shape[0], self.num_classes), off, device=x.device).scatter_(1, t.flip(0).to(x.device), on)
+        return x, y1 * lam + y2 * (1.0 - lam)

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import c_double, POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void_p
 from typing import Optional
 
 import torch
@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_attn_bwd_workspace_bytes", "vitk_patchify", "vitk_prefix_rows",
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
-    "vitk_debug_set_trace",
+    "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target",
 )
 
 
@@ -92,6 +92,9 @@ def load() -> ctypes.CDLL:
                                     c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_float, c_float, c_float,
                                     c_int64, c_float, c_float, c_int32, c_void_p]
     lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.vitk_mixup_batch.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_double, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_void_p]
+    lib.vitk_mixup_target.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_void_p]
     lib.vitk_debug_set_trace.argtypes = [c_void_p]
     lib.vitk_debug_set_trace.restype = None
     for name in EXPORTED_SYMBOLS:
@@ -416,4 +419,28 @@ def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
     _req(x, torch.float32, "sumsq x")
     with _Timed("sumsq"):
         _check(load().vitk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# Mixup / CutMix
+# ------------------------------------------------------------------------------------------------
+def mixup_batch(x: torch.Tensor, lam: float, use_cutmix: bool = False, box=(0, 0, 0, 0)) -> None:
+    """In place on fp32 NCHW ``x``: image b mixed with image B-1-b (mixup) or the box copied over (cutmix)."""
+    _req(x, torch.float32, "mixup x")
+    B, C, H, W = x.shape
+    yl, yh, xl, xh = (int(v) for v in box)
+    with _Timed("mixup_batch"):
+        _check(load().vitk_mixup_batch(x.data_ptr(), B, C, H, W, float(lam), int(use_cutmix), yl, yh, xl, xh, _stream()),
+               "vitk_mixup_batch")
+    _count()
+
+
+def mixup_target(labels: torch.Tensor, out: torch.Tensor, lam: float, smoothing: float) -> None:
+    _req(labels, torch.int64, "mixup labels")
+    _req(out, torch.float32, "mixup targets")
+    B, C = out.shape
+    with _Timed("mixup_target"):
+        _check(load().vitk_mixup_target(labels.data_ptr(), out.data_ptr(), B, C, float(lam), float(smoothing), _stream()),
+               "vitk_mixup_target")
     _count()

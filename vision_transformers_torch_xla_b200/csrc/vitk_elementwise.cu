@@ -415,6 +415,55 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
 
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
 
+
+// ---------------------------------------------------------------------------------------------
+// Mixup / CutMix on the device, in place, batch mode of timm.data.Mixup (constructed at
+// /root/reference/main.py:622-629, applied at engine.py:259-262): image b is mixed with image B-1-b.
+//   mixup : x_b <- x_b * lam + x_{B-1-b} * (1 - lam)          (two roundings, like x.mul_(lam).add_(x.flip(0).mul_(1-lam)))
+//   cutmix: x_b[:, yl:yh, xl:xh] <- x_{B-1-b}[:, yl:yh, xl:xh]
+// One thread handles the same float4 of both images of a pair, so the update is safe in place.
+// ---------------------------------------------------------------------------------------------
+__global__ void mixup_batch_kernel(float* __restrict__ x, long long pairs, long long per_img4, int Himg, int W4, float lam,
+                                   float om, int use_cutmix, int yl, int yh, int xl, int xh) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pairs * per_img4) return;
+  const long long pr = idx / per_img4, off = idx - pr * per_img4;
+  float4* a = reinterpret_cast<float4*>(x) + pr * per_img4 + off;
+  float4* b = reinterpret_cast<float4*>(x) + (2 * pairs - 1 - pr) * per_img4 + off;
+  float4 va = *a, vb = *b;
+  if (!use_cutmix) {
+    float4 ra, rb;
+    ra.x = __fadd_rn(__fmul_rn(va.x, lam), __fmul_rn(vb.x, om)); rb.x = __fadd_rn(__fmul_rn(vb.x, lam), __fmul_rn(va.x, om));
+    ra.y = __fadd_rn(__fmul_rn(va.y, lam), __fmul_rn(vb.y, om)); rb.y = __fadd_rn(__fmul_rn(vb.y, lam), __fmul_rn(va.y, om));
+    ra.z = __fadd_rn(__fmul_rn(va.z, lam), __fmul_rn(vb.z, om)); rb.z = __fadd_rn(__fmul_rn(vb.z, lam), __fmul_rn(va.z, om));
+    ra.w = __fadd_rn(__fmul_rn(va.w, lam), __fmul_rn(vb.w, om)); rb.w = __fadd_rn(__fmul_rn(vb.w, lam), __fmul_rn(va.w, om));
+    *a = ra;
+    *b = rb;
+  } else {
+    const long long row = off / W4;                 // (channel * H + y)
+    const int y = (int)(row % Himg), x0 = (int)(off - row * W4) * 4;
+    if (y < yl || y >= yh || x0 + 4 <= xl || x0 >= xh) return;
+    float4 ra = va, rb = vb;
+    if (x0 + 0 >= xl && x0 + 0 < xh) { ra.x = vb.x; rb.x = va.x; }
+    if (x0 + 1 >= xl && x0 + 1 < xh) { ra.y = vb.y; rb.y = va.y; }
+    if (x0 + 2 >= xl && x0 + 2 < xh) { ra.z = vb.z; rb.z = va.z; }
+    if (x0 + 3 >= xl && x0 + 3 < xh) { ra.w = vb.w; rb.w = va.w; }
+    *a = ra;
+    *b = rb;
+  }
+}
+
+// soft targets: out[b, c] = v(y_b == c) * lam + v(y_{B-1-b} == c) * (1 - lam), v = on / off value with label smoothing
+__global__ void mixup_target_kernel(const long long* __restrict__ labels, float* __restrict__ out, int B, int C, float lam,
+                                    float om, float on_value, float off_value) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * C) return;
+  const int b = (int)(idx / C), c = (int)(idx - (long long)b * C);
+  const float y1 = labels[b] == c ? on_value : off_value;
+  const float y2 = labels[B - 1 - b] == c ? on_value : off_value;
+  out[idx] = __fadd_rn(__fmul_rn(y1, lam), __fmul_rn(y2, om));
+}
+
 }  // namespace
 
 extern "C" int vitk_patchify(const float* img, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W,
@@ -554,4 +603,29 @@ extern "C" int vitk_sumsq(const float* x, int64_t n, float* out, void* stream) {
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
   return vitk_check_launch("sumsq");
+}
+
+extern "C" int vitk_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, double lam, int32_t use_cutmix,
+                                int32_t yl, int32_t yh, int32_t xl, int32_t xh, void* stream) {
+  VITK_REQUIRE(x && B > 0 && C > 0 && H > 0 && W > 0, VITK_ERR_SHAPE, "mixup_batch: bad shape");
+  VITK_REQUIRE(B % 2 == 0, VITK_ERR_SHAPE, "mixup_batch: batch size %d must be even", B);
+  VITK_REQUIRE(W % 4 == 0 && ((uintptr_t)x & 15) == 0, VITK_ERR_ALIGN, "mixup_batch: W %% 4 == 0 and 16-byte alignment required");
+  const long long per_img4 = (long long)C * H * W / 4, pairs = B / 2;
+  const long long n = pairs * per_img4;
+  mixup_batch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, pairs, per_img4, H, W / 4, (float)lam, (float)(1.0 - lam), use_cutmix, yl,
+                                                                                      yh, xl, xh);
+  return vitk_check_launch("mixup_batch");
+}
+
+extern "C" int vitk_mixup_target(const int64_t* labels, float* out, int32_t B, int32_t C, double lam, double smoothing,
+                                 void* stream) {
+  VITK_REQUIRE(labels && out && B > 0 && C > 0, VITK_ERR_SHAPE, "mixup_target: bad shape");
+  // lam, 1 - lam and the on / off values are formed in double and rounded once, like the Python scalars of the reference
+  const double off_d = smoothing / (double)C;
+  const float off_value = (float)off_d;
+  const float on_value = (float)(1.0 - smoothing + off_d);
+  const long long n = (long long)B * C;
+  mixup_target_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, B, C, (float)lam, (float)(1.0 - lam), on_value,
+                                                                                       off_value);
+  return vitk_check_launch("mixup_target");
 }
