@@ -125,15 +125,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     const uint32_t n_eff = roundup16(kvn);
     const uint32_t sK_u = smem_u32(smem + L::KV_OFF + j * 2 * TILE_BYTES);
     const uint32_t sV_u = sK_u + TILE_BYTES;
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // uniform control flow + one elected lane: the descriptors stay in uniform registers
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(&bar_kv[j], 0);
       tc_fence_after();
       const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+      const uint64_t qd = umma_desc_kmajor(sQ_u), kd = umma_desc_kmajor(sK_u);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_bf16_ss(tmem_s, umma_desc_kmajor(sQ_u + k * 32), umma_desc_kmajor(sK_u + k * 32), idesc, k > 0);
-      umma_commit(bar_s);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0);
+        umma_commit(bar_s);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
@@ -196,15 +199,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     tc_fence_before();
     __syncthreads();
     VITK_STAMP(4 + j * 4);
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
       const int ksteps = (int)n_eff / 16;
       const uint64_t pdesc = umma_desc_kmajor(sP_u), vdesc = umma_desc_mnmajor(sV_u, TILE_BYTES);
+      if (elect_one()) {
 #pragma unroll 4
-      for (int k = 0; k < ksteps; ++k)
-        umma_bf16_ss(tmem_o, pdesc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), vdesc + (uint64_t)(k * 128), idesc, k > 0);
-      umma_commit(bar_o);
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ss(tmem_o, pdesc + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), vdesc + (uint64_t)(k * 128), idesc, k > 0);
+        umma_commit(bar_o);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
@@ -2561,18 +2567,20 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
       my_d = acc;
     }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {   // uniform control flow + one elected lane
       if (i == 0) mbar_wait(bar_kv, 0);
       mbar_wait(bar_q, i & 1);
       tc_fence_after();
       const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+      const uint64_t qd = umma_desc_kmajor(sQ), kd = umma_desc_kmajor(sK), dod = umma_desc_kmajor(sDO), vd = umma_desc_kmajor(sV);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_bf16_ss(tm_s, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc, k > 0);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0);
 #pragma unroll
-      for (int k = 0; k < HD / 16; ++k)
-        umma_bf16_ss(tm_dp, umma_desc_kmajor(sDO + k * 32), umma_desc_kmajor(sV + k * 32), idesc, k > 0);
-      umma_commit(bar_sp);
+        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_dp, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc, k > 0);
+        umma_commit(bar_sp);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_sp, i & 1);
     tc_fence_after();
@@ -2611,21 +2619,22 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
       tc_fence_after();
       const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);
-      const int qsteps = (int)q_eff / 16;
-      for (int k = 0; k < qsteps; ++k)
-        umma_bf16_ss(tm_dv, umma_desc_mnmajor(sP_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sDO + k * 2048, TILE_BYTES),
-                     idesc_t, (i > 0 || k > 0));
-      for (int k = 0; k < qsteps; ++k)
-        umma_bf16_ss(tm_dk, umma_desc_mnmajor(sDS_u + k * 2048, TILE_BYTES), umma_desc_mnmajor(sQ + k * 2048, TILE_BYTES),
-                     idesc_t, (i > 0 || k > 0));
       const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);
-      for (int k = 0; k < (int)n_eff / 16; ++k)
-        umma_bf16_ss(tm_dq, umma_desc_kmajor(sDS_u + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                     umma_desc_mnmajor(sK + k * 2048, TILE_BYTES), idesc_q, k > 0);
-      umma_commit(bar_mma);
+      const int qsteps = (int)q_eff / 16;
+      const uint64_t p_mn = umma_desc_mnmajor(sP_u, TILE_BYTES), do_mn = umma_desc_mnmajor(sDO, TILE_BYTES);
+      const uint64_t ds_mn = umma_desc_mnmajor(sDS_u, TILE_BYTES), q_mn = umma_desc_mnmajor(sQ, TILE_BYTES);
+      const uint64_t ds_k = umma_desc_kmajor(sDS_u), k_mn = umma_desc_mnmajor(sK, TILE_BYTES);
+      if (elect_one()) {
+        for (int k = 0; k < qsteps; ++k) umma_bf16_ss(tm_dv, p_mn + (uint64_t)(k * 128), do_mn + (uint64_t)(k * 128), idesc_t, (i > 0 || k > 0));
+        for (int k = 0; k < qsteps; ++k) umma_bf16_ss(tm_dk, ds_mn + (uint64_t)(k * 128), q_mn + (uint64_t)(k * 128), idesc_t, (i > 0 || k > 0));
+        for (int k = 0; k < (int)n_eff / 16; ++k)
+          umma_bf16_ss(tm_dq, ds_k + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), k_mn + (uint64_t)(k * 128), idesc_q, k > 0);
+        umma_commit(bar_mma);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_mma, i & 1);
     tc_fence_after();
