@@ -27,7 +27,8 @@ def _ref(qkv, B, N, H, hd, dout=None):
 
 # (32, 197, 12) = 384 (b, h) items: more than one item per CTA of the persistent kernels (148 SMs)
 @pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 577, 4), (1, 300, 2),
-                                   (1, 129, 1), (2, 144, 2), (1, 255, 3), (32, 197, 12), (13, 198, 12)])
+                                   (1, 129, 1), (2, 144, 2), (1, 255, 3), (32, 197, 12), (13, 198, 12), (8, 577, 16), (5, 640, 7),
+                                   (9, 385, 5), (3, 257, 4)])
 def test_attn_fwd(cuda_device, B, N, H):
     from vision_transformers_torch_xla_b200 import _lib as L
     hd = 64
