@@ -1521,32 +1521,48 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       }
       mbar_wait(&q_full[g], rounds & 1);
       if (g == 1 && rounds == 0) mbar_wait(&p_full[0], 0);   // start half a step behind group 0: exps overlap the other group's MMA hop
+      // Everything the issue path needs is formed before the waits: the group idles from "P written" until the next
+      // S is ready, and this warp shares its scheduler with busy softmax warps (~10 cycles per dependent instruction).
       const uint64_t qdesc = umma_desc_kmajor(sQ);
-      for (int j = 0; j < QT; ++j, ++kvc) {
+      const uint64_t kdesc0 = umma_desc_kmajor(smem_u32(smem + L::KV_OFF));
+      const uint64_t vdesc0 = umma_desc_mnmajor(smem_u32(smem + L::KV_OFF + TILE_BYTES), TILE_BYTES);
+      constexpr uint64_t STAGE_STEP = (2 * TILE_BYTES) >> 4;
+      const uint32_t n_last = roundup16(N - (QT - 1) * TILE);
+      const uint32_t idesc_full = umma_idesc(TILE, TILE, 1, false, false), idesc_last = umma_idesc(TILE, n_last, 1, false, false);
+      {   // S_0
         const int st = kvc % L::STAGES;
-        const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
-        const uint32_t sK = smem_u32(smem + L::KV_OFF + st * 2 * TILE_BYTES), sV = sK + TILE_BYTES;
-        const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
-        const uint64_t kdesc = umma_desc_kmajor(sK), vdesc = umma_desc_mnmajor(sV, TILE_BYTES);
         mbar_wait(&kv_full[st], (kvc / L::STAGES) & 1);
         tc_fence_after();
-        if (elect_one()) {   // S_j (the previous P V, which read P out of the same columns, was issued before it)
+        const uint64_t kd = kdesc0 + (uint64_t)st * STAGE_STEP;
+        const uint32_t ids = (QT == 1) ? idesc_last : idesc_full;
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0);
+          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), ids, k > 0);
           umma_commit(&s_full[g]);
         }
         __syncwarp();
-        FWD5_STAMP(32 + 16 * g);
+      }
+      for (int j = 0; j < QT; ++j, ++kvc) {
+        const int st = kvc % L::STAGES, stn = (kvc + 1) % L::STAGES;
+        const bool last = j == QT - 1;
+        const int ksteps = (int)(last ? n_last : (uint32_t)TILE) / 16;
+        const uint64_t vd = vdesc0 + (uint64_t)st * STAGE_STEP, kdn = kdesc0 + (uint64_t)stn * STAGE_STEP;
+        const uint32_t idn = (j + 1 == QT - 1) ? idesc_last : idesc_full;
+        if (!last) mbar_wait(&kv_full[stn], ((kvc + 1) / L::STAGES) & 1);   // K_{j+1} is there before P_j arrives
         mbar_wait(&p_full[g], steps & 1);
-        FWD5_STAMP(32 + 16 * g);
         ++steps;
         if (j == 0 && rounds > 0) mbar_wait(&o_free[g], (rounds - 1) & 1);   // the previous q tile's O has been read out
         tc_fence_after();
         if (elect_one()) {
-          for (int ks = 0; ks < (int)n_eff / 16; ++ks)
-            umma_bf16_ts(slot + 128, slot + 8 * ks, vdesc + (uint64_t)(ks * 128), idesc_o, (j > 0 || ks > 0));
+          for (int ks = 0; ks < ksteps; ++ks) umma_bf16_ts(slot + 128, slot + 8 * ks, vd + (uint64_t)(ks * 128), idesc_o, (j > 0 || ks > 0));
           umma_commit(&kv_empty[st]);
-          if (j == QT - 1) umma_commit(&o_full[g]);
+          if (last) {
+            umma_commit(&o_full[g]);
+          } else {   // S_{j+1} right behind (it overwrites P_j, which the P V just issued reads first: same issue order)
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kdn + (uint64_t)(k * 2), idn, k > 0);
+            umma_commit(&s_full[g]);
+          }
         }
         __syncwarp();
       }
