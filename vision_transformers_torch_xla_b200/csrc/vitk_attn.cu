@@ -2843,23 +2843,27 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 // ================================================================================================
 struct BwdStreamSmem {
   static constexpr uint32_t KV_OFF = 0;
-  static constexpr uint32_t QDO_OFF = 2 * TILE_BYTES;
-  static constexpr uint32_t P_OFF = 4 * TILE_BYTES;
-  static constexpr uint32_t DS_OFF = 6 * TILE_BYTES;
-  static constexpr uint32_t BAR_OFF = 8 * TILE_BYTES;
+  static constexpr uint32_t QDO_OFF = 2 * TILE_BYTES;   // [2 buffers][Q_i, dO_i]
+  static constexpr uint32_t P_OFF = 6 * TILE_BYTES;
+  static constexpr uint32_t DS_OFF = 8 * TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = 10 * TILE_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 128;
 };
 
+// Q_i / dO_i are double-buffered (tile i+1 is loading while tile i is processed), S / dP of tile i+1 are issued right
+// behind the dV / dK / dQ MMAs of tile i (their TMEM buffers are free once the threads have read them), so they execute
+// while the threads read dQ_ij out and red.add it.  D = rowsum(O * dO) comes from the workspace (attn_dsum_kernel).
+// No masks: kv rows >= N are TMA zero fill (they reach only discarded dK / dV rows and add 0 to dQ); q rows >= N have
+// Q = dO = 0 and use lse = D = 0.
 __global__ void __launch_bounds__(128)
 attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                       const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                       const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq32,
-                       int N, int H, float scale) {
+                       const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                       float* __restrict__ dq32, int N, int H, float scale) {
   using L = BwdStreamSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* bar_q = bar_kv + 1;
-  uint64_t* bar_sp = bar_q + 1;
+  uint64_t* bar_q = bar_kv + 1;     // [2]
+  uint64_t* bar_sp = bar_q + 2;
   uint64_t* bar_mma = bar_sp + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
@@ -2873,7 +2877,8 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (threadIdx.x == 32) {
     mbar_init(bar_kv, 1);
-    mbar_init(bar_q, 1);
+    mbar_init(&bar_q[0], 1);
+    mbar_init(&bar_q[1], 1);
     mbar_init(bar_sp, 1);
     mbar_init(bar_mma, 1);
     fence_mbar_init();
@@ -2894,8 +2899,32 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   uint8_t* sP = smem + L::P_OFF;
   uint8_t* sDS = smem + L::DS_OFF;
   const uint32_t sK = smem_u32(smem + L::KV_OFF), sV = sK + TILE_BYTES;
-  const uint32_t sQ = smem_u32(smem + L::QDO_OFF), sDO = sQ + TILE_BYTES;
+  const uint32_t sQDO = smem_u32(smem + L::QDO_OFF);
   const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
+  const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
+  const uint64_t kd = umma_desc_kmajor(sK), vd = umma_desc_kmajor(sV), k_mn = umma_desc_mnmajor(sK, TILE_BYTES);
+
+  auto load_q = [&](int i) {   // thread 0 only
+    const int buf = i & 1;
+    mbar_arrive_expect_tx(&bar_q[buf], 2 * TILE_BYTES);
+    tma_load_3d(smem + L::QDO_OFF + buf * 2 * TILE_BYTES, &tm_qkv, &bar_q[buf], h * HD, i * TILE, b);
+    tma_load_3d(smem + L::QDO_OFF + buf * 2 * TILE_BYTES + TILE_BYTES, &tm_do, &bar_q[buf], h * HD, i * TILE, b);
+  };
+  // S = Q_i K_j^T and dP = dO_i V_j^T (warp 0, uniform control flow, one elected lane)
+  auto issue_s_dp = [&](int i) {
+    const uint32_t sQ = sQDO + (i & 1) * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
+    const uint64_t qd = umma_desc_kmajor(sQ), dod = umma_desc_kmajor(sDO);
+    mbar_wait(&bar_q[i & 1], (i >> 1) & 1);
+    tc_fence_after();
+    if (elect_one()) {
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_dp, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc, k > 0);
+      umma_commit(bar_sp);
+    }
+    __syncwarp();
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -2903,6 +2932,12 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     mbar_arrive_expect_tx(bar_kv, 2 * TILE_BYTES);
     tma_load_3d(smem + L::KV_OFF, &tm_qkv, bar_kv, (H + h) * HD, j * TILE, b);
     tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, (2 * H + h) * HD, j * TILE, b);
+    load_q(0);
+    if (nt > 1) load_q(1);
+  }
+  if (warp == 0) {
+    mbar_wait(bar_kv, 0);
+    issue_s_dp(0);
   }
 
   for (int i = 0; i < nt; ++i) {
@@ -2910,72 +2945,50 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const uint32_t q_eff = roundup16(qn);
     const bool row_ok = r < qn;
     const int q = i * TILE + r;
-    if (threadIdx.x == 0) {
-      // Q_i / dO_i buffer is free: the previous iteration ended with a CTA-wide sync after its MMAs retired
-      mbar_arrive_expect_tx(bar_q, 2 * TILE_BYTES);
-      tma_load_3d(smem + L::QDO_OFF, &tm_qkv, bar_q, h * HD, i * TILE, b);
-      tma_load_3d(smem + L::QDO_OFF + TILE_BYTES, &tm_do, bar_q, h * HD, i * TILE, b);
-    }
-    float my_lse2 = 0.f, my_d = 0.f;
+    float my_lse2 = 0.f, my_ds = 0.f;   // rows >= N: P = 2^S stays finite, dS = 0
     if (row_ok) {
       my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
-      const uint4* op = reinterpret_cast<const uint4*>(out + ((long long)b * N + q) * (H * HD) + h * HD);
-      const uint4* dp = reinterpret_cast<const uint4*>(dout + ((long long)b * N + q) * (H * HD) + h * HD);
-      float acc = 0.f;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 a = __ldg(op + g), d = __ldg(dp + g);
-        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
-        const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
-        acc += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
-      }
-      my_d = acc;
-    }
-    if (warp == 0) {   // uniform control flow + one elected lane
-      if (i == 0) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, i & 1);
-      tc_fence_after();
-      const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
-      const uint64_t qd = umma_desc_kmajor(sQ), kd = umma_desc_kmajor(sK), dod = umma_desc_kmajor(sDO), vd = umma_desc_kmajor(sV);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_dp, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc, k > 0);
-        umma_commit(bar_sp);
-      }
-      __syncwarp();
+      my_ds = dsum[((long long)b * H + h) * N + q] * scale;
     }
     mbar_wait(bar_sp, i & 1);
     tc_fence_after();
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t sv[32], dv[32];
-      tmem_ld_32x32(tm_s + lane_addr + c * 32, sv);
-      tmem_ld_32x32(tm_dp + lane_addr + c * 32, dv);
-      tmem_ld_wait();
-      if ((uint32_t)r < q_eff) {
-        float p[32], ds[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const bool ok = row_ok && (c * 32 + k < kvn);
-          const float e = ex2_approx(fmaf(__uint_as_float(sv[k]), c2, -my_lse2));
-          p[k] = ok ? e : 0.f;
-          ds[k] = ok ? e * (__uint_as_float(dv[k]) - my_d) * scale : 0.f;
-        }
+    if ((uint32_t)(warp * 32) < q_eff) {   // warp-uniform: some row of this warp is read by the dV / dK MMAs
+      uint32_t sa[32], da[32], sb[32], db[32];
+      auto chunk = [&](const uint32_t (&sv)[32], const uint32_t (&dv)[32], int c) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          if ((uint32_t)(c * 32 + g * 8) < n_eff) {
-            uint4 u, w;
-            u.x = pack_bf16x2(p[g * 8 + 0], p[g * 8 + 1]);
-            u.y = pack_bf16x2(p[g * 8 + 2], p[g * 8 + 3]);
-            u.z = pack_bf16x2(p[g * 8 + 4], p[g * 8 + 5]);
-            u.w = pack_bf16x2(p[g * 8 + 6], p[g * 8 + 7]);
-            w.x = pack_bf16x2(ds[g * 8 + 0], ds[g * 8 + 1]);
-            w.y = pack_bf16x2(ds[g * 8 + 2], ds[g * 8 + 3]);
-            w.z = pack_bf16x2(ds[g * 8 + 4], ds[g * 8 + 5]);
-            w.w = pack_bf16x2(ds[g * 8 + 6], ds[g * 8 + 7]);
-            st_swz(sP, r, c * 4 + g, u);
-            st_swz(sDS, r, c * 4 + g, w);
+          uint32_t pk[4], dk[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + 2 * k]), c2, -my_lse2));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + 2 * k + 1]), c2, -my_lse2));
+            pk[k] = pack_bf16x2(e0, e1);
+            dk[k] = pack_bf16x2(e0 * fmaf(__uint_as_float(dv[g * 8 + 2 * k]), scale, -my_ds),
+                                e1 * fmaf(__uint_as_float(dv[g * 8 + 2 * k + 1]), scale, -my_ds));
+          }
+          st_swz(sP, r, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          st_swz(sDS, r, c * 4 + g, make_uint4(dk[0], dk[1], dk[2], dk[3]));
+        }
+      };
+      tmem_ld_32x32(tm_s + lane_addr, sa);
+      tmem_ld_32x32(tm_dp + lane_addr, da);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        if (c < nchunks) {
+          if (c + 1 < nchunks) {
+            tmem_ld_32x32(tm_s + lane_addr + (c + 1) * 32, sb);
+            tmem_ld_32x32(tm_dp + lane_addr + (c + 1) * 32, db);
+          }
+          chunk(sa, da, c);
+          if (c + 1 < nchunks) {
+            tmem_ld_wait();
+            if (c + 2 < nchunks) {
+              tmem_ld_32x32(tm_s + lane_addr + (c + 2) * 32, sa);
+              tmem_ld_32x32(tm_dp + lane_addr + (c + 2) * 32, da);
+            }
+            chunk(sb, db, c + 1);
+            if (c + 2 < nchunks) tmem_ld_wait();
           }
         }
       }
@@ -2985,12 +2998,13 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
+      const uint32_t sQ = sQDO + (i & 1) * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
       const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);
       const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);
       const int qsteps = (int)q_eff / 16;
       const uint64_t p_mn = umma_desc_mnmajor(sP_u, TILE_BYTES), do_mn = umma_desc_mnmajor(sDO, TILE_BYTES);
       const uint64_t ds_mn = umma_desc_mnmajor(sDS_u, TILE_BYTES), q_mn = umma_desc_mnmajor(sQ, TILE_BYTES);
-      const uint64_t ds_k = umma_desc_kmajor(sDS_u), k_mn = umma_desc_mnmajor(sK, TILE_BYTES);
+      const uint64_t ds_k = umma_desc_kmajor(sDS_u);
       if (elect_one()) {
         for (int k = 0; k < qsteps; ++k) umma_bf16_ss(tm_dv, p_mn + (uint64_t)(k * 128), do_mn + (uint64_t)(k * 128), idesc_t, (i > 0 || k > 0));
         for (int k = 0; k < qsteps; ++k) umma_bf16_ss(tm_dk, ds_mn + (uint64_t)(k * 128), q_mn + (uint64_t)(k * 128), idesc_t, (i > 0 || k > 0));
@@ -2999,9 +3013,13 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         umma_commit(bar_mma);
       }
       __syncwarp();
+      // S / dP of the next q tile run while the threads read dQ_ij out (every thread has read S / dP of this tile)
+      if (i + 1 < nt) issue_s_dp(i + 1);
     }
     mbar_wait(bar_mma, i & 1);
     tc_fence_after();
+    // Q_i / dO_i are no longer read: their buffer takes tile i + 2
+    if (threadIdx.x == 0 && i + 2 < nt) load_q(i + 2);
     {
       uint32_t a0[32], a1[32];
       tmem_ld_32x32(tm_dq + lane_addr, a0);
@@ -3023,7 +3041,7 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
     }
     tc_fence_before();
-    __syncthreads();  // Q_i / dO_i / P / dS / dQ scratch may be overwritten by the next q tile
+    __syncthreads();  // P / dS / the dQ scratch may be overwritten by the next q tile
     tc_fence_after();
   }
 
@@ -3172,9 +3190,8 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * D * sizeof(float), st);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: memset: %s", cudaGetErrorString(e));
     dim3 grid((N + TILE - 1) / TILE, H, B);
-    attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, (const __nv_bfloat16*)out,
-                                                                    (const __nv_bfloat16*)dout, lse, (__nv_bfloat16*)dqkv,
-                                                                    dq32, N, H, scale);
+    attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H,
+                                                                    scale);
     rc = vitk_check_launch("attn_bwd_stream");
     if (rc) return rc;
     const long long n8 = rows * (D / 8);
