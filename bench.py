@@ -20,8 +20,17 @@ import sys
 import threading
 import time
 
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner at NCCL_DEBUG=WARN
+# ignores NCCL_DEBUG_FILE on this image), so file descriptor 1 points at stderr while the benchmark runs and is only
+# restored for the final print.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str) -> None:
+    sys.stdout.flush()
+    os.dup2(_REAL_STDOUT, 1)
+    print(line, flush=True)
 
 import torch
 
@@ -142,7 +151,7 @@ def run_reference(args):
     v = sample_b / dt
     cores = torch.get_num_threads()
     sample = f"{args.model} fwd+bwd+AdamW fp32 eager CPU, batch {sample_b} per step (bounded sample of batch {args.batch})"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "train images/sec", "value": v, "unit": "img/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -333,7 +342,7 @@ def main():
                               "frac_of_measured_sustained": step_tf / pk["tf"], "frac_of_nominal_2250": step_tf / 2250.0}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.model, args.batch)
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 if __name__ == "__main__":
