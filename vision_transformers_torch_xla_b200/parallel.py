@@ -11,12 +11,20 @@ on GPU — with a bucketed all-reduce driven by the fused backward stages:
   * the optimizer's pre-step hook waits for the outstanding buckets; the 1/world_size of the mean is folded
     into the AdamW kernel (``grad_scale``), so averaging costs no extra pass over the gradients.
 
+Two schedules (``VITK_DP_SYNC``): ``block`` is the bucketed, overlapped one described above; ``step`` (default) reduces
+the whole flat gradient once, right after backward.  Measured at 8 B200, ViT-B/16, batch 256/GPU, same box, back to back:
+``step`` 34.98 ms/step (58 545 img/s, 96 % of 8 x the 1-GPU rate) vs ``block`` 36.17 ms (56 622 img/s, 93 %): over
+NVSwitch the 346 MB all-reduce costs ~1.2 ms when it runs alone, while NCCL's CTAs running *during* backward take SMs away
+from kernels that are persistent with exactly one CTA per SM (GEMM, attention), and a displaced CTA only starts when
+another one has finished its whole tile loop.
+
 With ``update_freq > 1`` buckets are only reduced on the micro-batch that precedes ``optimizer.step()``
 (``no_sync()`` context, like DDP).
 """
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import List
 
 import torch
@@ -42,6 +50,9 @@ class DataParallel(nn.Module):
             dist.broadcast(st.flat, src=0)  # identical replicas (DDP does the same at construction)
             st._sig = None
         self._ranges = self._make_buckets(st)
+        self.sync_mode = os.environ.get("VITK_DP_SYNC", "step")   # "block": per-block buckets overlapped with backward
+        if self.sync_mode not in ("block", "step"):
+            raise ValueError(f"VITK_DP_SYNC={self.sync_mode!r}: expected 'block' or 'step'")
         st.grad_ready_hooks.append(self._on_grad_ready)
         if optimizer is not None:
             self.attach_optimizer(optimizer)
@@ -80,6 +91,9 @@ class DataParallel(nn.Module):
     def _on_grad_ready(self, tag: str):
         if not self.require_sync or self.world_size == 1:
             return
+        if self.sync_mode == "step":
+            self._pending = True
+            return
         rng = self._ranges.get(tag)
         if rng is None or rng[1] <= rng[0]:
             return
@@ -87,6 +101,9 @@ class DataParallel(nn.Module):
         self._works.append(dist.all_reduce(self.store.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
     def finish_gradient_sync(self):
+        if self._pending:
+            self._pending = False
+            dist.all_reduce(self.store.grad, op=dist.ReduceOp.SUM)
         for w in self._works:
             w.wait()
         self._works.clear()
