@@ -51,15 +51,20 @@ def _worker(rank, world, port, q):
         r = dp._ranges
         assert r["embed"][0] == 0 and r["embed"][1] == r["blocks.0."][0] and r["blocks.0."][1] == r["blocks.1."][0]
         assert r["blocks.1."][1] == r["head"][0] and r["head"][1] == st.total
-        # 3) hooks fire in backward order; the optimizer's pre-step hook waits; grads are SUMMED (mean is in grad_scale)
-        st.grad.fill_(float(rank + 1))
-        for tag in ("head", "blocks.1.", "blocks.0.", "embed"):
-            st.fire_grad_ready(tag)
-        assert len(dp._works) == 4
-        opt.step()
-        assert len(dp._works) == 0
-        assert torch.equal(st.grad, torch.full_like(st.grad, float(sum(range(1, world + 1)))))
-        assert torch.equal(m.head.weight.grad, torch.full_like(m.head.weight, 3.0))  # p.grad views the flat buffer
+        # 3) hooks fire in backward order; the optimizer's pre-step hook waits; grads are SUMMED (mean is in grad_scale).
+        #    "block": one asynchronous all-reduce per bucket; "step" (default): one all-reduce of the flat buffer at step().
+        assert dp.sync_mode == "step"
+        for mode, in_flight in (("block", 4), ("step", 0)):
+            dp.sync_mode = mode
+            st.grad.fill_(float(rank + 1))
+            for tag in ("head", "blocks.1.", "blocks.0.", "embed"):
+                st.fire_grad_ready(tag)
+            assert len(dp._works) == in_flight and dp._pending == (mode == "step")
+            opt.step()
+            assert len(dp._works) == 0 and not dp._pending
+            assert torch.equal(st.grad, torch.full_like(st.grad, float(sum(range(1, world + 1)))))
+            assert torch.equal(m.head.weight.grad, torch.full_like(m.head.weight, 3.0))  # p.grad views the flat buffer
+        dp.sync_mode = "block"
         # 4) no_sync(): gradient accumulation micro-steps do not communicate
         st.grad.fill_(float(rank + 1))
         with dp.no_sync():
