@@ -3119,6 +3119,7 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   if (variant == 0 && T == 2) return launch_fwd4(tm, out, lse, B, N, H, scale, s);
   if (variant == 0 && T > 2) return launch_fwd5(tm, out, lse, B, N, H, scale, s);
   if (variant == 3 && T == 2) return launch_fwd3(tm, out, lse, B, N, H, scale, s);
+  if (variant == 5 && T == 2) return launch_fwd5(tm, out, lse, B, N, H, scale, s);   // flash-style kv loop at short N (comparison)
   if (variant == 2 && T == 1) return launch_fwd2<1>(tm, out, lse, B, N, H, scale, s);
   if (variant == 2 && T == 2) return launch_fwd2<2>(tm, out, lse, B, N, H, scale, s);
   switch (T) {
