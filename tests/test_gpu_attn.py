@@ -107,6 +107,31 @@ def test_attn_older_kernels_still_agree(cuda_device, variant, monkeypatch):
         "g = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B, N, 3 * H * 64)\n"
         "e1 = ((out.float() - ref).abs().max() / ref.abs().max()).item(); e2 = ((dqkv.float() - g).abs().max() / g.abs().max()).item()\n"
         "assert e1 < 2e-2 and e2 < 3e-2, (e1, e2)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    env = dict(os.environ, VITK_ATTN_FWD=variant if variant != "3" else "0", VITK_ATTN_BWD=variant)
+    env = dict(os.environ, VITK_ATTN_FWD=variant, VITK_ATTN_BWD=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_attn_long_sequence_pingpong_variant(cuda_device):
+    """VITK_ATTN_BWD_LONG=5 (two-warpgroup variant of the N > 256 backward) gives the same gradients."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from vision_transformers_torch_xla_b200 import _lib as L\n"
+        "torch.manual_seed(0); B, N, H = 3, 577, 5\n"
+        "qkv = torch.randn(B, N, 3 * H * 64, device='cuda').bfloat16(); dout = torch.randn(B, N, H * 64, device='cuda').bfloat16()\n"
+        "out = torch.empty(B, N, H * 64, device='cuda', dtype=torch.bfloat16); lse = torch.empty(B, H, N, device='cuda')\n"
+        "dqkv = torch.empty_like(qkv)\n"
+        "L.attn_fwd(qkv, out, lse, B, N, H, 64, 0.125); L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, 64, 0.125)\n"
+        "q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)\n"
+        "q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)\n"
+        "o = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v\n"
+        "o.transpose(1, 2).reshape(B, N, H * 64).backward(dout.float())\n"
+        "g = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B, N, 3 * H * 64)\n"
+        "e2 = ((dqkv.float() - g).abs().max() / g.abs().max()).item()\n"
+        "assert e2 < 3e-2, e2\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VITK_ATTN_BWD_LONG="5"), capture_output=True, text=True,
+                       timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]

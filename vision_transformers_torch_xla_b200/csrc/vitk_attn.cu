@@ -3065,6 +3065,308 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   }
 }
 
+// ================================================================================================
+// Backward for 256 < N <= 640, ping-pong variant of the streaming kernel: still one CTA per (b, h, kv tile j) with K_j /
+// V_j resident and dV_j / dK_j accumulating in TMEM over all q tiles, but the q tiles are split between two warpgroups
+// (group g takes tiles g, g+2, ...; thread = row) that run out of phase like in attn_bwd4: S and dP share one TMEM
+// buffer per group (S -> P, then dP -> dS over P in smem), warp 8 issues every MMA from two in-order event queues
+// (S_t | P_t -> dV +=, dP_t | dS_t -> dK +=, dQ_t) served in arrival order, warp 9 streams Q_i / dO_i through two
+// buffers per group.  dQ_ij is produced into a per-group TMEM scratch tile, read out and red.add'ed into the fp32
+// workspace while the MMA warp already works for the other group.
+// TMEM: SdP_0 [0,128) | SdP_1 [128,256) | dV_j [256,320) | dK_j [320,384) | dQ scratch 0 [384,448) | 1 [448,512)
+// smem: K_j V_j (32K) | group g: 2 x (Q_i dO_i) (2 x 64K) | PdS_0 PdS_1 (64K) | barriers
+// ================================================================================================
+struct Bwd5Smem {
+  static constexpr uint32_t KV_OFF = 0;
+  static constexpr uint32_t QDO_OFF = 2 * TILE_BYTES;    // [g][buffer][Q, dO]
+  static constexpr uint32_t PDS_OFF = 10 * TILE_BYTES;   // [g][2 chunks of 64 kv columns]
+  static constexpr uint32_t BAR_OFF = 14 * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(BWD3_THREADS, 1)
+attn_bwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                 const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                 float* __restrict__ dq32, int N, int H, float scale) {
+  using L = Bwd5Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* q_full = bar_kv + 1;      // [g][buf]
+  uint64_t* q_empty = q_full + 4;     // [g][buf]
+  uint64_t* bar_s = q_empty + 4;      // [g]
+  uint64_t* bar_p = bar_s + 2;        // [g] count 4
+  uint64_t* bar_dp = bar_p + 2;       // [g]
+  uint64_t* bar_ds = bar_dp + 2;      // [g] count 4
+  uint64_t* bar_dq = bar_ds + 2;      // [g] MMA -> group: dQ scratch ready
+  uint64_t* dq_free = bar_dq + 2;     // [g] count 4, group -> MMA: scratch read out
+  uint64_t* bar_final = dq_free + 2;  // MMA -> groups: dV_j, dK_j final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int QT = (N + TILE - 1) / TILE;
+  const int kvn = min(TILE, N - j * TILE);
+  const uint32_t n_eff = roundup16(kvn);
+  const int nch = (int)(n_eff + 31) / 32;
+  const int ntile[2] = {(QT + 1) / 2, QT / 2};   // q tiles of group 0 / 1
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_p[i], 4);
+      mbar_init(&bar_dp[i], 1);
+      mbar_init(&bar_ds[i], 4);
+      mbar_init(&bar_dq[i], 1);
+      mbar_init(&dq_free[i], 4);
+    }
+    mbar_init(bar_final, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
+
+  if (warp == 9) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      tma_prefetch_desc(&tm_do);
+      mbar_arrive_expect_tx(bar_kv, 2 * TILE_BYTES);
+      tma_load_3d(smem + L::KV_OFF, &tm_qkv, bar_kv, (H + h) * HD, j * TILE, b);
+      tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, (2 * H + h) * HD, j * TILE, b);
+      for (int t = 0; t < ntile[0]; ++t) {
+        for (int g = 0; g < 2; ++g) {
+          if (t >= ntile[g]) continue;
+          const int buf = t & 1, i = g + 2 * t;
+          if (t >= 2) mbar_wait(&q_empty[g * 2 + buf], ((t >> 1) & 1) ^ 1);
+          uint8_t* dst = smem + L::QDO_OFF + (g * 2 + buf) * 2 * TILE_BYTES;
+          mbar_arrive_expect_tx(&q_full[g * 2 + buf], 2 * TILE_BYTES);
+          tma_load_3d(dst, &tm_qkv, &q_full[g * 2 + buf], h * HD, i * TILE, b);
+          tma_load_3d(dst + TILE_BYTES, &tm_do, &q_full[g * 2 + buf], h * HD, i * TILE, b);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------ MMA issuer: two in-order event queues served in arrival order ------------------------------
+    const uint32_t sKV = smem_u32(smem + L::KV_OFF), sQDO = smem_u32(smem + L::QDO_OFF), sPDS = smem_u32(smem + L::PDS_OFF);
+    const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
+    const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);    // A, B MN-major: P^T dO, dS^T Q
+    const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);   // dS K
+    const uint64_t kd = umma_desc_kmajor(sKV), vd = umma_desc_kmajor(sKV + TILE_BYTES), k_mn = umma_desc_mnmajor(sKV, TILE_BYTES);
+    int ev[2] = {0, 0};                 // queue position of group g: 3 * tile + {0: S, 1: P -> dV, dP, 2: dS -> dK, dQ}
+    bool dv_init = false, dk_init = false;
+    mbar_wait(bar_kv, 0);
+    while (ev[0] < 3 * ntile[0] || ev[1] < 3 * ntile[1]) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (ev[g] >= 3 * ntile[g]) continue;
+        const int t = ev[g] / 3, k = ev[g] - 3 * t, buf = t & 1;
+        const uint32_t par = t & 1;
+        const uint32_t sQ = sQDO + (g * 2 + buf) * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES, sP = sPDS + g * 2 * TILE_BYTES;
+        const uint32_t q_eff = roundup16(min(TILE, N - (g + 2 * t) * TILE));
+        bool ready;
+        if (k == 0) ready = mbar_test(&q_full[g * 2 + buf], (t >> 1) & 1);
+        else if (k == 1) ready = mbar_test(&bar_p[g], par) && (g == 0 || dv_init);
+        else ready = mbar_test(&bar_ds[g], par) && (t == 0 || mbar_test(&dq_free[g], (t - 1) & 1)) && (g == 0 || dk_init);
+        if (!ready) continue;
+        tc_fence_after();
+        if (k == 0) {
+          const uint64_t qd = umma_desc_kmajor(sQ);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tmem_base + g * 128, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk > 0);
+            umma_commit(&bar_s[g]);
+          }
+        } else if (k == 1) {
+          const uint64_t p_mn = umma_desc_mnmajor(sP, TILE_BYTES), do_mn = umma_desc_mnmajor(sDO, TILE_BYTES), dod = umma_desc_kmajor(sDO);
+          const uint32_t acc0 = dv_init ? 1u : 0u;
+          if (elect_one()) {
+            for (int kk = 0; kk < (int)q_eff / 16; ++kk)
+              umma_bf16_ss(tm_dv, p_mn + (uint64_t)(kk * 128), do_mn + (uint64_t)(kk * 128), idesc_t, kk > 0 ? 1u : acc0);
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tmem_base + g * 128, dod + (uint64_t)(kk * 2), vd + (uint64_t)(kk * 2), idesc_s, kk > 0);
+            umma_commit(&bar_dp[g]);
+          }
+          dv_init = true;
+        } else {
+          const uint64_t ds_mn = umma_desc_mnmajor(sP, TILE_BYTES), q_mn = umma_desc_mnmajor(sQ, TILE_BYTES), ds_k = umma_desc_kmajor(sP);
+          const uint32_t acc0 = dk_init ? 1u : 0u;
+          if (elect_one()) {
+            for (int kk = 0; kk < (int)q_eff / 16; ++kk)
+              umma_bf16_ss(tm_dk, ds_mn + (uint64_t)(kk * 128), q_mn + (uint64_t)(kk * 128), idesc_t, kk > 0 ? 1u : acc0);
+            for (int kk = 0; kk < (int)n_eff / 16; ++kk)
+              umma_bf16_ss(tm_dq + g * HD, ds_k + (uint64_t)((kk >> 2) * (TILE_BYTES >> 4) + (kk & 3) * 2), k_mn + (uint64_t)(kk * 128),
+                           idesc_q, kk > 0);
+            umma_commit(&bar_dq[g]);
+            umma_commit(&q_empty[g * 2 + buf]);
+          }
+          dk_init = true;
+        }
+        __syncwarp();
+        ++ev[g];
+      }
+    }
+    if (elect_one()) umma_commit(bar_final);
+    __syncwarp();
+  } else {
+    // ------------------------------ warpgroup g: rows of its q tiles ------------------------------
+    const int g = warp >> 2, r = threadIdx.x & 127;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tm_sdp = tmem_base + g * 128 + lane_addr;
+    uint8_t* sPDS = smem + L::PDS_OFF + g * 2 * TILE_BYTES;
+    const float c2 = scale * LOG2E;
+    const int D = H * HD;
+    for (int t = 0; t < ntile[g]; ++t) {
+      const int i = g + 2 * t;
+      const int qn = min(TILE, N - i * TILE);
+      const uint32_t q_eff = roundup16(qn);
+      const bool warp_active = (uint32_t)((warp & 3) * 32) < q_eff;
+      const int q = i * TILE + r;
+      const bool row_ok = r < qn;
+      float my_lse2 = 0.f, my_ds = 0.f;   // rows >= N: P = 2^S stays finite, dS = 0
+      if (row_ok) {
+        my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
+        my_ds = dsum[((long long)b * H + h) * N + q] * scale;
+      }
+      // ---- S -> P ----
+      mbar_wait(&bar_s[g], t & 1);
+      tc_fence_after();
+      if (warp_active) {
+        uint32_t ra[32], rb[32];
+        auto p_chunk = [&](const uint32_t (&v)[32], int c) {
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+              pk[x] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(v[gg * 8 + 2 * x]), c2, -my_lse2)),
+                                  ex2_approx(fmaf(__uint_as_float(v[gg * 8 + 2 * x + 1]), c2, -my_lse2)));
+            st_swz(sPDS, r, c * 4 + gg, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          }
+        };
+        tmem_ld_32x32(tm_sdp, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          if (c < nch) {
+            if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, rb);
+            p_chunk(ra, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32(tm_sdp + (c + 2) * 32, ra);
+              p_chunk(rb, c + 1);
+              if (c + 2 < nch) tmem_ld_wait();
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[g]);
+
+      // ---- dP -> dS (over P) ----
+      mbar_wait(&bar_dp[g], t & 1);
+      tc_fence_after();
+      if (warp_active) {
+        uint32_t ra[32], rb[32];
+        auto ds_chunk = [&](const uint32_t (&v)[32], int c) {
+          uint4 pall[4];
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg)
+            pall[gg] = *reinterpret_cast<const uint4*>(sPDS + ((c * 4 + gg) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + gg) & 7) ^ (r & 7)) << 4));
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            const uint32_t pw[4] = {pall[gg].x, pall[gg].y, pall[gg].z, pall[gg].w};
+            uint32_t ds[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const float2 pp = unpack_bf16x2(pw[x]);
+              ds[x] = pack_bf16x2(pp.x * fmaf(__uint_as_float(v[gg * 8 + 2 * x]), scale, -my_ds),
+                                  pp.y * fmaf(__uint_as_float(v[gg * 8 + 2 * x + 1]), scale, -my_ds));
+            }
+            *reinterpret_cast<uint4*>(sPDS + ((c * 4 + gg) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + gg) & 7) ^ (r & 7)) << 4)) =
+                make_uint4(ds[0], ds[1], ds[2], ds[3]);
+          }
+        };
+        tmem_ld_32x32(tm_sdp, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          if (c < nch) {
+            if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, rb);
+            ds_chunk(ra, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld_32x32(tm_sdp + (c + 2) * 32, ra);
+              ds_chunk(rb, c + 1);
+              if (c + 2 < nch) tmem_ld_wait();
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ds[g]);
+
+      // ---- dQ_ij: scratch -> registers (hand the scratch back) -> red.add into the fp32 workspace ----
+      mbar_wait(&bar_dq[g], t & 1);
+      tc_fence_after();
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(tm_dq + g * HD + lane_addr, a0);
+      tmem_ld_32x32(tm_dq + g * HD + lane_addr + 32, a1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dq_free[g]);
+      if (row_ok) {
+        float* dst = dq32 + ((long long)b * N + q) * D + h * HD;
+#pragma unroll
+        for (int gg = 0; gg < 8; ++gg) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + gg * 4), "f"(__uint_as_float(a0[gg * 4])),
+                       "f"(__uint_as_float(a0[gg * 4 + 1])), "f"(__uint_as_float(a0[gg * 4 + 2])), "f"(__uint_as_float(a0[gg * 4 + 3]))
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 + gg * 4), "f"(__uint_as_float(a1[gg * 4])),
+                       "f"(__uint_as_float(a1[gg * 4 + 1])), "f"(__uint_as_float(a1[gg * 4 + 2])), "f"(__uint_as_float(a1[gg * 4 + 3]))
+                       : "memory");
+        }
+      }
+    }
+    // ---- dV_j (group 0) / dK_j (group 1) ----
+    mbar_wait(bar_final, 0);
+    tc_fence_after();
+    {
+      uint32_t a0[32], a1[32];
+      const int kv = j * TILE + r;
+      const uint32_t src = (g == 0 ? tm_dv : tm_dk) + lane_addr;
+      tmem_ld_32x32(src, a0);
+      tmem_ld_32x32(src + 32, a1);
+      tmem_ld_wait();
+      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * D) + ((g == 0 ? 2 : 1) * H + h) * HD, a0, a1);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // dqkv[row, 0:D] = bf16(dq32[row, 0:D])  (row pitch of dqkv is 3*D)
 __global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int D) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -3169,6 +3471,8 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
     if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd5Smem::BYTES);
+    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -3191,8 +3495,19 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * D * sizeof(float), st);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: memset: %s", cudaGetErrorString(e));
     dim3 grid((N + TILE - 1) / TILE, H, B);
-    attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H,
-                                                                    scale);
+    // VITK_ATTN_BWD_LONG=5 selects the two-warpgroup ping-pong variant.  Measured at ViT-L/384 (B = 64, H = 16, N = 577):
+    // 816 us for both — each group's S -> P -> (dV, dP) -> dS -> (dK, dQ) chain is latency-bound (~8 k cycles per q tile),
+    // and 3 + 2 tiles on two groups are no shorter than 5 tiles at ~6 k on one; 156 us of either are the dQ red.adds
+    // (838 MB of fp32 atomics per layer), ~90 us the memset / cast / D kernels around it.
+    static const int long_variant = [] {
+      const char* e = getenv("VITK_ATTN_BWD_LONG");
+      return e ? atoi(e) : 0;
+    }();
+    if (long_variant != 5)
+      attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H,
+                                                                      scale);
+    else
+      attn_bwd5_kernel<<<grid, BWD3_THREADS, Bwd5Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H, scale);
     rc = vitk_check_launch("attn_bwd_stream");
     if (rc) return rc;
     const long long n8 = rows * (D / 8);
