@@ -193,6 +193,14 @@ int vitk_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, doubl
 int vitk_mixup_target(const int64_t* labels, float* out, int32_t B, int32_t C, double lam, double smoothing,
                       void* stream);
 
+/* LayerScale backward (/root/reference/models/vision_transformer.py:80-106; the forward is the `colscale` of the
+ * residual GEMM epilogue).  vitk_colscale_bf16: x[r, c] *= gamma[c] in place on the bf16 branch gradient.
+ * vitk_layerscale_grad: dgamma[c] = (sum_k W[c,k] dW[c,k] + bias[c] dbias[c]) / gamma[c]  (SET, not accumulated; W / dW are
+ * the [C, K] weight of the branch's last Linear and its gradient computed from the gamma-scaled branch gradient). */
+int vitk_colscale_bf16(void* x_bf16, const float* gamma, int64_t rows, int32_t dim, void* stream);
+int vitk_layerscale_grad(const float* W, const float* dW, const float* bias, const float* dbias, const float* gamma,
+                         float* dgamma, int32_t C, int32_t K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -255,6 +255,44 @@ def test_engine_train_one_epoch_and_evaluate(cuda_device):
     assert set(ev) == {"loss", "acc1", "acc5"} and math.isfinite(ev["loss"])
 
 
+def test_layerscale_matches_oracle(cuda_device):
+    """init_values -> LayerScale (/root/reference/models/vision_transformer.py:80-106): forward through the residual
+    epilogue's column scale, gamma gradients from the branch's weight gradients (vitk_layerscale_grad)."""
+    from vision_transformers_torch_xla_b200.losses import SoftTargetCrossEntropy
+    from vision_transformers_torch_xla_b200.models import create_model
+    from oracle import vit_oracle as O
+
+    torch.manual_seed(0)
+    kw = dict(num_classes=1000, global_pool="avg", init_values=0.1)
+    ref = O.create_model("vit_tiny_patch16_224", **kw).to(cuda_device)
+    mine = create_model("vit_tiny_patch16_224", **kw).to(cuda_device)
+    assert set(mine.state_dict()) == set(ref.state_dict()) and "blocks.0.ls1.gamma" in mine.state_dict()
+    with torch.no_grad():   # make the scales non-uniform so that a wrong channel mapping cannot hide
+        for blk in ref.blocks:
+            blk.ls1.gamma.mul_(torch.rand_like(blk.ls1.gamma) + 0.5)
+            blk.ls2.gamma.mul_(torch.rand_like(blk.ls2.gamma) + 0.5)
+    mine.load_state_dict(ref.state_dict())
+    ref.train()
+    mine.train()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 3, 224, 224, generator=g).to(cuda_device)
+    y = O.mixup_soft_targets(torch.randint(0, 1000, (4,), generator=g)).to(cuda_device)
+    out_ref = ref(x)
+    O.SoftTargetCrossEntropy()(out_ref, y).backward()
+    out = mine(x)
+    SoftTargetCrossEntropy()(out, y).backward()
+    assert rel_err(out, out_ref) < 2e-2
+    for name in ("blocks.0.ls1.gamma", "blocks.5.ls2.gamma", "blocks.11.ls1.gamma", "blocks.11.ls2.gamma", "blocks.3.mlp.fc2.weight",
+                 "blocks.3.attn.proj.weight", "blocks.0.attn.qkv.weight"):
+        a = dict(mine.named_parameters())[name].grad
+        b = dict(ref.named_parameters())[name].grad
+        assert rms_err(a, b) < 2e-2 and cos_sim(a, b) > 0.999, name
+    # gradient accumulation: a second backward doubles dgamma (it is recomputed from the accumulated weight gradient)
+    g1 = mine.blocks[5].ls2.gamma.grad.clone()
+    SoftTargetCrossEntropy()(mine(x), y).backward()
+    assert rms_err(mine.blocks[5].ls2.gamma.grad, 2 * g1) < 1e-2
+
+
 def test_checkpoint_save_resume(cuda_device, tmp_path):
     """Reference format (/root/reference/utils/__init__.py:686-770): {'model','optimizer','epoch','scaler','args',
     'model_ema'}; resuming restores weights, Adam moments, step count and the fused EMA (the split-K wgrad

@@ -62,7 +62,7 @@ def test_create_model_kwargs_contract():
 
 def test_options_outside_the_fast_path_raise_instead_of_falling_back():
     for kw in (dict(qk_norm=True), dict(reg_tokens=4), dict(pre_norm=True), dict(global_pool="map"),
-               dict(dynamic_img_size=True), dict(init_values=1e-5), dict(attn_drop_rate=0.1), dict(no_embed_class=True)):
+               dict(dynamic_img_size=True), dict(attn_drop_rate=0.1), dict(no_embed_class=True)):
         with pytest.raises(NotImplementedError):
             VisionTransformer(embed_dim=64, depth=1, num_heads=1, **kw)
     with pytest.raises(NotImplementedError):

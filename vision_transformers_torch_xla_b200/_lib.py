@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "vitk_layernorm_bwd", "vitk_attn_fwd", "vitk_attn_bwd", "vitk_attn_bwd_workspace_bytes", "vitk_patchify", "vitk_prefix_rows",
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
-    "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target",
+    "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target", "vitk_colscale_bf16", "vitk_layerscale_grad",
 )
 
 
@@ -94,6 +94,8 @@ def load() -> ctypes.CDLL:
     lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.vitk_mixup_batch.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_double, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_void_p]
+    lib.vitk_colscale_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p]
+    lib.vitk_layerscale_grad.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.vitk_mixup_target.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_double, c_double, c_void_p]
     lib.vitk_debug_set_trace.argtypes = [c_void_p]
     lib.vitk_debug_set_trace.restype = None
@@ -443,4 +445,26 @@ def mixup_target(labels: torch.Tensor, out: torch.Tensor, lam: float, smoothing:
     with _Timed("mixup_target"):
         _check(load().vitk_mixup_target(labels.data_ptr(), out.data_ptr(), B, C, float(lam), float(smoothing), _stream()),
                "vitk_mixup_target")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerScale (backward side; the forward is the residual GEMM's colscale)
+# ------------------------------------------------------------------------------------------------
+def colscale_bf16(x: torch.Tensor, gamma: torch.Tensor, rows: int, dim: int) -> None:
+    _req(x, torch.bfloat16, "colscale x")
+    _req(gamma, torch.float32, "colscale gamma")
+    with _Timed("colscale_bf16"):
+        _check(load().vitk_colscale_bf16(x.data_ptr(), gamma.data_ptr(), rows, dim, _stream()), "vitk_colscale_bf16")
+    _count()
+
+
+def layerscale_grad(W: torch.Tensor, dW: torch.Tensor, bias: Optional[torch.Tensor], dbias: Optional[torch.Tensor],
+                    gamma: torch.Tensor, dgamma: torch.Tensor) -> None:
+    for t, nm in ((W, "W"), (dW, "dW"), (gamma, "gamma"), (dgamma, "dgamma")):
+        _req(t, torch.float32, f"layerscale_grad {nm}")
+    C, K = W.shape
+    with _Timed("layerscale_grad"):
+        _check(load().vitk_layerscale_grad(W.data_ptr(), dW.data_ptr(), _ptr(bias), _ptr(dbias), gamma.data_ptr(),
+                                           dgamma.data_ptr(), C, K, _stream()), "vitk_layerscale_grad")
     _count()

@@ -464,6 +464,55 @@ __global__ void mixup_target_kernel(const long long* __restrict__ labels, float*
   out[idx] = __fadd_rn(__fmul_rn(y1, lam), __fmul_rn(y2, om));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// LayerScale (/root/reference/models/vision_transformer.py:80-106), backward side.
+//   colscale_bf16: x[r, c] *= gamma[c] in place on the bf16 branch gradient that feeds the branch's dgrad / wgrad
+//     (the forward multiplies the branch output by gamma inside the residual GEMM epilogue).
+//   layerscale_grad: the branch output y = a W^T + b is never stored, but
+//       dgamma_c = sum_r g[r,c] y[r,c] = sum_k W[c,k] (sum_r g[r,c] a[r,k]) + b_c sum_r g[r,c]
+//     and the weight / bias gradients of the branch's last Linear, computed from the gamma-scaled gradient, are
+//     dW[c,:] = gamma_c * (sum_r g[r,c] a[r,:]), db_c = gamma_c * sum_r g[r,c].  Hence
+//       dgamma_c = (sum_k W[c,k] dW[c,k] + b_c db_c) / gamma_c,
+//     linear in the (possibly accumulated, possibly all-reduced) dW: it is SET, not added.  One warp per channel.
+// ---------------------------------------------------------------------------------------------
+__global__ void colscale_bf16_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, long long rows, int dim) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte unit
+  const int per_row = dim >> 3;
+  if (idx >= rows * per_row) return;
+  const int c = (int)(idx % per_row) * 8;
+  uint4* p = reinterpret_cast<uint4*>(x) + idx;
+  uint4 u = *p;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), d = unpack_bf16x2(u.z), e = unpack_bf16x2(u.w);
+  u.x = pack_bf16x2(a.x * g0.x, a.y * g0.y);
+  u.y = pack_bf16x2(b.x * g0.z, b.y * g0.w);
+  u.z = pack_bf16x2(d.x * g1.x, d.y * g1.y);
+  u.w = pack_bf16x2(e.x * g1.z, e.y * g1.w);
+  *p = u;
+}
+
+__global__ void layerscale_grad_kernel(const float* __restrict__ W, const float* __restrict__ dW, const float* __restrict__ b,
+                                       const float* __restrict__ db, const float* __restrict__ gamma, float* __restrict__ dgamma,
+                                       int C, int K) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  const int lane = threadIdx.x & 31;
+  const float4* w4 = reinterpret_cast<const float4*>(W + (long long)c * K);
+  const float4* d4 = reinterpret_cast<const float4*>(dW + (long long)c * K);
+  float acc = 0.f;
+  for (int k = lane; k < (K >> 2); k += 32) {
+    const float4 w = __ldg(w4 + k), d = d4[k];
+    acc += w.x * d.x + w.y * d.y + w.z * d.z + w.w * d.w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (b != nullptr) acc = fmaf(b[c], db[c], acc);
+    const float g = gamma[c];
+    dgamma[c] = g != 0.f ? acc / g : 0.f;
+  }
+}
+
 }  // namespace
 
 extern "C" int vitk_patchify(const float* img, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W,
@@ -628,4 +677,22 @@ extern "C" int vitk_mixup_target(const int64_t* labels, float* out, int32_t B, i
   mixup_target_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)labels, out, B, C, (float)lam, (float)(1.0 - lam), on_value,
                                                                                        off_value);
   return vitk_check_launch("mixup_target");
+}
+
+extern "C" int vitk_colscale_bf16(void* x_bf16, const float* gamma, int64_t rows, int32_t dim, void* stream) {
+  VITK_REQUIRE(x_bf16 && gamma && rows >= 0 && dim > 0 && dim % 8 == 0, VITK_ERR_SHAPE, "colscale_bf16: bad shape (dim %% 8 == 0)");
+  VITK_REQUIRE(((uintptr_t)x_bf16 & 15) == 0 && ((uintptr_t)gamma & 15) == 0, VITK_ERR_ALIGN, "colscale_bf16: 16-byte alignment");
+  if (rows == 0) return VITK_OK;
+  const long long n = rows * (dim / 8);
+  colscale_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)x_bf16, gamma, rows, dim);
+  return vitk_check_launch("colscale_bf16");
+}
+
+extern "C" int vitk_layerscale_grad(const float* W, const float* dW, const float* bias, const float* dbias, const float* gamma,
+                                    float* dgamma, int32_t C, int32_t K, void* stream) {
+  VITK_REQUIRE(W && dW && gamma && dgamma && C > 0 && K > 0 && K % 4 == 0, VITK_ERR_SHAPE, "layerscale_grad: bad shape (K %% 4 == 0)");
+  VITK_REQUIRE((bias == nullptr) == (dbias == nullptr), VITK_ERR_SHAPE, "layerscale_grad: bias and dbias go together");
+  VITK_REQUIRE(((uintptr_t)W & 15) == 0 && ((uintptr_t)dW & 15) == 0, VITK_ERR_ALIGN, "layerscale_grad: 16-byte alignment");
+  layerscale_grad_kernel<<<(unsigned)((C + 7) / 8), 256, 0, (cudaStream_t)stream>>>(W, dW, bias, dbias, gamma, dgamma, C, K);
+  return vitk_check_launch("layerscale_grad");
 }

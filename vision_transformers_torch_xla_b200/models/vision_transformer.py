@@ -196,17 +196,15 @@ class Block(nn.Module):
             raise NotImplementedError("Block: only norm_layer=LayerNorm and mlp_layer=Mlp are built")
         if scale_mlp_norm:
             raise NotImplementedError("Block: scale_mlp_norm is not built")
-        if init_values:
-            raise NotImplementedError("Block: LayerScale (init_values) is not built yet; none of the reference configs use it")
         self.norm1 = norm_layer(dim)
         self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_norm=qk_norm, scale_norm=scale_attn_norm,
                               proj_bias=proj_bias, attn_drop=attn_drop, proj_drop=proj_drop, norm_layer=norm_layer)
-        self.ls1 = nn.Identity()
+        self.ls1 = LayerScale(dim, init_values=init_values) if init_values else nn.Identity()
         self.drop_path1 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
         self.norm2 = norm_layer(dim)
         self.mlp = mlp_layer(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, bias=proj_bias,
                              drop=proj_drop)
-        self.ls2 = nn.Identity()
+        self.ls2 = LayerScale(dim, init_values=init_values) if init_values else nn.Identity()
         self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
         self._vitk_tag = "block"
 

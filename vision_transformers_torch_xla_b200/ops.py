@@ -125,9 +125,12 @@ class BlockFn(torch.autograd.Function):
         att = _empty((M, D), torch.bfloat16, dev)
         lse = _empty((B, H, N), torch.float32, dev)
         L.attn_fwd(qkv, att, lse, B, N, H, hd, blk.attn.scale)
+        # LayerScale (vision_transformer.py:80-106): gamma rides in the residual epilogue as a per-column scale
+        g1 = blk.ls1.gamma.data if hasattr(blk.ls1, "gamma") else None
+        g2 = blk.ls2.gamma.data if hasattr(blk.ls2, "gamma") else None
         x_mid = _empty((B, N, D), torch.float32, dev)
         L.gemm(att, sh(blk.attn.proj.weight), x_mid, M=M, N=D, K=D, epilogue=L.EPI_RESID, bias=bias(blk.attn.proj),
-               resid=x, rowscale=rs1, rows_per_group=N)
+               resid=x, rowscale=rs1, rows_per_group=N, colscale=g1)
         ln2 = _empty((M, D), torch.bfloat16, dev)
         mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
         L.layernorm_fwd(x_mid, blk.norm2.weight.data, blk.norm2.bias.data, ln2, mean2, rstd2, M, D, eps)
@@ -136,7 +139,7 @@ class BlockFn(torch.autograd.Function):
         L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=L.EPI_GELU, bias=bias(blk.mlp.fc1), aux=h)
         x_out = _empty((B, N, D), torch.float32, dev)
         L.gemm(act, sh(blk.mlp.fc2.weight), x_out, M=M, N=D, K=F, epilogue=L.EPI_RESID, bias=bias(blk.mlp.fc2),
-               resid=x_mid, rowscale=rs2, rows_per_group=N)
+               resid=x_mid, rowscale=rs2, rows_per_group=N, colscale=g2)
         if save:
             ctx.blk, ctx.store, ctx.tag = blk, store, tag
             ctx.dims = (B, N, D, H, hd, F)
@@ -162,8 +165,21 @@ class BlockFn(torch.autograd.Function):
             colsum=None if lin.bias is None else gr(lin.bias))
 
         # ---------------- MLP branch: x_out = x_mid + rs2 * (fc2(gelu(fc1(ln2))) ) ----------------
+        # LayerScale: the branch gradient is g * rs * gamma; dgamma follows from the branch's last weight gradient
+        # (vitk_layerscale_grad), so the branch output never has to be stored
+        def ls_bwd_scale(gb, ls):
+            if hasattr(ls, "gamma"):
+                L.colscale_bf16(gb, ls.gamma.data, M, D)
+
+        def ls_bwd_grad(ls, lin):
+            if hasattr(ls, "gamma") and ls.gamma.requires_grad:
+                L.layerscale_grad(lin.weight.data, gr(lin.weight), None if lin.bias is None else lin.bias.data,
+                                  None if lin.bias is None else gr(lin.bias), ls.gamma.data, gr(ls.gamma))
+
         gb2 = _bf16_grad(store, g, rs2, N * D).view(M, D)
+        ls_bwd_scale(gb2, blk.ls2)   # gb2 is exclusively ours (popped from the side channel or freshly made)
         wgrad(gb2, act, blk.mlp.fc2, D, F)
+        ls_bwd_grad(blk.ls2, blk.mlp.fc2)
         dh = act  # reuse: gelu output is dead after the fc2 wgrad above
         L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
         del gb2, h
@@ -178,7 +194,9 @@ class BlockFn(torch.autograd.Function):
         del dln2, ln2, x_mid, g
 
         # ---------------- attention branch: x_mid = x + rs1 * proj(attn(qkv(ln1))) ----------------
+        ls_bwd_scale(gb1, blk.ls1)
         wgrad(gb1, att, blk.attn.proj, D, D)
+        ls_bwd_grad(blk.ls1, blk.attn.proj)
         datt = _empty((M, D), torch.bfloat16, dev)
         L.gemm(gb1, sh(blk.attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
         dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
