@@ -11,6 +11,7 @@ instead of after every step (engine.py:278-279, 290-299).
 """
 from __future__ import annotations
 
+import os
 import time
 from typing import Iterable, Optional
 
@@ -67,7 +68,7 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
             wandb_logger._wandb.log({"train/loss": metric_logger.meters["loss"].value, "train/learning_rate": lr_now,
                                      "train/epoch": epoch})
 
-    if on_gpu:
+    if on_gpu and os.environ.get("VITK_NO_PREFETCH", "0") != "1":
         data_loader = utils.DevicePrefetcher(data_loader, torch.device(device))   # H2D of batch i+1 overlaps step i
     for data_iter_step, (samples, targets) in enumerate(metric_logger.log_every(data_loader, 10, header, quiet=quiet)):
         step = data_iter_step // update_freq
