@@ -112,6 +112,56 @@ def test_against_torchvision_vit_independent_implementation():
         assert torch.allclose(m(x), ref(x), atol=2e-5, rtol=1e-4)
 
 
+def test_against_huggingface_vit_second_independent_implementation():
+    """A second independently written ViT (transformers.ViTForImageClassification, the architecture timm's checkpoints
+    were ported to): shared weights must give the same logits AND the same parameter gradients."""
+    tr = pytest.importorskip("transformers")
+    torch.manual_seed(0)
+    D, depth, heads = 128, 2, 2
+    cfg = tr.ViTConfig(hidden_size=D, num_hidden_layers=depth, num_attention_heads=heads, intermediate_size=4 * D,
+                       hidden_act="gelu", layer_norm_eps=1e-6, image_size=64, patch_size=16, num_channels=3, qkv_bias=True,
+                       num_labels=10, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    ref = tr.ViTForImageClassification(cfg)
+    m = O.VisionTransformer(img_size=64, patch_size=16, embed_dim=D, depth=depth, num_heads=heads, num_classes=10,
+                            global_pool="token")
+    with torch.no_grad():
+        for prm in m.parameters():
+            if prm.ndim == 1:
+                prm.add_(0.1 * torch.randn_like(prm))
+    sd = {"vit.embeddings.cls_token": m.cls_token, "vit.embeddings.position_embeddings": m.pos_embed,
+          "vit.embeddings.patch_embeddings.projection.weight": m.patch_embed.proj.weight,
+          "vit.embeddings.patch_embeddings.projection.bias": m.patch_embed.proj.bias,
+          "vit.layernorm.weight": m.norm.weight, "vit.layernorm.bias": m.norm.bias,
+          "classifier.weight": m.head.weight, "classifier.bias": m.head.bias}
+    for i, blk in enumerate(m.blocks):
+        p = f"vit.encoder.layer.{i}."
+        wq, wk, wv = blk.attn.qkv.weight.chunk(3, 0)
+        bq, bk, bv = blk.attn.qkv.bias.chunk(3, 0)
+        for nm, w, b in (("query", wq, bq), ("key", wk, bk), ("value", wv, bv)):
+            sd[p + f"attention.attention.{nm}.weight"], sd[p + f"attention.attention.{nm}.bias"] = w, b
+        sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"] = blk.attn.proj.weight, blk.attn.proj.bias
+        sd[p + "layernorm_before.weight"], sd[p + "layernorm_before.bias"] = blk.norm1.weight, blk.norm1.bias
+        sd[p + "layernorm_after.weight"], sd[p + "layernorm_after.bias"] = blk.norm2.weight, blk.norm2.bias
+        sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"] = blk.mlp.fc1.weight, blk.mlp.fc1.bias
+        sd[p + "output.dense.weight"], sd[p + "output.dense.bias"] = blk.mlp.fc2.weight, blk.mlp.fc2.bias
+    ref.load_state_dict({k: v.detach().clone() for k, v in sd.items()}, strict=True)
+    ref.train()
+    m.train()
+    x = torch.randn(3, 3, 64, 64)
+    t = torch.softmax(torch.randn(3, 10), -1)
+    out_ref = ref(pixel_values=x).logits
+    out = m(x)
+    assert torch.allclose(out, out_ref, atol=2e-5, rtol=1e-4)
+    O.SoftTargetCrossEntropy()(out, t).backward()
+    O.SoftTargetCrossEntropy()(out_ref, t).backward()
+    g_ref = dict(ref.named_parameters())
+    assert torch.allclose(m.blocks[0].mlp.fc1.weight.grad, g_ref["vit.encoder.layer.0.intermediate.dense.weight"].grad, atol=1e-6, rtol=1e-3)
+    assert torch.allclose(m.blocks[1].attn.qkv.weight.grad[:D], g_ref["vit.encoder.layer.1.attention.attention.query.weight"].grad,
+                          atol=1e-6, rtol=1e-3)
+    assert torch.allclose(m.patch_embed.proj.weight.grad, g_ref["vit.embeddings.patch_embeddings.projection.weight"].grad,
+                          atol=1e-6, rtol=1e-3)
+
+
 def test_losses_closed_forms():
     torch.manual_seed(0)
     x = torch.randn(5, 11)
