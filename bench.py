@@ -295,12 +295,31 @@ def main():
     # ---------------- timed region 2: end to end through engine.train_one_epoch ----------------
     e2e = None
     if not args.no_e2e:
-        loader = [host[i % 2] for i in range(args.steps)]
+        fetch_times = []
+
+        class _Loader:   # pinned host batches; notes when the engine asks for each one (diagnostics on stderr only)
+            def __len__(self):
+                return args.steps
+
+            def __iter__(self):
+                for i in range(args.steps):
+                    fetch_times.append(time.perf_counter())
+                    yield host[i % 2]
+
+        loader = _Loader()
+        # untimed warm-up of the end-to-end path itself (the engine's own small torch ops, the prefetcher's buffers and
+        # stream, pinned read-back buffers: first use costs 0.2-0.5 s of lazy CUDA module loading and allocation)
+        engine.train_one_epoch(train_model, crit, [host[i % 2] for i in range(args.warmup)], opt, dev, 0, None,
+                               log_freq=1, update_freq=1, quiet=True)
         barrier()
         e0.record()
         engine.train_one_epoch(train_model, crit, loader, opt, dev, 0, None, log_freq=1, update_freq=1, quiet=True)
         e1.record()
         barrier()
+        if rank == 0 and len(fetch_times) > 2:
+            gaps = sorted((b - a) * 1e3 for a, b in zip(fetch_times, fetch_times[1:]))
+            print(f"[e2e] host interval between batch fetches: median {gaps[len(gaps) // 2]:.1f} ms, max {gaps[-1]:.1f} ms, "
+                  f"first fetch -> last fetch {1e3 * (fetch_times[-1] - fetch_times[0]):.1f} ms", file=sys.stderr)
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if distributed:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -8,7 +8,9 @@ from conftest import elem_err, rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("rows,dim", [(1576, 192), (1000, 384), (4097, 768), (577, 1024), (3, 768)])
+# rows >= 4096 take the shared-memory-ring backward (bulk async copies), fewer rows the register-resident one
+@pytest.mark.parametrize("rows,dim", [(1576, 192), (1000, 384), (4097, 768), (577, 1024), (3, 768),
+                                      (5000, 192), (4100, 384), (4096, 512), (4099, 1024), (50432, 768)])
 def test_layernorm_fwd_bwd(cuda_device, rows, dim):
     from vision_transformers_torch_xla_b200 import _lib as L
     torch.manual_seed(0)
@@ -46,6 +48,10 @@ def test_layernorm_fwd_bwd(cuda_device, rows, dim):
     g2 = torch.empty(rows, dim, device=cuda_device)
     L.layernorm_bwd(dy, x, mean, rstd, gamma, None, g2, None, None, 1, None, None, rows, dim)
     assert rel_err(g2, xr.grad) < 1e-4
+    # in place on the residual gradient (g_out is g_in), the way the block backward calls it
+    g3 = g_in.clone()
+    L.layernorm_bwd(dy, x, mean, rstd, gamma, g3, g3, None, None, 1, None, None, rows, dim)
+    assert torch.equal(g3, g_out)
 
 
 def test_layernorm_strided_rows(cuda_device):
