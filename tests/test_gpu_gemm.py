@@ -73,23 +73,32 @@ def test_fprop_gelu_dual(cuda_device):
     assert elem_err(aux.float(), h.grad) < BF16_TOL  # aux = gelu'(h)
 
 
-def test_fprop_resid_scales(cuda_device):
+# K <= 1536 takes the TMA residual-ring epilogue (panels prefetched across tiles, TMA stores), larger K the
+# register-prefetch one; N = 200 / 1000 end in partial 32-column boxes, M = 5000 / 50432 give every CTA several tiles
+@pytest.mark.parametrize("M,N,K", [(394, 768, 3072), (394, 768, 768), (5000, 768, 768), (1000, 384, 384), (300, 200, 256),
+                                   (130, 1000, 512), (50432, 768, 768), (2049, 1024, 1024)])
+def test_fprop_resid_scales(cuda_device, M, N, K):
     from vision_transformers_torch_xla_b200 import _lib as L
-    M, N, K = 394, 768, 3072
     a = _mk((M, K), cuda_device, seed=1).bfloat16()
     w = _mk((N, K), cuda_device, 0.02, seed=2).bfloat16()
     bias = _mk((N,), cuda_device, seed=3)
     resid = _mk((M, N), cuda_device, seed=4)
-    rs = torch.tensor([1.0 / 0.9, 0.0], device=cuda_device)
+    groups = (M + 196) // 197
+    rs = torch.tensor([1.0 / 0.9, 0.0, 1.0], device=cuda_device).repeat((groups + 2) // 3)[:groups].contiguous()
     cs = _mk((N,), cuda_device, seed=5)
     out = torch.empty((M, N), device=cuda_device)
     L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_RESID, bias=bias, resid=resid, rowscale=rs, rows_per_group=197,
            colscale=cs)
-    ref = resid + rs.repeat_interleave(197)[:, None] * cs[None, :] * (a.float() @ w.float().t() + bias)
+    acc = a.float() @ w.float().t() + bias
+    ref = resid + rs.repeat_interleave(197)[:M, None] * cs[None, :] * acc
     assert rel_err(out, ref) < F32_TOL
     out2 = torch.empty((M, N), device=cuda_device)
     L.gemm(a, w, out2, M=M, N=N, K=K, epilogue=L.EPI_RESID, bias=bias, resid=resid)
-    assert rel_err(out2, resid + a.float() @ w.float().t() + bias) < F32_TOL
+    assert rel_err(out2, resid + acc) < F32_TOL
+    # in place on the residual stream (out is resid), the way the block forward calls it; same bits as out of place
+    x = resid.clone()
+    L.gemm(a, w, x, M=M, N=N, K=K, epilogue=L.EPI_RESID, bias=bias, resid=x)
+    assert torch.equal(x, out2)
 
 
 def test_patch_epilogue(cuda_device):

@@ -64,6 +64,21 @@ constexpr uint32_t kStgBytes = (EPI == EPI_BF16) ? 2048u : 4096u;
 // two [32 rows][64 B] panels per warp in the 64-byte-swizzle layout (see the epilogue branch of gemm_kernel).
 template <int EPI, int PART_N>
 constexpr bool kTmaEpi = (EPI == EPI_GELU || EPI == EPI_DGELU) && PART_N == 64;
+// Residual epilogue through TMA: every epilogue warp owns a ring of three [32 rows][128 B] fp32 panels (128-byte
+// swizzle).  The residual panels of the warp's tile sequence are loaded up to two panels ahead (across tile
+// boundaries: the tile schedule is static), the sum is formed in place and leaves by a TMA store, so the epilogue
+// issues no global loads / stores and keeps 1.5-2 panels per warp in flight instead of one.  (The single-CTA
+// 256-column tile has no room for the rings next to three operand stages and keeps the register-prefetch path.)
+// The rings take 96 KB, i.e. two of the six operand stages of the 256-wide CTA-pair tile: a win for the short-K,
+// HBM-bound projection (K = 768: 123 -> 81 us per launch inside the training step) and a loss for the MMA-bound fc2
+// (K = 3072: 183 -> 197 us), so the dispatcher picks this variant (internal epilogue code EPI_RESID_TMA) for K <= 1536.
+constexpr int EPI_RESID_TMA = 100;
+constexpr int kResidTmaMaxK = 1536;
+template <int EPI, int BLOCK_N, bool CTA2>
+constexpr bool kTmaResid = (EPI == EPI_RESID_TMA);
+constexpr int kResidBufs = 3;
+template <int EPI, int BLOCK_N, bool CTA2>
+constexpr uint32_t kStgBytesFor = kTmaResid<EPI, BLOCK_N, CTA2> ? kResidBufs * 4096u : kStgBytes<EPI>;
 
 // CTA2: a pair of CTAs (cluster of 2, one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2.
 // Each CTA stages its own 128 rows of A but only HALF of the B tile, so per-SM operand traffic from L2 (and smem
@@ -380,8 +395,9 @@ template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int EW, bool CTA2>
 __global__ void __launch_bounds__(128 + EW * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
-  constexpr uint32_t STG_BYTES = kStgBytes<EPI>;
+  constexpr uint32_t STG_BYTES = kStgBytesFor<EPI, BLOCK_N, CTA2>;
   using Cfg = TileCfg<BLOCK_N, EW, STG_BYTES, CTA2>;
+  constexpr bool TMA_RESID = kTmaResid<EPI, BLOCK_N, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool ROLES_HI = true;
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
@@ -424,7 +440,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&empty_bar[s], CS ? EW : 1);  // CS: the epilogue warps release the slot after their column sums
       mbar_init(&mma_done[s], 1);
     }
-    for (int s = 0; s < EW; ++s) mbar_init(&aux_bar[s], 1);
+    for (int s = 0; s < (TMA_RESID ? EW * kResidBufs : EW); ++s) mbar_init(&aux_bar[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], CTA2 ? 2 * EW : EW);  // CTA2: epilogue warps of BOTH CTAs release the leader
@@ -575,6 +591,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int cstage = 0;
     uint32_t cphase = 0;
     [[maybe_unused]] uint32_t tphase = 0;   // kTmaEpi x GELU': parity of this warp's aux barrier
+    // TMA_RESID: this warp's panel sequence q = 0, 1, ... runs over its tiles (NP panels each); panel q lives in ring
+    // buffer q % 3 and is announced on res_bar[q % 3]
+    [[maybe_unused]] uint64_t* res_bar = aux_bar + ew * kResidBufs;
+    [[maybe_unused]] uint8_t* ring = stg_base + ew * STG_BYTES;
+    [[maybe_unused]] int rq = 0;            // sequence number of the panel being processed
+    [[maybe_unused]] int rbuf = 0;          // rq % kResidBufs
+    [[maybe_unused]] uint32_t rphase = 0;   // (rq / kResidBufs) & 1
+    [[maybe_unused]] auto resid_issue = [&](int qq) {   // one elected lane: fetch the residual panel qq of the sequence
+      constexpr int NP = PART_N / 32;
+      const int u = unit0 + (qq / NP) * ustride;
+      if (u >= total_units) return;
+      const int nb = u % p.num_n_tiles, mb = u / p.num_n_tiles;
+      const int b = qq % kResidBufs;
+      mbar_arrive_expect_tx(&res_bar[b], 4096);
+      tma_load_2d(ring + b * 4096, &tmAux, &res_bar[b], nb * BLOCK_N + part * PART_N + (qq % NP) * 32,
+                  mb * TILE_M + (int)rank * BLOCK_M + quad * 32);
+    };
+    if constexpr (TMA_RESID) {
+      if (elect_one()) {
+        resid_issue(0);
+        resid_issue(1);
+      }
+      __syncwarp();
+    }
     for (int unit = unit0; unit < total_units; unit += ustride) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.num_n_tiles;
@@ -634,7 +674,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       float rs = 1.0f;
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID || EPI == EPI_DGELU) {
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID || EPI == EPI_RESID_TMA || EPI == EPI_DGELU) {
         if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
       }
       if constexpr (kTmaEpi<EPI, PART_N>) {
@@ -736,6 +776,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
           }
         }
+      } else if constexpr (TMA_RESID) {
+        static_assert(W == 32, "residual panels are 32 columns wide");
+        const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < PART_N / 32; ++c) {
+          const int col_in_tile = part * PART_N + c * 32;
+          const int col0 = n_blk * BLOCK_N + col_in_tile;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col_in_tile;
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr, acc);
+          mbar_wait(&res_bar[rbuf], rphase);
+          // panel rq + 2 goes into the buffer panel rq - 1 left by a TMA store issued one iteration ago
+          if (elect_one()) {
+            tma_store_wait_read();
+            resid_issue(rq + 2);
+          }
+          __syncwarp();
+          tmem_ld_wait();
+          if (c + 1 == PART_N / 32) release_acc();
+          uint8_t* buf = ring + rbuf * 4096;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 cs = make_float4(rs, rs, rs, rs);
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col0 + u * 4 < p.N) {
+              if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + u * 4));
+              if (p.colscale != nullptr) {
+                const float4 cc = __ldg(reinterpret_cast<const float4*>(p.colscale + col0 + u * 4));
+                cs.x *= cc.x; cs.y *= cc.y; cs.z *= cc.z; cs.w *= cc.w;
+              }
+            }
+            float4* sp = reinterpret_cast<float4*>(buf + lane * 128 + ((u ^ (lane & 7)) << 4));
+            const float4 a = *sp;
+            *sp = make_float4(fmaf(__uint_as_float(acc[u * 4]) + bb.x, cs.x, a.x), fmaf(__uint_as_float(acc[u * 4 + 1]) + bb.y, cs.y, a.y),
+                              fmaf(__uint_as_float(acc[u * 4 + 2]) + bb.z, cs.z, a.z), fmaf(__uint_as_float(acc[u * 4 + 3]) + bb.w, cs.w, a.w));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d(&tmOut, buf, col0, row0);
+            tma_store_commit();
+          }
+          __syncwarp();
+          ++rq;
+          if (++rbuf == kResidBufs) { rbuf = 0; rphase ^= 1; }
+        }
       } else if constexpr (kStaged<EPI> && W == 32) {
         uint8_t* stg = stg_base + ew * STG_BYTES;
         const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
@@ -796,7 +884,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (!released) release_acc();
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
-    if constexpr (kTmaEpi<EPI, PART_N>) {
+    if constexpr (kTmaEpi<EPI, PART_N> || TMA_RESID) {
       if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the bulk stores
       __syncwarp();
     }
@@ -833,12 +921,19 @@ int pick_splits(int tiles, int num_k_blocks, int slots) {
   return best;
 }
 
+// TMA needs 16-byte aligned bases and row pitches; anything else takes the register-prefetch residual epilogue
+inline bool resid_tma_ok(const vitk_gemm_args* a) {
+  static const bool enabled = [] { const char* e = getenv("VITK_GEMM_RESID_TMA"); return !(e != nullptr && e[0] == '0'); }();
+  return enabled && a->resid != nullptr && (((uintptr_t)a->out | (uintptr_t)a->resid) & 15) == 0 && a->ld_out % 4 == 0 &&
+         a->ld_resid % 4 == 0 && a->N % 4 == 0;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool CTA2>
 int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   // 16 epilogue warps for the GELU epilogues (~20 instructions per element); 8 elsewhere.  With BLOCK_N = 192 and
   // 16 warps a warp's share is 48 columns, which is not a whole number of 32-column panels -> keep 8 there.
   constexpr int EW = ((EPI == EPI_GELU || EPI == EPI_DGELU) && BLOCK_N != 192) ? 16 : 8;
-  using Cfg = TileCfg<BLOCK_N, EW, kStgBytes<EPI>, CTA2>;
+  using Cfg = TileCfg<BLOCK_N, EW, kStgBytesFor<EPI, BLOCK_N, CTA2>, CTA2>;
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap tmA, tmB;
   int rc;
@@ -852,6 +947,12 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   CUtensorMap tmOut, tmAux;
   memset(&tmOut, 0, sizeof(tmOut));
   memset(&tmAux, 0, sizeof(tmAux));
+  if (kTmaResid<EPI, BLOCK_N, CTA2>) {
+    rc = vitk_make_tmap_2d(&tmOut, a->out, 4, a->N, a->M, a->ld_out, 32, 32);
+    if (rc) return rc;
+    rc = vitk_make_tmap_2d(&tmAux, a->resid, 4, a->N, a->M, a->ld_resid, 32, 32);
+    if (rc) return rc;
+  }
   if (kTmaEpi<EPI, BLOCK_N / (EW / 4)>) {
     rc = vitk_make_tmap_2d_sw64(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 32, 32);
     if (rc) return rc;
@@ -920,7 +1021,11 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
     switch (a->epilogue) {
       case EPI_BF16:  return launch_gemm<BLOCK_N, false, false, EPI_BF16, CTA2>(a, stream);
       case EPI_GELU:  return launch_gemm<BLOCK_N, false, false, EPI_GELU, CTA2>(a, stream);
-      case EPI_RESID: return launch_gemm<BLOCK_N, false, false, EPI_RESID, CTA2>(a, stream);
+      case EPI_RESID:
+        if constexpr (CTA2 || BLOCK_N < 256) {
+          if (a->K <= kResidTmaMaxK && resid_tma_ok(a)) return launch_gemm<BLOCK_N, false, false, EPI_RESID_TMA, CTA2>(a, stream);
+        }
+        return launch_gemm<BLOCK_N, false, false, EPI_RESID, CTA2>(a, stream);
       case EPI_F32:   return launch_gemm<BLOCK_N, false, false, EPI_F32, CTA2>(a, stream);
       case EPI_PATCH: return launch_gemm<BLOCK_N, false, false, EPI_PATCH, CTA2>(a, stream);
     }
