@@ -1,5 +1,7 @@
 """Groups an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel name: launches, total us, share.
-usage: python tools/ncu_launch_summary.py launches.csv > profiles/rNN_ncu_launches_step.txt"""
+usage: python tools/ncu_launch_summary.py launches.csv [--last-step MARKER] > profiles/rNN_ncu_launches_step.txt
+--last-step adamw keeps only the launches of the last complete training step: those after the second-to-last launch whose
+name contains MARKER, up to and including the last one (every step ends with exactly one AdamW launch)."""
 import csv
 import re
 import sys
@@ -8,10 +10,14 @@ from collections import OrderedDict
 rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 5]
 hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 col = {h: i for i, h in enumerate(rows[hdr])}
+body = [r for r in rows[hdr + 1:] if r[col["Metric Name"]] == "gpu__time_duration.sum"]
+if "--last-step" in sys.argv:
+    marker = sys.argv[sys.argv.index("--last-step") + 1]
+    marks = [i for i, r in enumerate(body) if marker in r[col["Kernel Name"]]]
+    if len(marks) >= 2:
+        body = body[marks[-2] + 1:marks[-1] + 1]
 agg = OrderedDict()
-for r in rows[hdr + 1:]:
-    if r[col["Metric Name"]] != "gpu__time_duration.sum":
-        continue
+for r in body:
     name = r[col["Kernel Name"]]
     name = re.sub(r"\(anonymous namespace\)::|<unnamed>::|void ", "", name)
     name = re.sub(r"\(.*$", "", name)
