@@ -224,7 +224,7 @@ __host__ __device__ inline uint32_t ring_header_bytes(int dim, int warps) {
 }
 
 template <int VPL, bool EXACT>
-__global__ void __launch_bounds__((VPL <= 4 ? RING_MAX_WARPS : VPL <= 6 ? 12 : 10) * 32, 1)
+__global__ void __launch_bounds__((VPL <= 4 ? RING_MAX_WARPS : VPL <= 6 ? 12 : 8) * 32, 1)
 ln_bwd_ring_kernel(const __nv_bfloat16* __restrict__ dy, long long ld_dy, const float* __restrict__ x,
                    long long ld_x, const float* __restrict__ mean, const float* __restrict__ rstd,
                    const float* __restrict__ gamma, const float* __restrict__ g_in,
@@ -381,7 +381,7 @@ inline int ring_env(int which) {
 inline int ring_warps(int dim) {
   const long long budget = 227 * 1024 - 1024;
   const int stages = ring_env(1);
-  int wmax = (dim <= 512 ? RING_MAX_WARPS : dim <= 768 ? 12 : 10);  // the launch bounds of VPL = 6 / 8
+  int wmax = (dim <= 512 ? RING_MAX_WARPS : dim <= 768 ? 12 : 8);  // the launch bounds of VPL = 6 / 8
   if (ring_env(0) > 0 && ring_env(0) < wmax) wmax = ring_env(0);
   for (int w = wmax; w >= 1; --w)
     if ((long long)ring_header_bytes(dim, w) + (long long)w * stages * 10 * dim <= budget) return w;
