@@ -679,18 +679,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       if constexpr (kTmaEpi<EPI, PART_N>) {
         // ---- TMA-staged epilogue: no global loads / stores, no bounds predicates (the tensor maps clip) ----
-        uint8_t* buf0 = stg_base + ew * STG_BYTES;   // [32 rows][64 B], unit u of row r at u ^ ((r >> 1) & 3)
-        uint8_t* buf1 = buf0 + 2048;
+        // x GELU': one [32 rows][128 B] panel, 16-byte chunk u of row r at u ^ (r & 7) (128-byte swizzle);
+        // GELU: two [32 rows][64 B] panels (gelu, gelu'), unit u of row r at u ^ ((r >> 1) & 3) (64-byte swizzle)
+        uint8_t* buf0 = stg_base + ew * STG_BYTES;
+        [[maybe_unused]] uint8_t* buf1 = buf0 + 2048;
         const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
         const int colp = n_blk * BLOCK_N + part * PART_N;
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + part * PART_N;
         if constexpr (EPI == EPI_DGELU) {
-          // aux = gelu'(h) panels of this tile are fetched while the tile's MMAs still run
+          // aux = gelu'(h) of this warp's [32 rows][64 columns] is fetched while the tile's MMAs still run: ONE box of
+          // 128-byte rows (128-byte swizzle: chunk u of row r at u ^ (r & 7)), multiplied in place and stored as one box,
+          // so every row segment that reaches L2 is a whole line (with two 64-byte boxes per row the L2 write hit
+          // rate was exactly 50 %: every line arrived in two halves)
           if (elect_one()) {
-            tma_store_wait_read();   // the previous tile's output panels have left buf0 / buf1
+            tma_store_wait_read();   // the previous tile's output panel has left the buffer
             mbar_arrive_expect_tx(&aux_bar[ew], 4096);
             tma_load_2d(buf0, &tmAux, &aux_bar[ew], colp, row0);
-            tma_load_2d(buf1, &tmAux, &aux_bar[ew], colp + 32, row0);
           }
           __syncwarp();
           mbar_wait(&tmem_full[as], aphase);
@@ -702,28 +706,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld_wait();
           release_acc();
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint8_t* buf = hf ? buf1 : buf0;
-            const uint32_t(&acc)[32] = hf ? acc1 : acc0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              uint4* slot = reinterpret_cast<uint4*>(buf + stg_b16(lane, u));
-              const uint4 du = *slot;
-              const float2 d0 = unpack_bf16x2(du.x), d1 = unpack_bf16x2(du.y), d2 = unpack_bf16x2(du.z), d3 = unpack_bf16x2(du.w);
-              const uint32_t* a = acc + u * 8;
-              uint4 o;
-              o.x = pack_bf16x2(__uint_as_float(a[0]) * (d0.x * rs), __uint_as_float(a[1]) * (d0.y * rs));
-              o.y = pack_bf16x2(__uint_as_float(a[2]) * (d1.x * rs), __uint_as_float(a[3]) * (d1.y * rs));
-              o.z = pack_bf16x2(__uint_as_float(a[4]) * (d2.x * rs), __uint_as_float(a[5]) * (d2.y * rs));
-              o.w = pack_bf16x2(__uint_as_float(a[6]) * (d3.x * rs), __uint_as_float(a[7]) * (d3.y * rs));
-              *slot = o;   // in place: every thread rewrites exactly the 64 bytes it read
-            }
+          for (int u = 0; u < 8; ++u) {
+            uint4* slot = reinterpret_cast<uint4*>(buf0 + lane * 128 + ((u ^ (lane & 7)) << 4));
+            const uint4 du = *slot;
+            const float2 d0 = unpack_bf16x2(du.x), d1 = unpack_bf16x2(du.y), d2 = unpack_bf16x2(du.z), d3 = unpack_bf16x2(du.w);
+            const uint32_t* a = (u < 4 ? acc0 : acc1) + (u & 3) * 8;
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(a[0]) * (d0.x * rs), __uint_as_float(a[1]) * (d0.y * rs));
+            o.y = pack_bf16x2(__uint_as_float(a[2]) * (d1.x * rs), __uint_as_float(a[3]) * (d1.y * rs));
+            o.z = pack_bf16x2(__uint_as_float(a[4]) * (d2.x * rs), __uint_as_float(a[5]) * (d2.y * rs));
+            o.w = pack_bf16x2(__uint_as_float(a[6]) * (d3.x * rs), __uint_as_float(a[7]) * (d3.y * rs));
+            *slot = o;   // in place: every thread rewrites exactly the 128 bytes it read
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (elect_one()) {
             tma_store_2d(&tmOut, buf0, colp, row0);
-            tma_store_2d(&tmOut, buf1, colp + 32, row0);
             tma_store_commit();
           }
           __syncwarp();
@@ -954,9 +952,15 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
     if (rc) return rc;
   }
   if (kTmaEpi<EPI, BLOCK_N / (EW / 4)>) {
-    rc = vitk_make_tmap_2d_sw64(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 32, 32);
-    if (rc) return rc;
-    rc = vitk_make_tmap_2d_sw64(&tmAux, a->aux, 2, a->N, a->M, a->ld_aux, 32, 32);
+    if (EPI == EPI_DGELU) {   // [32 rows][128 B] boxes, 128-byte swizzle
+      rc = vitk_make_tmap_2d(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 64, 32);
+      if (rc) return rc;
+      rc = vitk_make_tmap_2d(&tmAux, a->aux, 2, a->N, a->M, a->ld_aux, 64, 32);
+    } else {                  // [32 rows][64 B] boxes, 64-byte swizzle
+      rc = vitk_make_tmap_2d_sw64(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 32, 32);
+      if (rc) return rc;
+      rc = vitk_make_tmap_2d_sw64(&tmAux, a->aux, 2, a->N, a->M, a->ld_aux, 32, 32);
+    }
     if (rc) return rc;
   }
 
