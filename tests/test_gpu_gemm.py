@@ -44,16 +44,19 @@ def test_fprop_block_n_forced(cuda_device, block_n):
     assert rel_err(out, a.float() @ w.float().t()) < F32_TOL
 
 
-def test_fprop_bf16_rowscale(cuda_device):
+# bf16 outputs with 16-byte aligned rows leave through TMA as [32 rows][128 B] boxes (N = 200 / 1000: the last box of a row
+# is clipped by the tensor map; M = 5000: several tiles per CTA)
+@pytest.mark.parametrize("M,N,K", [(394, 768, 768), (5000, 2304, 768), (300, 200, 256), (2049, 1000, 512), (128, 64, 64)])
+def test_fprop_bf16_rowscale(cuda_device, M, N, K):
     from vision_transformers_torch_xla_b200 import _lib as L
-    M, N, K = 394, 768, 768
     a = _mk((M, K), cuda_device, seed=1).bfloat16()
     w = _mk((N, K), cuda_device, 0.05, seed=2).bfloat16()
     bias = _mk((N,), cuda_device, seed=3)
-    rs = torch.tensor([0.0, 1.25], device=cuda_device)
-    out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    groups = (M + 196) // 197
+    rs = torch.tensor([0.0, 1.25, 1.0], device=cuda_device).repeat((groups + 2) // 3)[:groups].contiguous()
+    out = torch.full((M, N), float("nan"), device=cuda_device, dtype=torch.bfloat16)
     L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_BF16, bias=bias, rowscale=rs, rows_per_group=197)
-    ref = (a.float() @ w.float().t() + bias) * rs.repeat_interleave(197)[:, None]
+    ref = (a.float() @ w.float().t() + bias) * rs.repeat_interleave(197)[:M, None]
     assert elem_err(out.float(), ref) < BF16_TOL
 
 

@@ -73,12 +73,17 @@ constexpr bool kTmaEpi = (EPI == EPI_GELU || EPI == EPI_DGELU) && PART_N == 64;
 // HBM-bound projection (K = 768: 123 -> 81 us per launch inside the training step) and a loss for the MMA-bound fc2
 // (K = 3072: 183 -> 197 us), so the dispatcher picks this variant (internal epilogue code EPI_RESID_TMA) for K <= 1536.
 constexpr int EPI_RESID_TMA = 100;
+// bf16 epilogue through TMA (internal code): pairs of 32-column chunks leave as ONE [32 rows][128 B] box, so that every
+// row segment reaching L2 is a whole line and the epilogue issues no global stores; taken when the output rows are
+// 16-byte aligned and the warp's share of the tile is a multiple of 64 columns
+constexpr int EPI_BF16_TMA = 101;
 constexpr int kResidTmaMaxK = 1536;
 template <int EPI, int BLOCK_N, bool CTA2>
 constexpr bool kTmaResid = (EPI == EPI_RESID_TMA);
 constexpr int kResidBufs = 3;
 template <int EPI, int BLOCK_N, bool CTA2>
 constexpr uint32_t kStgBytesFor = kTmaResid<EPI, BLOCK_N, CTA2> ? kResidBufs * 4096u : kStgBytes<EPI>;
+static_assert(kStgBytes<EPI_BF16_TMA> == 4096u, "one [32][128 B] panel per epilogue warp");
 
 // CTA2: a pair of CTAs (cluster of 2, one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2.
 // Each CTA stages its own 128 rows of A but only HALF of the B tile, so per-SM operand traffic from L2 (and smem
@@ -398,6 +403,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr uint32_t STG_BYTES = kStgBytesFor<EPI, BLOCK_N, CTA2>;
   using Cfg = TileCfg<BLOCK_N, EW, STG_BYTES, CTA2>;
   constexpr bool TMA_RESID = kTmaResid<EPI, BLOCK_N, CTA2>;
+  constexpr bool TMA_BF16 = (EPI == EPI_BF16_TMA);
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool ROLES_HI = true;
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
@@ -674,7 +680,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       float rs = 1.0f;
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID || EPI == EPI_RESID_TMA || EPI == EPI_DGELU) {
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_TMA || EPI == EPI_RESID || EPI == EPI_RESID_TMA || EPI == EPI_DGELU) {
         if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
       }
       if constexpr (kTmaEpi<EPI, PART_N>) {
@@ -773,6 +779,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             __syncwarp();
           }
+        }
+      } else if constexpr (TMA_BF16) {
+        static_assert(PART_N % 64 == 0, "128-byte boxes are 64 bf16 columns wide");
+        const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
+        uint8_t* buf = stg_base + ew * STG_BYTES;   // [32 rows][128 B], 16-byte chunk u of row r at u ^ (r & 7)
+        mbar_wait(&tmem_full[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < PART_N / 64; ++c) {
+          const int col_in_tile = part * PART_N + c * 64;
+          const int col0 = n_blk * BLOCK_N + col_in_tile;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + col_in_tile;
+          uint32_t acc0[32], acc1[32];
+          tmem_ld_32x32(taddr, acc0);
+          tmem_ld_32x32(taddr + 32, acc1);
+          tmem_ld_wait();
+          if (c + 1 == PART_N / 64) release_acc();
+          uint4 o[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t* a = (u < 4 ? acc0 : acc1) + (u & 3) * 8;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (p.bias != nullptr && col0 + u * 8 < p.N) {
+              b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + u * 8));
+              b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + u * 8 + 4));
+            }
+            o[u].x = pack_bf16x2((__uint_as_float(a[0]) + b0.x) * rs, (__uint_as_float(a[1]) + b0.y) * rs);
+            o[u].y = pack_bf16x2((__uint_as_float(a[2]) + b0.z) * rs, (__uint_as_float(a[3]) + b0.w) * rs);
+            o[u].z = pack_bf16x2((__uint_as_float(a[4]) + b1.x) * rs, (__uint_as_float(a[5]) + b1.y) * rs);
+            o[u].w = pack_bf16x2((__uint_as_float(a[6]) + b1.z) * rs, (__uint_as_float(a[7]) + b1.w) * rs);
+          }
+          // the previous box must have been read by the TMA unit before the panel is overwritten
+          if (elect_one()) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(buf + lane * 128 + ((u ^ (lane & 7)) << 4)) = o[u];
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d(&tmOut, buf, col0, row0);
+            tma_store_commit();
+          }
+          __syncwarp();
         }
       } else if constexpr (TMA_RESID) {
         static_assert(W == 32, "residual panels are 32 columns wide");
@@ -882,7 +931,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (!released) release_acc();
       if (++as == ACC_STAGES) { as = 0; aphase ^= 1; }
     }
-    if constexpr (kTmaEpi<EPI, PART_N> || TMA_RESID) {
+    if constexpr (kTmaEpi<EPI, PART_N> || TMA_RESID || TMA_BF16) {
       if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the bulk stores
       __syncwarp();
     }
@@ -926,6 +975,11 @@ inline bool resid_tma_ok(const vitk_gemm_args* a) {
          a->ld_resid % 4 == 0 && a->N % 4 == 0;
 }
 
+inline bool bf16_tma_ok(const vitk_gemm_args* a) {
+  static const bool enabled = [] { const char* e = getenv("VITK_GEMM_BF16_TMA"); return !(e != nullptr && e[0] == '0'); }();
+  return enabled && ((uintptr_t)a->out & 15) == 0 && a->ld_out % 8 == 0 && a->N % 8 == 0;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool CTA2>
 int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   // 16 epilogue warps for the GELU epilogues (~20 instructions per element); 8 elsewhere.  With BLOCK_N = 192 and
@@ -945,6 +999,10 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   CUtensorMap tmOut, tmAux;
   memset(&tmOut, 0, sizeof(tmOut));
   memset(&tmAux, 0, sizeof(tmAux));
+  if (EPI == EPI_BF16_TMA) {
+    rc = vitk_make_tmap_2d(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 64, 32);
+    if (rc) return rc;
+  }
   if (kTmaResid<EPI, BLOCK_N, CTA2>) {
     rc = vitk_make_tmap_2d(&tmOut, a->out, 4, a->N, a->M, a->ld_out, 32, 32);
     if (rc) return rc;
@@ -1023,7 +1081,11 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
   }
   if (!amn && !bmn) {
     switch (a->epilogue) {
-      case EPI_BF16:  return launch_gemm<BLOCK_N, false, false, EPI_BF16, CTA2>(a, stream);
+      case EPI_BF16:
+        if constexpr (BLOCK_N % 128 == 0) {
+          if (bf16_tma_ok(a)) return launch_gemm<BLOCK_N, false, false, EPI_BF16_TMA, CTA2>(a, stream);
+        }
+        return launch_gemm<BLOCK_N, false, false, EPI_BF16, CTA2>(a, stream);
       case EPI_GELU:  return launch_gemm<BLOCK_N, false, false, EPI_GELU, CTA2>(a, stream);
       case EPI_RESID:
         if constexpr (CTA2 || BLOCK_N < 256) {
@@ -1035,7 +1097,11 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
     }
   } else if (!amn && bmn) {
     switch (a->epilogue) {
-      case EPI_BF16:  return launch_gemm<BLOCK_N, false, true, EPI_BF16, CTA2>(a, stream);
+      case EPI_BF16:
+        if constexpr (BLOCK_N % 128 == 0) {
+          if (bf16_tma_ok(a)) return launch_gemm<BLOCK_N, false, true, EPI_BF16_TMA, CTA2>(a, stream);
+        }
+        return launch_gemm<BLOCK_N, false, true, EPI_BF16, CTA2>(a, stream);
       case EPI_DGELU: return launch_gemm<BLOCK_N, false, true, EPI_DGELU, CTA2>(a, stream);
       case EPI_F32:   return launch_gemm<BLOCK_N, false, true, EPI_F32, CTA2>(a, stream);
     }
