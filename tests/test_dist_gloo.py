@@ -54,12 +54,16 @@ def _worker(rank, world, port, q):
         # 3) hooks fire in backward order; the optimizer's pre-step hook waits; grads are SUMMED (mean is in grad_scale).
         #    "block": one asynchronous all-reduce per bucket; "step" (default): one all-reduce of the flat buffer at step().
         assert dp.sync_mode == "step"
-        for mode, in_flight in (("block", 4), ("step", 0)):
+        #    "tail" (VITK_DP_SYNC=tail:1): blocks.1 .. head in one asynchronous all-reduce fired when blocks.1 is ready,
+        #    the rest (embed, blocks.0) at step().
+        for mode, in_flight in (("block", 4), ("step", 0), ("tail", 1)):
             dp.sync_mode = mode
+            if mode == "tail":
+                dp._tail_tag, dp._tail_lo = "blocks.1.", r["blocks.1."][0]
             st.grad.fill_(float(rank + 1))
             for tag in ("head", "blocks.1.", "blocks.0.", "embed"):
                 st.fire_grad_ready(tag)
-            assert len(dp._works) == in_flight and dp._pending == (mode == "step")
+            assert len(dp._works) == in_flight and dp._pending == (mode in ("step", "tail"))
             opt.step()
             assert len(dp._works) == 0 and not dp._pending
             assert torch.equal(st.grad, torch.full_like(st.grad, float(sum(range(1, world + 1)))))

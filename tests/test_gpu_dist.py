@@ -12,9 +12,9 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, sync):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
-                      LOCAL_RANK=str(rank))
+                      LOCAL_RANK=str(rank), VITK_DP_SYNC=sync)
     try:
         from vision_transformers_torch_xla_b200 import optim_factory, utils
         from vision_transformers_torch_xla_b200.losses import SoftTargetCrossEntropy
@@ -73,7 +73,8 @@ def _worker(rank, world, port, q):
             dist.destroy_process_group()
 
 
-def test_data_parallel_two_gpus():
+@pytest.mark.parametrize("sync", ["step", "block", "tail:1"])
+def test_data_parallel_two_gpus(sync):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     s = socket.socket()
@@ -82,7 +83,7 @@ def test_data_parallel_two_gpus():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, sync)) for r in range(2)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=300) for _ in procs)
