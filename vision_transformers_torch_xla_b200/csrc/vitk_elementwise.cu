@@ -353,10 +353,12 @@ struct AdamwHyper {
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, float* __restrict__ ema, long long n,
-             const uint8_t* __restrict__ chunk_group, int chunk, const AdamwHyper h) {
+             const uint8_t* __restrict__ chunk_group, int chunk, const __grid_constant__ AdamwHyper h) {
+  // (__grid_constant__: h.lr[grp] is read straight from the parameter bank; without it the dynamic index makes the
+  //  compiler copy both arrays to local memory in every thread)
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
-  const int grp = chunk_group ? chunk_group[i4 / chunk] : 0;
+  const int grp = chunk_group ? chunk_group[(unsigned long long)i4 < 0xffffffffull ? (unsigned)i4 / (unsigned)chunk : i4 / chunk] : 0;
   const float lr = h.lr[grp], wd = h.wd[grp];
   float4 pv = *reinterpret_cast<float4*>(p + i4);
   float4 gv = *reinterpret_cast<float4*>(g + i4);
