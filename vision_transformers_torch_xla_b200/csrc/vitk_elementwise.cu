@@ -125,25 +125,24 @@ __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
+// one block per token row (no per-thread 64-bit index arithmetic: the flat-index version spent ~300 instructions
+// per 16-byte store on three 64-bit divisions)
 __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, float* __restrict__ g, int B, int N,
                                 int D, int prefix, int mode) {
-  const int dv = D / 4;
-  const long long total = (long long)B * N * dv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c = (int)(idx % dv);
-  const int t = (int)((idx / dv) % N);
-  const int b = (int)(idx / ((long long)dv * N));
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool live = (mode == 1) ? (t == 0) : (t >= prefix);
-  if (live) {
-    r = __ldg(reinterpret_cast<const float4*>(dpooled + (long long)b * D + c * 4));
-    if (mode == 0) {
-      const float inv = 1.0f / (float)(N - prefix);
+  const unsigned row = blockIdx.x;
+  const unsigned b = row / (unsigned)N, t = row - b * (unsigned)N;
+  const bool live = (mode == 1) ? (t == 0) : ((int)t >= prefix);
+  const float inv = (mode == 0) ? 1.0f / (float)(N - prefix) : 1.0f;
+  const float4* src = reinterpret_cast<const float4*>(dpooled + (long long)b * D);
+  float4* dst = reinterpret_cast<float4*>(g + (long long)row * D);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      r = __ldg(src + c);
       r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
     }
+    dst[c] = r;
   }
-  *reinterpret_cast<float4*>(g + ((long long)b * N + t) * D + c * 4) = r;
 }
 
 // out[c] += sum_r x[r, c].  block (32, 8): 32 lanes x 8 columns each = 256 columns, 8 row lanes.
@@ -560,8 +559,9 @@ extern "C" int vitk_pool_bwd(const float* dpooled, float* g, int32_t B, int32_t 
                              int32_t mode, void* stream) {
   VITK_REQUIRE(B > 0 && N > prefix && D > 0 && D % 4 == 0, VITK_ERR_SHAPE, "pool_bwd: bad shape");
   VITK_REQUIRE(mode == 0 || mode == 1, VITK_ERR_UNSUPPORTED, "pool_bwd: mode %d (0=avg, 1=token)", mode);
-  const long long total = (long long)B * N * (D / 4);
-  pool_bwd_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dpooled, g, B, N, D, prefix, mode);
+  VITK_REQUIRE((long long)B * N < (1LL << 31), VITK_ERR_SHAPE, "pool_bwd: B * N must be below 2^31");
+  const int threads = (D / 4 + 31) / 32 * 32;   // one float4 per thread up to D = 1024
+  pool_bwd_kernel<<<(unsigned)((long long)B * N), threads < 256 ? threads : 256, 0, (cudaStream_t)stream>>>(dpooled, g, B, N, D, prefix, mode);
   return vitk_check_launch("pool_bwd");
 }
 
