@@ -14,18 +14,22 @@ using namespace vitk;
 // ------------------------------------------------------------------------------------------------
 // patchify: fp32 NCHW -> bf16 [B*P, C*ps*ps], column order (c, ph, pw)
 // ------------------------------------------------------------------------------------------------
+// IDX: unsigned when the flat index fits 32 bits (the usual case) - the 64-bit divisions of the long long version are
+// several hundred instructions per 32-byte load
+template <typename IDX>
 __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out,
                                 int B, int C, int H, int W, int ps) {
   const long long total = (long long)B * C * H * (W / 8);
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int wv = W / 8;
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total) return;
+  const IDX idx = (IDX)idx64;
+  const IDX wv = (IDX)(W / 8);
   const int xv = (int)(idx % wv);
-  long long t = idx / wv;
-  const int y = (int)(t % H);
-  t /= H;
-  const int c = (int)(t % C);
-  const int b = (int)(t / C);
+  IDX t = idx / wv;
+  const int y = (int)(t % (IDX)H);
+  t /= (IDX)H;
+  const int c = (int)(t % (IDX)C);
+  const int b = (int)(t / (IDX)C);
   const float4* src = reinterpret_cast<const float4*>(img + (((long long)b * C + c) * H + y) * W + xv * 8);
   const float4 a0 = __ldg(src), a1 = __ldg(src + 1);
   const int gw = W / ps, gh = H / ps;
@@ -330,7 +334,9 @@ __global__ void rowscale_cast_kernel(const float* __restrict__ in, const float* 
                                      long long elems_per_group, __nv_bfloat16* __restrict__ out, long long n) {
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
-  const float s = rowscale ? __ldg(rowscale + i4 / elems_per_group) : 1.0f;
+  const float s = rowscale ? __ldg(rowscale + ((n < (1LL << 32) && elems_per_group < (1LL << 32)) ? (long long)((unsigned)i4 / (unsigned)elems_per_group)
+                                                                                                  : i4 / elems_per_group))
+                           : 1.0f;
   const float4 v = *reinterpret_cast<const float4*>(in + i4);
   uint2 o;
   o.x = pack_bf16x2(v.x * s, v.y * s);
@@ -523,7 +529,10 @@ extern "C" int vitk_patchify(const float* img, void* patches_bf16, int32_t B, in
                "patchify: H=%d W=%d must be multiples of ps=%d and ps a multiple of 8", H, W, ps);
   VITK_REQUIRE(((uintptr_t)img & 15) == 0 && ((uintptr_t)patches_bf16 & 15) == 0, VITK_ERR_ALIGN, "patchify: unaligned");
   const long long total = (long long)B * C * H * (W / 8);
-  patchify_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)patches_bf16, B, C, H, W, ps);
+  if (total < (1LL << 32))
+    patchify_kernel<unsigned><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)patches_bf16, B, C, H, W, ps);
+  else
+    patchify_kernel<long long><<<blocks_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16*)patches_bf16, B, C, H, W, ps);
   return vitk_check_launch("patchify");
 }
 
