@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 1
+#define VITK_ABI_VERSION 2
 
 enum vitk_status {
   VITK_STATUS_OK = 0,
@@ -39,6 +39,9 @@ int vitk_abi_version(void);
 const char* vitk_last_error(void);
 /* Compile-time target of the device code in this library, e.g. "sm_100a". */
 const char* vitk_arch(void);
+/* First 16 hex digits of the sha256 over the sources the library was built from (csrc/Makefile); a binding
+ * recomputes it over the sources next to the library and refuses a stale binary. */
+const char* vitk_build_id(void);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM — tcgen05/TMEM bf16 GEMM with fused epilogues.   D[M,N] = opA(A)[M,K] * opB(B)[N,K]^T
@@ -119,14 +122,23 @@ int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
  * patchify: fp32 NCHW image -> bf16 [B*P, C*ps*ps] rows in (c, ph, pw) order == proj.weight.view(D,-1)
  * prefix_rows: x[b, j, :] = prefix_tok[j, :] + pos[j, :] for j < prefix (cls / dist tokens)
  * embed_bwd: from g fp32 [B, N, D]: gp_bf16 [B*P, D] (patch rows), dpos[N, D] += sum_b g,
- *            dprefix[prefix, D] += sum_b g[b, j, :]
+ *            dprefix0[D] += sum_b g[b, 0, :] (cls_token), dprefix1[D] += sum_b g[b, 1, :] (dist_token, prefix == 2);
+ *            either may be NULL (frozen token)
  * ---------------------------------------------------------------------------------------------- */
 int vitk_patchify(const float* img, void* patches_bf16, int32_t B, int32_t C, int32_t H, int32_t W,
                   int32_t ps, void* stream);
 int vitk_prefix_rows(float* x, const float* prefix_tok, const float* pos, int32_t B, int32_t N,
                      int32_t D, int32_t prefix, void* stream);
-int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix, int32_t B, int32_t N,
-                   int32_t D, int32_t prefix, void* stream);
+int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix0, float* dprefix1, int32_t B,
+                   int32_t N, int32_t D, int32_t prefix, void* stream);
+
+/* DropPath (timm drop_path as called by Block, vision_transformer.py:160-161, 172-178): all per-sample keep masks of one
+ * forward pass in one launch.  rs fp32 [rows, B]: rs[r, b] = Bernoulli(1 - drop_probs[r]) / (1 - drop_probs[r]).
+ * drop_probs is a HOST array of `rows` <= 128 probabilities (copied by value into the launch), rows ordered as the
+ * reference draws them (block 0 attention branch, block 0 MLP branch, block 1 ...).  Philox4x32-10 keyed by
+ * (seed, offset): same (seed, offset) -> same masks. */
+int vitk_droppath_masks(float* rs, const float* drop_probs, int32_t rows, int32_t B, uint64_t seed,
+                        uint64_t offset, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pooling (global_pool_nlc: vision_transformer.py:419-441).  mode 0 = 'avg' over non-prefix
@@ -154,7 +166,9 @@ int vitk_ce_fwd_bwd(const float* logits, const float* soft_targets, const int64_
                     float smoothing, const float* teacher_logits, float kd_alpha, float kd_temp,
                     float* loss, float* dlogits, float* row_loss_scratch, int32_t B, int32_t C,
                     void* stream);
-/* out_bf16[i] = in_f32[i] * scale_dev[0]   (applies the upstream grad of the loss, no host sync) */
+/* x[i] *= scale_dev[0] in place (the upstream gradient of the loss applied to dlogits, no host sync) */
+int vitk_scale_f32(float* x, const float* scale_dev, int64_t n, void* stream);
+/* out_bf16[i] = in_f32[i] * scale_dev[0] */
 int vitk_scale_cast_bf16(const float* in, const float* scale_dev, void* out_bf16, int64_t n,
                          void* stream);
 /* out_bf16[i] = in_f32[i] * rowscale[i / elems_per_group]  (DropPath scale on a gradient stream; rowscale may be NULL) */
@@ -167,21 +181,28 @@ int vitk_cast_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
  * Fused multi-tensor AdamW over flat buffers (torch.optim.AdamW semantics, reference
  * optim_factory.py:248-249; stepped at engine.py:185/271).  All parameters live in one flat fp32
  * buffer; `chunk_group[i]` gives the param-group id of elements [i*chunk, (i+1)*chunk).
- *   g' = g * grad_scale;  p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2
+ *   g' = g * grad_scale * (grad_scale_dev ? grad_scale_dev[0] : 1)
+ *   p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2
  *   p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps);   shadow_bf16 = bf16(p);  ema = d ema + (1-d) p
  * lr[] / wd[] are HOST arrays of length num_groups (copied by value into the launch).
+ * g_bf16 (optional): read the gradient from this bf16 copy instead of g (the copy the data-parallel layer all-reduces
+ * at half the bytes); g is then only zeroed (zero_grad).  grad_scale_dev (optional): device scalar multiplied into the
+ * gradient, e.g. the clip coefficient vitk_clip_coef left on the device.
  * ---------------------------------------------------------------------------------------------- */
-int vitk_adamw_flat(float* p, float* g, float* m, float* v, void* shadow_bf16, float* ema,
-                    int64_t n, const uint8_t* chunk_group, int32_t chunk, int32_t num_groups,
-                    const float* lr, const float* wd, float beta1, float beta2, float eps,
-                    int64_t step, float grad_scale, float ema_decay, int32_t zero_grad,
-                    void* stream);
+int vitk_adamw_flat(float* p, float* g, const void* g_bf16, const float* grad_scale_dev, float* m, float* v,
+                    void* shadow_bf16, float* ema, int64_t n, const uint8_t* chunk_group, int32_t chunk,
+                    int32_t num_groups, const float* lr, const float* wd, float beta1, float beta2, float eps,
+                    int64_t step, float grad_scale, float ema_decay, int32_t zero_grad, void* stream);
 /* Tuning aid: when non-NULL, the first CTA of the attention kernels stamps clock64() at its phase boundaries into
  * this device buffer of >= 32 int64 (tools/attn_trace.py prints the timeline).  NULL (default) disables it. */
 void vitk_debug_set_trace(long long* device_buf);
 
-/* out[0] += sum_i x[i]^2 (for clip_grad_norm_) */
+/* Gradient clipping (engine.py:175-177; torch.nn.utils.clip_grad_norm_) without a host sync or an extra pass:
+ * vitk_sumsq / vitk_sumsq_bf16: out[0] += sum_i x[i]^2;  vitk_clip_coef: norm[0] = sqrt(sumsq[0]) * grad_scale (optional output),
+ * coef[0] = min(1, max_norm / (norm + 1e-6)), which vitk_adamw_flat multiplies in through grad_scale_dev. */
 int vitk_sumsq(const float* x, int64_t n, float* out, void* stream);
+int vitk_sumsq_bf16(const void* x_bf16, int64_t n, float* out, void* stream);
+int vitk_clip_coef(const float* sumsq, float grad_scale, float max_norm, float* coef, float* norm, void* stream);
 
 /* Mixup / CutMix, batch mode, in place on fp32 NCHW images (image b mixes with image B-1-b); replaces
  * timm.data.Mixup._mix_batch as constructed at /root/reference/main.py:622-629 and applied at engine.py:259-262.

@@ -5,14 +5,24 @@ A plain eager-PyTorch fp32 restatement of the reference's algorithm
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this package; the product
 (``vision_transformers_torch_xla_b200``) never does and has no CPU fallback.
 
-PARITY UNPINNED.  The reference cannot be imported offline: its leaf arithmetic (Attention, Mlp,
-PatchEmbed, LayerNorm, DropPath, SoftTargetCrossEntropy, ...) lives in the un-vendored pip package
-``timm==1.0.15`` (/root/reference/requirements.txt:13, resolved through
-/root/reference/models/_compat.py:27-172), and the reference's own tests (test_kd.py) assert no
-numerical values.  This file therefore restates timm 1.0.15's published semantics (SURVEY.md
-Appendix A.2) and is pinned only by structural known-answers (parameter counts, state_dict layout,
-shapes, loss at init, closed-form schedules — tests/test_oracle.py) and by an independent
-cross-implementation check against ``torchvision.models.VisionTransformer`` on shared weights.
+PARITY PIN.  The reference cannot be imported as a package offline (timm / torch_xla / tensorflow are
+absent), and its own tests (test_kd.py) assert no numerical values.  It is pinned in two halves:
+
+* IN-TREE HALF — PINNED TO THE REFERENCE'S OWN CODE: everything the reference itself defines on the hot
+  path (LayerScale, Block, global_pool_nlc, VisionTransformer ctor wiring / init order / _pos_embed / forward,
+  the vit_* / my_vit_* / deit_* entrypoints, VisionTransformerDistilled, cosine_scheduler,
+  get_parameter_groups / create_optimizer, the closure-local DistillationLoss / StudentWithDistillation,
+  engine.train_one_epoch's eager branch with its schedule write, engine.evaluate) is ast-extracted from
+  /root/reference and EXECUTED by tests/golden/make_ref_fixtures.py; tests/test_ref_fixtures.py holds this
+  file to those outputs (logits, per-block activations, every gradient, seeded-init checksums, schedules,
+  group membership, loss values, 10-step engine runs) at <= 1e-6.
+* LEAF HALF — UNPINNED: the leaf arithmetic (Attention, Mlp, PatchEmbed, LayerNorm, DropPath,
+  SoftTargetCrossEntropy, Mixup, accuracy) lives in the un-vendored pip package ``timm==1.0.15``
+  (/root/reference/requirements.txt:13, resolved through /root/reference/models/_compat.py:27-172) whose
+  source is not in the container.  These few classes restate timm 1.0.15's published semantics (SURVEY.md
+  Appendix A.2) and are cross-checked against two independent implementations of the same architecture
+  (``torchvision.models.VisionTransformer`` and ``transformers.ViTForImageClassification`` on shared
+  weights, tests/test_oracle.py).
 
 Each class/function cites the reference lines it follows.
 """
@@ -405,13 +415,21 @@ class StudentWithDistillation(nn.Module):
 # --------------------------------------------------------------------------------------------
 # optimizer groups, schedules, train step (optim_factory.py, utils/__init__.py, engine.py)
 # --------------------------------------------------------------------------------------------
-def get_parameter_groups(model: nn.Module, weight_decay: float = 1e-5, skip_list: Iterable[str] = ()) -> List[dict]:
-    """/root/reference/optim_factory.py:155-195 (non-TPU shape rule), lr_scale = 1."""
+def get_parameter_groups(model: nn.Module, weight_decay: float = 1e-5, skip_list: Iterable[str] = (),
+                         tpu_name_rule: bool = False) -> List[dict]:
+    """/root/reference/optim_factory.py:155-195 (non-TPU shape rule), lr_scale = 1.  ``tpu_name_rule`` selects the
+    name-only rule the reference uses when ``PJRT_DEVICE=TPU`` (:104-106): the two differ
+    only for 1-D parameters whose name carries neither ``.bias`` nor ``norm``/``bn`` (LayerScale ``gamma``)."""
     groups: Dict[str, dict] = {}
     for name, param in model.named_parameters():
         if not param.requires_grad:
             continue
-        if len(param.shape) == 1 or name.endswith(".bias") or name in skip_list:
+        if tpu_name_rule:
+            no_decay = (name.endswith(".bias") or name.endswith(".weight") and ("norm" in name.lower() or "bn" in name.lower())
+                        or name in skip_list)
+        else:
+            no_decay = len(param.shape) == 1 or name.endswith(".bias") or name in skip_list
+        if no_decay:
             group_name, this_wd = "no_decay", 0.0
         else:
             group_name, this_wd = "decay", weight_decay
@@ -477,7 +495,7 @@ def train_one_epoch(model, criterion, data_loader, optimizer, epoch: int = 0, st
     """Eager branch of /root/reference/engine.py:19-333 without logging/EMA/mixup (host-side, out of scope)."""
     model.train(True)
     optimizer.zero_grad()
-    losses = []
+    losses, lrs = [], []
     for data_iter_step, (samples, targets) in enumerate(data_loader):
         step = data_iter_step // update_freq
         if num_training_steps_per_epoch is not None and step >= num_training_steps_per_epoch:
@@ -488,7 +506,38 @@ def train_one_epoch(model, criterion, data_loader, optimizer, epoch: int = 0, st
         loss, _ = train_step(model, criterion, optimizer, samples, targets, update_freq,
                              do_step=(data_iter_step + 1) % update_freq == 0)
         losses.append(float(loss))
-    return {"loss": float(np.mean(losses)) if losses else float("nan"), "lr": optimizer.param_groups[0]["lr"]}
+        lrs.append(optimizer.param_groups[0]["lr"])   # engine.py:299-300: the lr meter is fed every logged iteration
+    return {"loss": float(np.mean(losses)) if losses else float("nan"), "lr": float(np.mean(lrs)) if lrs else float("nan"),
+            "losses": losses}
+
+
+def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1,)):
+    """timm.utils.accuracy (1.0.15): top-k precision in percent."""
+    maxk = min(max(topk), output.size()[1])
+    batch_size = target.size(0)
+    _, pred = output.topk(maxk, 1, True, True)
+    pred = pred.t()
+    correct = pred.eq(target.reshape(1, -1).expand_as(pred))
+    return [correct[:min(k, maxk)].reshape(-1).float().sum(0) * 100.0 / batch_size for k in topk]
+
+
+@torch.no_grad()
+def evaluate(data_loader, model) -> Dict[str, float]:
+    """/root/reference/engine.py:339-430 without the TPU plumbing: CrossEntropyLoss + top-1 / top-5 meters; the loss
+    meter averages per batch (``update(loss=...)`` with n=1), the accuracy meters per sample (n=batch_size)."""
+    criterion = nn.CrossEntropyLoss()
+    model.eval()
+    tot = {"loss": [0.0, 0], "acc1": [0.0, 0], "acc5": [0.0, 0]}
+    for batch in data_loader:
+        images, target = batch[0], batch[-1]
+        output = model(images)
+        loss = criterion(output, target)
+        acc1, acc5 = accuracy(output, target, topk=(1, 5))
+        n = images.shape[0]
+        for k, v, w in (("loss", loss.item(), 1), ("acc1", acc1.item(), n), ("acc5", acc5.item(), n)):
+            tot[k][0] += v * w
+            tot[k][1] += w
+    return {k: v[0] / v[1] for k, v in tot.items()}
 
 
 def mixup_soft_targets(labels: torch.Tensor, num_classes: int = 1000, lam: float = 0.7, smoothing: float = 0.1):

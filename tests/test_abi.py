@@ -41,8 +41,24 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_arch(lib):
-    assert lib.vitk_abi_version() == 1
+    from vision_transformers_torch_xla_b200 import _lib
+
+    src = open(HEADER).read()
+    assert lib.vitk_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define VITK_ABI_VERSION (\d+)", src).group(1))
     assert lib.vitk_arch() == b"sm_100a"
+
+
+def test_build_id_ties_the_binary_to_the_sources(lib, monkeypatch, tmp_path):
+    """libvitk.so carries the sha256 of the sources it was built from; load() refuses a binary that does not match the
+    sources next to it (a stale .so shipped with newer sources would otherwise go unnoticed)."""
+    from vision_transformers_torch_xla_b200 import _lib
+
+    lib.vitk_build_id.restype = ctypes.c_char_p
+    assert lib.vitk_build_id().decode() == _lib.source_build_id()
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "source_build_id", lambda: "0" * 16)
+    with pytest.raises(_lib.VitkError, match="stale"):
+        _lib.load()
 
 
 def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
@@ -84,13 +100,16 @@ def test_argument_validation_reports_through_error_slot(lib):
     rc = lib.vitk_gemm_bf16(ctypes.byref(args), None)
     assert rc < 0 and b"empty problem" in lib.vitk_last_error()
     assert lib.vitk_gemm_bf16(None, None) < 0
-    rc = lib.vitk_attn_fwd(None, None, None, 1, 16, 1, 32, ctypes.c_float(1.0), None)
-    assert rc == -6 and b"head_dim" in lib.vitk_last_error()  # VITK_STATUS_UNSUPPORTED
+    rc = lib.vitk_attn_fwd(None, None, None, 1, 16, 1, 72, ctypes.c_float(1.0), None)
+    assert rc == -6 and b"head_dim" in lib.vitk_last_error()  # VITK_STATUS_UNSUPPORTED (wider than the 64-wide head tile)
     rc = lib.vitk_layernorm_fwd(None, 770, None, None, None, 770, None, None, 4, 770, ctypes.c_float(1e-6), None)
     assert rc < 0 and b"multiple of 4" in lib.vitk_last_error()
-    rc = lib.vitk_adamw_flat(None, None, None, None, None, None, 6, None, 64, 1, None, None, ctypes.c_float(0.9),
+    rc = lib.vitk_adamw_flat(None, None, None, None, None, None, None, None, 6, None, 64, 1, None, None, ctypes.c_float(0.9),
                              ctypes.c_float(0.999), ctypes.c_float(1e-8), 1, ctypes.c_float(1.0), ctypes.c_float(0.0), 0, None)
     assert rc < 0
+    probs = (ctypes.c_float * 2)(0.1, 1.5)
+    rc = lib.vitk_droppath_masks(ctypes.c_void_p(16), probs, 2, 4, 0, 0, None)
+    assert rc < 0 and b"drop_probs" in lib.vitk_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -8,8 +8,9 @@ wrapper raises, it never routes to PyTorch kernels or to the CPU oracle.
 from __future__ import annotations
 
 import ctypes
+import hashlib
 import os
-from ctypes import c_double, POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import c_double, POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint8, c_uint64, c_void_p
 from typing import Optional
 
 import torch
@@ -26,7 +27,25 @@ EXPORTED_SYMBOLS = (
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
     "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target", "vitk_colscale_bf16", "vitk_layerscale_grad",
+    "vitk_build_id", "vitk_droppath_masks", "vitk_scale_f32", "vitk_clip_coef", "vitk_sumsq_bf16",
 )
+
+ABI_VERSION = 2
+#: the files whose sha256 csrc/Makefile bakes into the library (same list, same order)
+_BUILD_SOURCES = ("csrc/vitk_host.cu", "csrc/vitk_gemm.cu", "csrc/vitk_attn.cu", "csrc/vitk_norm.cu",
+                  "csrc/vitk_elementwise.cu", "csrc/vitk_common.cuh", "csrc/vitk_internal.h", "../include/vitk.h")
+
+
+def source_build_id() -> Optional[str]:
+    """sha256 (first 16 hex digits) over the kernel sources next to this package, or None if they are not there."""
+    h = hashlib.sha256()
+    for rel in _BUILD_SOURCES:
+        path = os.path.join(_HERE, rel)
+        if not os.path.exists(path):
+            return None
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 class GemmArgs(Structure):
@@ -66,6 +85,18 @@ def load() -> ctypes.CDLL:
     lib.vitk_abi_version.restype = c_int32
     lib.vitk_last_error.restype = c_char_p
     lib.vitk_arch.restype = c_char_p
+    if lib.vitk_abi_version() != ABI_VERSION:
+        raise VitkError(f"{LIB_PATH} has ABI version {lib.vitk_abi_version()}, this binding needs {ABI_VERSION}: rebuild it "
+                        "(`python -c 'import __graft_entry__ as g; g.build()'`)")
+    try:
+        lib.vitk_build_id.restype = c_char_p
+        built = lib.vitk_build_id().decode()
+    except AttributeError:
+        built = "absent"
+    want = source_build_id()
+    if want is not None and built != want and os.environ.get("VITK_ALLOW_STALE_LIB", "0") != "1":
+        raise VitkError(f"{LIB_PATH} is stale: built from sources {built}, the sources on disk hash to {want}. Rebuild it "
+                        "(`python -c 'import __graft_entry__ as g; g.build()'`); set VITK_ALLOW_STALE_LIB=1 to override.")
     lib.vitk_gemm_bf16.argtypes = [POINTER(GemmArgs), c_void_p]
     lib.vitk_layernorm_fwd.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                        c_void_p, c_int64, c_int32, c_float, c_void_p]
@@ -79,7 +110,11 @@ def load() -> ctypes.CDLL:
     lib.vitk_attn_bwd_workspace_bytes.restype = c_int64
     lib.vitk_patchify.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_prefix_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
-    lib.vitk_embed_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
+    lib.vitk_embed_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                   c_void_p]
+    lib.vitk_droppath_masks.argtypes = [c_void_p, POINTER(c_float), c_int32, c_int32, c_uint64, c_uint64, c_void_p]
+    lib.vitk_scale_f32.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.vitk_clip_coef.argtypes = [c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]
     lib.vitk_pool_fwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_pool_bwd.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_colsum_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]
@@ -88,10 +123,12 @@ def load() -> ctypes.CDLL:
     lib.vitk_scale_cast_bf16.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     lib.vitk_rowscale_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]
     lib.vitk_cast_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
-    lib.vitk_adamw_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+    lib.vitk_adamw_flat.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                    c_void_p,
                                     c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_float, c_float, c_float,
                                     c_int64, c_float, c_float, c_int32, c_void_p]
     lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.vitk_sumsq_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.vitk_mixup_batch.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_double, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_void_p]
     lib.vitk_colscale_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p]
@@ -102,7 +139,7 @@ def load() -> ctypes.CDLL:
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version", "vitk_attn_bwd_workspace_bytes",
-                        "vitk_debug_set_trace"):
+                        "vitk_debug_set_trace", "vitk_build_id"):
             fn.restype = c_int32
     _lib = lib
     return lib
@@ -323,11 +360,45 @@ def prefix_rows(x: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor, B: int, N
 
 
 def embed_bwd(g: torch.Tensor, gp: Optional[torch.Tensor], dpos: Optional[torch.Tensor],
-              dprefix: Optional[torch.Tensor], B: int, N: int, D: int, prefix: int) -> None:
+              dprefix0: Optional[torch.Tensor], dprefix1: Optional[torch.Tensor], B: int, N: int, D: int, prefix: int) -> None:
+    """dpos / dprefix0 / dprefix1 are ACCUMULATED into (pos_embed / cls_token / dist_token gradient rows)."""
     _req(g, torch.float32, "embed_bwd g")
+    for t in (dpos, dprefix0, dprefix1):
+        if t is not None:
+            _req(t, torch.float32, "embed_bwd gradient row")
     with _Timed("embed_bwd"):
-        _check(load().vitk_embed_bwd(g.data_ptr(), _ptr(gp), _ptr(dpos), _ptr(dprefix), B, N, D, prefix, _stream()),
-               "vitk_embed_bwd")
+        _check(load().vitk_embed_bwd(g.data_ptr(), _ptr(gp), _ptr(dpos), _ptr(dprefix0), _ptr(dprefix1), B, N, D, prefix,
+                                     _stream()), "vitk_embed_bwd")
+    _count()
+
+
+def droppath_masks(rs: torch.Tensor, drop_probs, seed: int, offset: int) -> None:
+    """rs fp32 [rows, B] <- Bernoulli(1 - p[row]) / (1 - p[row]); one launch for every DropPath of a forward pass."""
+    _req(rs, torch.float32, "droppath_masks rs")
+    rows, B = rs.shape
+    arr = (c_float * rows)(*[float(p) for p in drop_probs])
+    with _Timed("droppath_masks"):
+        _check(load().vitk_droppath_masks(rs.data_ptr(), arr, rows, B, seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
+                                          _stream()), "vitk_droppath_masks")
+    _count()
+
+
+def scale_f32_(x: torch.Tensor, scale: torch.Tensor) -> None:
+    """x *= scale[0] in place; ``scale`` is a device scalar (no host sync)."""
+    _req(x, torch.float32, "scale_f32 x")
+    _req(scale, torch.float32, "scale_f32 scale")
+    with _Timed("scale_f32"):
+        _check(load().vitk_scale_f32(x.data_ptr(), scale.data_ptr(), x.numel(), _stream()), "vitk_scale_f32")
+    _count()
+
+
+def clip_coef(sumsq_t: torch.Tensor, grad_scale: float, max_norm: float, coef: torch.Tensor,
+              norm: Optional[torch.Tensor]) -> None:
+    for t in (sumsq_t, coef):
+        _req(t, torch.float32, "clip_coef")
+    with _Timed("clip_coef"):
+        _check(load().vitk_clip_coef(sumsq_t.data_ptr(), grad_scale, max_norm, coef.data_ptr(), _ptr(norm), _stream()),
+               "vitk_clip_coef")
     _count()
 
 
@@ -403,24 +474,36 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
 def adamw_flat(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, shadow: Optional[torch.Tensor],
                ema: Optional[torch.Tensor], chunk_group: Optional[torch.Tensor], chunk: int, lrs, wds, beta1: float,
                beta2: float, eps: float, step: int, grad_scale: float = 1.0, ema_decay: float = 0.0,
-               zero_grad: bool = False) -> None:
+               zero_grad: bool = False, g_bf16: Optional[torch.Tensor] = None,
+               grad_scale_dev: Optional[torch.Tensor] = None) -> None:
     for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _req(t, torch.float32, f"adamw {nm}")
+    if g_bf16 is not None:
+        _req(g_bf16, torch.bfloat16, "adamw g_bf16")
+        if g_bf16.numel() != p.numel():
+            raise VitkError("adamw: g_bf16 must have as many elements as p")
+    if grad_scale_dev is not None:
+        _req(grad_scale_dev, torch.float32, "adamw grad_scale_dev")
     n = p.numel()
     ng = len(lrs)
     lr_arr = (c_float * ng)(*[float(x) for x in lrs])
     wd_arr = (c_float * ng)(*[float(x) for x in wds])
     with _Timed("adamw_flat"):
-        _check(load().vitk_adamw_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), _ptr(ema), n,
-                                      _ptr(chunk_group), chunk, ng, lr_arr, wd_arr, beta1, beta2, eps, step, grad_scale,
-                                      ema_decay, int(zero_grad), _stream()), "vitk_adamw_flat")
+        _check(load().vitk_adamw_flat(p.data_ptr(), g.data_ptr(), _ptr(g_bf16), _ptr(grad_scale_dev), m.data_ptr(),
+                                      v.data_ptr(), _ptr(shadow), _ptr(ema), n, _ptr(chunk_group), chunk, ng, lr_arr, wd_arr,
+                                      beta1, beta2, eps, step, grad_scale, ema_decay, int(zero_grad), _stream()),
+               "vitk_adamw_flat")
     _count()
 
 
 def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
-    _req(x, torch.float32, "sumsq x")
+    """out[0] += sum(x^2); x fp32 or bf16."""
+    _req(out, torch.float32, "sumsq out")
+    if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+        raise VitkError(f"sumsq x: expected a float32 / bfloat16 CUDA tensor, got {x.dtype} on {x.device}")
+    fn = load().vitk_sumsq if x.dtype == torch.float32 else load().vitk_sumsq_bf16
     with _Timed("sumsq"):
-        _check(load().vitk_sumsq(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
+        _check(fn(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
     _count()
 
 

@@ -62,7 +62,7 @@ struct FwdSmem {
 template <int T>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                float* __restrict__ lse, int N, int H, float scale, long long* trace) {
+                float* __restrict__ lse, int N, int H, int hd, float scale, long long* trace) {
   VITK_STAMP(0);
   using L = FwdSmem<T>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -99,12 +99,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     mbar_arrive_expect_tx(bar_q, TILE_BYTES);
-    tma_load_3d(smem + L::Q_OFF, &tm_qkv, bar_q, h * HD, q0, b);
+    tma_load_head(smem + L::Q_OFF, &tm_qkv, bar_q, h, q0, b);
     for (int j = 0; j < nkv; ++j) {
       mbar_arrive_expect_tx(&bar_kv[j], 2 * TILE_BYTES);
-      tma_load_3d(smem + L::KV_OFF + j * 2 * TILE_BYTES, &tm_qkv, &bar_kv[j], (H + h) * HD, j * TILE, b);
-      tma_load_3d(smem + L::KV_OFF + j * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, &bar_kv[j],
-                  (2 * H + h) * HD, j * TILE, b);
+      tma_load_head(smem + L::KV_OFF + j * 2 * TILE_BYTES, &tm_qkv, &bar_kv[j], H + h, j * TILE, b);
+      tma_load_head(smem + L::KV_OFF + j * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, &bar_kv[j], 2 * H + h, j * TILE, b);
     }
   }
 
@@ -229,9 +228,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   const int q = q0 + r;
   if (q < N) {
     const float inv = 1.0f / l_run;
-    __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * HD) + h * HD;
+    __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * hd) + h * hd;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
+      if (g * 8 >= hd) break;   // columns >= head_dim are the zero padding of the 64-wide tiles
       uint4 u;
       u.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
       u.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
@@ -265,9 +265,11 @@ struct BwdSmem {
   static constexpr uint32_t BYTES = BAR_OFF + 128;
 };
 
-__device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+// one accumulator row (columns 0..31 in a, 32..63 in b) -> bf16; only the first `hd` (multiple of 8) columns exist
+__device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint32_t (&a)[32], const uint32_t (&b)[32], int hd) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
+    if (g * 8 >= hd) break;
     uint4 u;
     u.x = pack_bf16x2(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
     u.y = pack_bf16x2(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
@@ -277,6 +279,7 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
   }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
+    if (32 + g * 8 >= hd) break;
     uint4 u;
     u.x = pack_bf16x2(__uint_as_float(b[g * 8 + 0]), __uint_as_float(b[g * 8 + 1]));
     u.y = pack_bf16x2(__uint_as_float(b[g * 8 + 2]), __uint_as_float(b[g * 8 + 3]));
@@ -288,8 +291,8 @@ __device__ __forceinline__ void store_row_bf16_64(__nv_bfloat16* dst, const uint
 
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const float* __restrict__ dsum_g, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, float scale,
-                long long* trace) {
+                const float* __restrict__ dsum_g, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv, int N, int H, int hd,
+                float scale, long long* trace) {
   using L = BwdSmem;
   VITK_STAMP(0);
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -325,10 +328,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tma_prefetch_desc(&tm_do);
     mbar_arrive_expect_tx(bar_ld, nt * 4 * TILE_BYTES);
     for (int t = 0; t < nt; ++t) {
-      tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, h * HD, t * TILE, b);
-      tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_do, bar_ld, h * HD, t * TILE, b);
-      tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, (H + h) * HD, t * TILE, b);
-      tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, bar_ld, (2 * H + h) * HD, t * TILE, b);
+      tma_load_head(smem + L::QDO_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, h, t * TILE, b);
+      tma_load_head(smem + L::QDO_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_do, bar_ld, h, t * TILE, b);
+      tma_load_head(smem + L::KV_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, H + h, t * TILE, b);
+      tma_load_head(smem + L::KV_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, bar_ld, 2 * H + h, t * TILE, b);
     }
   }
 
@@ -487,11 +490,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
       tmem_ld_wait();
       const int kv = j * TILE + r;
-      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (2 * H + h) * HD, a0, a1);
+      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * hd) + (2 * H + h) * hd, a0, a1, hd);
       tmem_ld_32x32(tm_dk + lane_addr, a0);
       tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
       tmem_ld_wait();
-      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (H + h) * HD, a0, a1);
+      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * hd) + (H + h) * hd, a0, a1, hd);
     }
     // NOTE: the next kv tile's dV/dK MMAs (accumulate = 0) are only issued after the next
     // iteration's __syncthreads, i.e. after every thread finished these TMEM reads.
@@ -507,7 +510,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tmem_ld_32x32(tm_dq + i * HD + lane_addr + 32, a1);
     tmem_ld_wait();
     const int q = i * TILE + r;
-    if (q < N) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * HD) + h * HD, a0, a1);
+    if (q < N) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * hd) + h * hd, a0, a1, hd);
   }
 
   VITK_STAMP(30);
@@ -518,255 +521,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     tmem_dealloc(tmem_base, 512);
   }
   VITK_STAMP(31);
-}
-
-// ================================================================================================
-// Forward, persistent variant for N <= 256 (single-pass softmax: the whole score row lives in TMEM).
-//
-// 320 threads: warps 0-7 = softmax / epilogue, warp 8 = TMA producer, warp 9 = MMA issuer.  Two threads share a
-// score row (thread (r, half) owns row r and one half of the kv columns; TMEM lane = row, so both warpgroups can
-// read it) and exchange max / sum through smem: with one warp per scheduler the softmax is latency-bound, two warps
-// per scheduler nearly double its throughput.  One CTA per SM loops over work items (b, h, q-tile):
-//   * Q/K/V tiles of item n+1 are prefetched into the second smem stage while item n is processed,
-//   * S is double-buffered in TMEM (2 x 256 columns): S_{n+1} = Q K^T is issued before the softmax of item n ends,
-//   * O_n = P_n V (written into columns [0,64) of S_n's buffer once S_n has been consumed) is read back while the
-//     tensor core already works on S_{n+1}.
-// smem: 2 stages x (Q 16K + K T*16K + V T*16K) | P [T*2 chunks][128 rows][128 B] | exchange | barriers
-// ================================================================================================
-template <int T>
-struct Fwd2Smem {
-  static constexpr uint32_t STAGE = (1 + 2 * T) * TILE_BYTES;
-  static constexpr uint32_t P_OFF = 2 * STAGE;
-  static constexpr uint32_t XCH_OFF = P_OFF + 2 * T * TILE_BYTES;     // float [2 kind][2 half][128]
-  static constexpr uint32_t BAR_OFF = XCH_OFF + 2 * 2 * 128 * 4;
-  static constexpr uint32_t BYTES = BAR_OFF + 256;
-};
-
-template <int T>
-__global__ void __launch_bounds__(320, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-                 int B, int N, int H, float scale) {
-  using L = Fwd2Smem<T>;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [2] TMA -> MMA
-  uint64_t* stage_empty = stage_full + 2;                                  // [2] MMA -> TMA
-  uint64_t* s_full = stage_empty + 2;                                      // [2] MMA -> softmax (S ready)
-  uint64_t* o_full = s_full + 2;                                           // [2] MMA -> softmax (O ready)
-  uint64_t* tmem_free = o_full + 2;                                        // [2] softmax -> MMA (buffer drained)
-  uint64_t* p_full = tmem_free + 2;                                        // [1] softmax -> MMA (P written)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_full + 1);
-  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int QT = (N + TILE - 1) / TILE;
-  const int items = B * H * QT;
-  const uint32_t n_eff = roundup16(N);
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&stage_full[i], 1);
-      mbar_init(&stage_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&tmem_free[i], 256);
-    }
-    mbar_init(p_full, 256);
-    fence_mbar_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 8) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      int n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int st = n & 1;
-        const int qt = it % QT, bh = it / QT, h = bh % H, b = bh / H;
-        mbar_wait(&stage_empty[st], ((n >> 1) & 1) ^ 1);
-        uint8_t* base = smem + st * L::STAGE;
-        mbar_arrive_expect_tx(&stage_full[st], L::STAGE);
-        tma_load_3d(base, &tm_qkv, &stage_full[st], h * HD, qt * TILE, b);
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-          tma_load_3d(base + (1 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (H + h) * HD, t * TILE, b);
-          tma_load_3d(base + (1 + T + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (2 * H + h) * HD, t * TILE, b);
-        }
-      }
-    }
-  } else if (warp == 9) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
-      const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
-      const uint32_t sP = smem_u32(smem + L::P_OFF);
-      const int ksteps = (int)n_eff / 16;
-      auto issue_s = [&](int n) {
-        const int st = n & 1;
-        mbar_wait(&stage_full[st], (n >> 1) & 1);
-        mbar_wait(&tmem_free[st], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t sQ = smem_u32(smem + st * L::STAGE), sK = sQ + TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + st * 256, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc_s, k > 0);
-        umma_commit(&s_full[st]);
-      };
-      int count = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x) ++count;
-      if (count > 0) issue_s(0);
-      for (int n = 0; n < count; ++n) {
-        const int st = n & 1;
-        if (n + 1 < count) issue_s(n + 1);
-        mbar_wait(p_full, n & 1);
-        tc_fence_after();
-        const uint32_t sV = smem_u32(smem + st * L::STAGE) + (1 + T) * TILE_BYTES;
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ss(tmem_base + st * 256, umma_desc_kmajor(sP + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                       umma_desc_mnmajor(sV + k * 2048, TILE_BYTES), idesc_o, k > 0);
-        umma_commit(&o_full[st]);
-        umma_commit(&stage_empty[st]);  // Q, K (S done earlier in issue order) and V are free again
-      }
-    }
-  } else {
-    // ------------------------------ softmax / epilogue (256 threads, 2 per row) ------------------------------
-    const int r = threadIdx.x & 127;
-    const int half = threadIdx.x >> 7;
-    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const float c2 = scale * LOG2E;
-    uint8_t* sP = smem + L::P_OFF;
-    const int nchunks = (int)(n_eff + 31) / 32;      // 32-column chunks of the score row (<= 8)
-    const int c_lo = half == 0 ? 0 : (nchunks + 1) / 2;
-    const int c_hi = half == 0 ? (nchunks + 1) / 2 : nchunks;
-    float prev_m = 0.f;
-    int prev_it = -1;
-
-    // read this thread's 32 columns of O of the previous item, normalise, store; hand the TMEM buffer back
-    auto finish = [&](int n_prev, float l) {
-      const int st = n_prev & 1;
-      mbar_wait(&o_full[st], (n_prev >> 1) & 1);
-      tc_fence_after();
-      uint32_t o[32];
-      tmem_ld_32x32(tmem_base + st * 256 + lane_addr + half * 32, o);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&tmem_free[st]);
-      const int qt = prev_it % QT, bh = prev_it / QT, h = bh % H, b = bh / H;
-      const int q = qt * TILE + r;
-      if (q < N) {
-        const float inv = 1.0f / l;
-        __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * HD) + h * HD + half * 32;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + g * 8) = u;
-        }
-        if (half == 0 && lse) lse[((long long)b * H + h) * N + q] = prev_m * scale + __logf(l);
-      }
-    };
-
-    int n = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int st = n & 1;
-      const uint32_t tS = tmem_base + st * 256 + lane_addr;
-      float* xm = xch;         // [half][row] partial maxima of this item
-      float* xs = xch + 256;   // [half][row] partial sums (read one item later)
-      mbar_wait(&s_full[st], (n >> 1) & 1);
-      tc_fence_after();
-      // this thread's half of the score row -> registers (<= 4 chunks of 32 columns)
-      uint32_t sv[4][32];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = c_lo + cc;
-        if (c < c_hi) {
-          tmem_ld_32x32(tS + c * 32, sv[cc]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(sv[cc][i]));
-        }
-      }
-      xm[half * 128 + r] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(xm[r], xm[128 + r]);
-      const float l_prev = xs[r] + xs[128 + r];          // row sum of the previous item (both halves)
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone has read xm / xs: they may be overwritten
-      // O of the previous item (its P*V has long finished): frees the P buffer for this item as a side effect
-      if (n > 0) finish(n - 1, l_prev);
-      const float mc = mx * c2;
-      float rowsum = 0.f;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = c_lo + cc;
-        if (c < c_hi) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if ((uint32_t)(c * 32 + g * 8) < n_eff) {
-              float p[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float e = ex2_approx(fmaf(__uint_as_float(sv[cc][g * 8 + i]), c2, -mc));
-                p[i] = (c * 32 + g * 8 + i < N) ? e : 0.f;
-              }
-              uint4 u;
-              u.x = pack_bf16x2(p[0], p[1]);
-              u.y = pack_bf16x2(p[2], p[3]);
-              u.z = pack_bf16x2(p[4], p[5]);
-              u.w = pack_bf16x2(p[6], p[7]);
-              st_swz(sP, r, c * 4 + g, u);
-              const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
-              rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
-            }
-          }
-        }
-      }
-      xs[half * 128 + r] = rowsum;   // read by both halves after the next item's first bar.sync
-      prev_m = mx;
-      prev_it = it;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    if (n > 0) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // partial sums of the last item are visible
-      finish(n - 1, xch[256 + r] + xch[256 + 128 + r]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-template <int T>
-int launch_fwd2(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
-  auto kern = attn_fwd2_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd2Smem<T>::BYTES);
-    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int items = B * H * ((N + TILE - 1) / TILE);
-  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
-  kern<<<grid, 320, Fwd2Smem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, B, N, H, scale);
-  return vitk_check_launch("attn_fwd2");
 }
 
 // ================================================================================================
@@ -791,322 +545,13 @@ struct Fwd3Smem {
   static constexpr uint32_t BAR_OFF = XCH_OFF + 2 * 2 * 2 * 128 * 4;
   static constexpr uint32_t BYTES = BAR_OFF + 256;
 };
-constexpr int FWD3_THREADS = 19 * 32;
-
-__global__ void __launch_bounds__(FWD3_THREADS, 1)
-attn_fwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
-                 int B, int N, int H, float scale, long long* trace) {
-  using L = Fwd3Smem;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* stage_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [2] TMA -> MMA warps
-  uint64_t* stage_empty = stage_full + 2;                                  // [2] both MMA warps -> TMA
-  uint64_t* s_full = stage_empty + 2;                                      // [g] MMA -> group: S ready
-  uint64_t* p_full = s_full + 2;                                           // [g] group -> MMA: P written
-  uint64_t* o_full = p_full + 2;                                           // [g] MMA -> group: O ready
-  uint64_t* slot_free = o_full + 2;                                        // [g] group -> MMA: O read out
-  uint64_t* o_staged = slot_free + 2;                                      // [g] group -> MMA: bf16 O tile in smem
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_staged + 2);
-  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
-
-  // timeline of items 2 and 3 of CTA 0 (tools/attn_trace3.py): role base + 8 * (n - 2) + event
-#define FWD3_STAMP(base, ev)                                                       \
-  do {                                                                             \
-    if (trace != nullptr && blockIdx.x == 0 && (n == 2 || n == 3)) trace[(base) + 8 * (n - 2) + (ev)] = clock64(); \
-  } while (0)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = B * H;
-  const uint32_t n_eff = roundup16(N);
-  const int KS = (int)n_eff / 16;  // 16-column units of the score row == k-steps of P V
-  const int k0 = KS / 2, k1 = KS - k0;
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&stage_full[i], 1);
-      mbar_init(&stage_empty[i], 4);   // per MMA warp: Q/K/V reads retired + its group's O staging tile stored
-      mbar_init(&o_staged[i], 8);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);        // one arrival per softmax warp
-      mbar_init(&o_full[i], 1);
-      mbar_init(&slot_free[i], 8);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 18) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 18) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      int n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int st = n & 1;
-        const int h = it % H, b = it / H;
-        mbar_wait(&stage_empty[st], ((n >> 1) & 1) ^ 1);
-        uint8_t* base = smem + st * L::STAGE;
-        mbar_arrive_expect_tx(&stage_full[st], L::STAGE);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          tma_load_3d(base + t * TILE_BYTES, &tm_qkv, &stage_full[st], h * HD, t * TILE, b);
-          tma_load_3d(base + (2 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (H + h) * HD, t * TILE, b);
-          tma_load_3d(base + (4 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (2 * H + h) * HD, t * TILE, b);
-        }
-      }
-    }
-  } else if (warp >= 16) {
-    // ------------------------------ MMA issuer of group g ------------------------------
-    // The whole warp runs the loop (uniform control flow keeps the descriptors in uniform registers); one elected
-    // lane issues.  Group 1 starts half an item late (it waits for group 0's first P), so that from then on one
-    // group's exps overlap the other group's MMA / TMEM / store phases.
-    {
-      const int g = warp - 16;
-      const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
-      const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P (TMEM, K-major), B = V MN-major
-      const uint32_t slot = tmem_base + g * 256;
-      const uint32_t phi = 16 * k0;  // first TMEM column of the packed P of the upper column half
-      // bf16 O tile of item m (staged by the group in the dead Q_g tile of its stage) -> global, then release the stage
-      auto store_o = [&](int m, int item) {
-        const int st = m & 1;
-        mbar_wait(&o_staged[g], m & 1);
-        if (elect_one()) {
-          tma_store_3d(&tm_out, smem + st * L::STAGE + g * TILE_BYTES, (item % H) * HD, g * TILE, item / H);  // rows >= N clipped
-          tma_store_commit_and_wait_read();
-          mbar_arrive(&stage_empty[st]);
-        }
-        __syncwarp();
-      };
-      int n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int st = n & 1;
-        const uint32_t sbase = smem_u32(smem + st * L::STAGE);
-        const uint32_t sQ = sbase + g * TILE_BYTES, sK = sbase + 2 * TILE_BYTES, sV = sbase + 4 * TILE_BYTES;
-        mbar_wait(&stage_full[st], (n >> 1) & 1);
-        if (lane == 0) FWD3_STAMP(32 + 16 * g, 0);
-        if (n > 0) mbar_wait(&slot_free[g], (n - 1) & 1);
-        else if (g == 1) mbar_wait(&p_full[0], 0);
-        if (lane == 0) FWD3_STAMP(32 + 16 * g, 1);
-        tc_fence_after();
-        const uint64_t qdesc = umma_desc_kmajor(sQ), kdesc = umma_desc_kmajor(sK);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k > 0);
-          umma_commit(&s_full[g]);
-        }
-        __syncwarp();
-        if (lane == 0) FWD3_STAMP(32 + 16 * g, 2);
-        if (n > 0) store_o(n - 1, it - (int)gridDim.x);   // nothing else to do until this group's P arrives
-        mbar_wait(&p_full[g], n & 1);
-        if (lane == 0) FWD3_STAMP(32 + 16 * g, 3);
-        tc_fence_after();
-        const uint64_t vdesc = umma_desc_mnmajor(sV, TILE_BYTES);
-        if (elect_one()) {
-          for (int ks = 0; ks < k0; ++ks) umma_bf16_ts(slot + 192, slot + 8 * ks, vdesc + (uint64_t)(ks * 128), idesc_o, ks > 0);
-          for (int ks = 0; ks < k1; ++ks)
-            umma_bf16_ts(slot + 192, slot + phi + 8 * ks, vdesc + (uint64_t)((k0 + ks) * 128), idesc_o, 1);
-          umma_commit(&o_full[g]);
-          umma_commit(&stage_empty[st]);  // this group's reads of Q_g / K / V have retired
-        }
-        __syncwarp();
-        if (lane == 0) FWD3_STAMP(32 + 16 * g, 4);
-      }
-      if (n > 0) {
-        store_o(n - 1, blockIdx.x + (n - 1) * (int)gridDim.x);
-        if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the store
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------ softmax group g: 256 threads, 2 per score row ------------------------------
-    const int g = warp >> 3, quarter = warp & 3, half = (warp >> 2) & 1;
-    const int r = quarter * 32 + lane;
-    const uint32_t slot = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int qn = g == 0 ? min(TILE, N) : N - TILE;   // valid rows of this q tile
-    const bool active = quarter * 32 < qn;             // warp-uniform: some row of this warp is real
-    const int my_k = half ? k1 : k0;                   // 16-column units owned by this thread
-    const int c0 = half ? 16 * k0 : 0;                 // first score column (and first packed-P column)
-    float* xm = xch + g * 512;                         // [half][row] partial maxima
-    float* xs = xm + 256;                              // [half][row] partial sums
-    const float c2 = scale * LOG2E;
-    const int q = g * TILE + r;
-    int n = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const bool tr = (warp & 7) == 0 && lane == 0;
-      mbar_wait(&s_full[g], n & 1);
-      tc_fence_after();
-      if (tr) FWD3_STAMP(16 * g, 0);
-      uint32_t ra[16], rb[16];  // the only TMEM staging registers: shared by both passes and the O read-out
-
-      // ---- pass 1: row maximum over this thread's columns ----
-      float mx = -INFINITY;
-      if (active) {
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll 1
-        for (int u0 = 0; u0 < my_k; u0 += 2) {
-          tmem_ld_32x16(slot + c0 + u0 * 16, ra);
-          if (u0 + 1 < my_k) tmem_ld_32x16(slot + c0 + (u0 + 1) * 16, rb);
-          tmem_ld_wait();
-#pragma unroll
-          for (int uu = 0; uu < 2; ++uu) {
-            if (u0 + uu < my_k) {
-              const uint32_t(&v)[16] = uu ? rb : ra;
-              const int col = c0 + (u0 + uu) * 16;
-              if (col + 16 <= N) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  m0 = fmaxf(m0, __uint_as_float(v[i]));
-                  m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-                  m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-                  m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (col + i < N) m0 = fmaxf(m0, __uint_as_float(v[i]));
-              }
-            }
-          }
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      }
-      if (tr) FWD3_STAMP(16 * g, 1);
-      xm[half * 128 + r] = mx;
-      named_bar_sync(1 + g, 256);
-      if (tr) FWD3_STAMP(16 * g, 2);
-      mx = fmaxf(xm[r], xm[128 + r]);
-
-      // ---- pass 2: P = exp2(S * c2 - mx * c2) -> packed bf16 written back over S ----
-      float s0 = 0.f, s1 = 0.f;
-      if (active) {
-        const float mc = mx * c2;
-        uint32_t(&cur)[16] = ra;
-        uint32_t(&nxt)[16] = rb;
-        tmem_ld_32x16(slot + c0, cur);
-        tmem_ld_wait();
-#pragma unroll 1
-        for (int u = 0; u < my_k; ++u) {
-          const bool more = u + 1 < my_k;
-          if (more) tmem_ld_32x16(slot + c0 + (u + 1) * 16, nxt);  // in flight while this unit's exps issue
-          const int col = c0 + u * 16;
-          uint32_t pk[8];
-          if (col + 16 <= N) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * i]), c2, -mc));
-              const float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * i + 1]), c2, -mc));
-              s0 += e0;
-              s1 += e1;
-              pk[i] = pack_bf16x2(e0, e1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float e0 = ex2_approx(fmaf(__uint_as_float(cur[2 * i]), c2, -mc));
-              float e1 = ex2_approx(fmaf(__uint_as_float(cur[2 * i + 1]), c2, -mc));
-              e0 = (col + 2 * i < N) ? e0 : 0.f;
-              e1 = (col + 2 * i + 1 < N) ? e1 : 0.f;
-              s0 += e0;
-              s1 += e1;
-              pk[i] = pack_bf16x2(e0, e1);
-            }
-          }
-          tmem_st_32x8(slot + c0 + u * 8, pk);
-          if (more) {
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
-          }
-          if (tr && trace != nullptr && blockIdx.x == 0 && n == 2) trace[64 + 16 * g + u] = clock64();
-        }
-        tmem_st_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[g]);
-      if (tr) FWD3_STAMP(16 * g, 3);
-
-      xs[half * 128 + r] = s0 + s1;
-      named_bar_sync(1 + g, 256);
-      if (tr) FWD3_STAMP(16 * g, 4);
-      const float l = xs[r] + xs[128 + r];
-
-      // ---- O = P V: this thread's 32 of the 64 output columns ----
-      mbar_wait(&o_full[g], n & 1);
-      tc_fence_after();
-      if (tr) FWD3_STAMP(16 * g, 5);
-      if (active) {
-        tmem_ld_32x16(slot + 192 + half * 32, ra);
-        tmem_ld_32x16(slot + 192 + half * 32 + 16, rb);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&slot_free[g]);
-      if (tr) FWD3_STAMP(16 * g, 6);
-      // normalised bf16 rows -> the (dead) Q_g tile of this item's stage, 128-byte swizzled -> one TMA store per group
-      const int st = n & 1;
-      uint8_t* stg = smem + st * L::STAGE + g * TILE_BYTES;
-      const int h = it % H, b = it / H;
-      if (active) {
-        const float inv = 1.0f / l;
-#pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          const uint32_t(&o)[16] = gg < 2 ? ra : rb;
-          const int e = (gg & 1) * 8;
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv, __uint_as_float(o[e + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
-          st_swz(stg, r, half * 4 + gg, u);
-        }
-        if (half == 0 && q < N && lse) lse[((long long)b * H + h) * N + q] = mx * scale + __logf(l);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_staged[g]);   // the group's MMA warp issues the TMA store
-      if (tr) FWD3_STAMP(16 * g, 7);
-    }
-  }
-#undef FWD3_STAMP
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 18) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-int launch_fwd3(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
-  CUtensorMap tm_out;
-  int rc = vitk_make_tmap_3d(&tm_out, out, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD, HD,
-                             TILE, 1);
-  if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd3Smem::BYTES);
-    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd3: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int items = B * H;
-  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
-  attn_fwd3_kernel<<<grid, FWD3_THREADS, Fwd3Smem::BYTES, s>>>(tm, tm_out, lse, B, N, H, scale, g_trace_buf);
-  return vitk_check_launch("attn_fwd3");
-}
 
 // ================================================================================================
-// Forward, one-thread-per-row variant of attn_fwd3 (same smem stages, barriers, TMEM slots and TMA-stored O).
+// attn_fwd4: the kernel built on the structure above with ONE thread per score row.
 // 11 warps: group g = warps 4g..4g+3 (thread = score row of q tile g), warp 8 + g issues group g's MMAs, warp 10 is
 // the TMA producer.  With 168 registers per thread the score row is processed in 32-column chunks that are
 // double-buffered in registers and fully unrolled (the structure of the backward's P phase, which sustains ~10 cycles
-// per exp per warp; attn_fwd3's 16-column rolled loop with two threads per row needed ~29), there is no max / sum
+// per exp per warp; a 16-column rolled loop with two threads per row needed ~29), there is no max / sum
 // exchange and no named barrier, and P is one contiguous run of packed columns [0, n_eff / 2) written in place
 // behind the read pointer.
 // ================================================================================================
@@ -1168,9 +613,9 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         mbar_arrive_expect_tx(&stage_full[st], L::STAGE);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          tma_load_3d(base + t * TILE_BYTES, &tm_qkv, &stage_full[st], h * HD, t * TILE, b);
-          tma_load_3d(base + (2 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (H + h) * HD, t * TILE, b);
-          tma_load_3d(base + (4 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], (2 * H + h) * HD, t * TILE, b);
+          tma_load_head(base + t * TILE_BYTES, &tm_qkv, &stage_full[st], h, t * TILE, b);
+          tma_load_head(base + (2 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], H + h, t * TILE, b);
+          tma_load_head(base + (4 + t) * TILE_BYTES, &tm_qkv, &stage_full[st], 2 * H + h, t * TILE, b);
         }
       }
     }
@@ -1184,7 +629,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       const int st = m & 1;
       mbar_wait(&o_staged[g], m & 1);
       if (elect_one()) {
-        tma_store_3d(&tm_out, smem + st * L::STAGE + g * TILE_BYTES, (item % H) * HD, g * TILE, item / H);  // rows >= N clipped
+        tma_store_head(&tm_out, smem + st * L::STAGE + g * TILE_BYTES, item % H, g * TILE, item / H);  // rows >= N clipped
         tma_store_commit_and_wait_read();
         mbar_arrive(&stage_empty[st]);
       }
@@ -1380,11 +825,7 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   }
 }
 
-int launch_fwd4(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
-  CUtensorMap tm_out;
-  int rc = vitk_make_tmap_3d(&tm_out, out, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD, HD,
-                             TILE, 1);
-  if (rc) return rc;
+int launch_fwd4(const CUtensorMap& tm, const CUtensorMap& tm_out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd3Smem::BYTES);
@@ -1487,15 +928,15 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
           mbar_wait(&q_empty[g], (qcnt[g] & 1) ^ 1);
           ++qcnt[g];
           mbar_arrive_expect_tx(&q_full[g], TILE_BYTES);
-          tma_load_3d(smem + L::Q_OFF + g * TILE_BYTES, &tm_qkv, &q_full[g], h * HD, qt * TILE, b);
+          tma_load_head(smem + L::Q_OFF + g * TILE_BYTES, &tm_qkv, &q_full[g], h, qt * TILE, b);
         }
         for (int j = 0; j < QT; ++j, ++kvc) {
           const int st = kvc % L::STAGES;
           mbar_wait(&kv_empty[st], ((kvc / L::STAGES) & 1) ^ 1);
           uint8_t* base = smem + L::KV_OFF + st * 2 * TILE_BYTES;
           mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-          tma_load_3d(base, &tm_qkv, &kv_full[st], (H + h) * HD, j * TILE, b);
-          tma_load_3d(base + TILE_BYTES, &tm_qkv, &kv_full[st], (2 * H + h) * HD, j * TILE, b);
+          tma_load_head(base, &tm_qkv, &kv_full[st], H + h, j * TILE, b);
+          tma_load_head(base + TILE_BYTES, &tm_qkv, &kv_full[st], 2 * H + h, j * TILE, b);
         }
       }
     }
@@ -1569,7 +1010,7 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       // bf16 O tile (staged by the group in the Q_g tile) -> global; then the Q_g tile may be reloaded
       mbar_wait(&o_staged[g], rounds & 1);
       if (elect_one()) {
-        tma_store_3d(&tm_out, smem + L::Q_OFF + g * TILE_BYTES, h * HD, qt * TILE, b);  // rows >= N clipped
+        tma_store_head(&tm_out, smem + L::Q_OFF + g * TILE_BYTES, h, qt * TILE, b);  // rows >= N clipped
         tma_store_commit_and_wait_read();
         mbar_arrive(&q_empty[g]);
       }
@@ -1743,11 +1184,7 @@ attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   }
 }
 
-int launch_fwd5(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
-  CUtensorMap tm_out;
-  int rc = vitk_make_tmap_3d(&tm_out, out, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD, HD,
-                             TILE, 1);
-  if (rc) return rc;
+int launch_fwd5(const CUtensorMap& tm, const CUtensorMap& tm_out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd5Smem::BYTES);
@@ -1764,20 +1201,21 @@ int launch_fwd5(const CUtensorMap& tm, void* out, float* lse, int B, int N, int 
 // D[b, h, n] = sum_d O[b, n, h, d] * dO[b, n, h, d]: one warp per token row, fully coalesced 16-byte loads.
 // (Computing it inside the backward kernel costs ~10k cycles of exposed, row-strided global loads per CTA.)
 __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                                 float* __restrict__ dsum, long long rows, int N, int H) {
+                                 float* __restrict__ dsum, long long rows, int N, int H, int hd) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const long long b = row / N;
   const int n = (int)(row - b * N);
-  const uint4* op = reinterpret_cast<const uint4*>(out + row * (long long)(H * HD));
-  const uint4* dp = reinterpret_cast<const uint4*>(dout + row * (long long)(H * HD));
-  const int nchunk = H * HD / 8;  // 16-byte chunks per row; 8 chunks per head
-  for (int c0 = 0; c0 < nchunk; c0 += 32) {
-    const int c = c0 + lane;
+  const __nv_bfloat16* op = out + row * (long long)(H * hd);
+  const __nv_bfloat16* dp = dout + row * (long long)(H * hd);
+  const int u = lane & 7;              // 16-byte chunk of the head: 8 lanes per head, 4 heads per pass
+  const bool live = u * 8 < hd;
+  for (int h0 = 0; h0 < H; h0 += 4) {
+    const int h = h0 + (lane >> 3);
     float s = 0.f;
-    if (c < nchunk) {
-      const uint4 a = __ldg(op + c), d = __ldg(dp + c);
+    if (h < H && live) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(op + h * hd) + u), d = __ldg(reinterpret_cast<const uint4*>(dp + h * hd) + u);
       const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
       const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
       s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
@@ -1785,285 +1223,8 @@ __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if ((lane & 7) == 0 && c < nchunk) dsum[(b * H + (c >> 3)) * N + n] = s;
+    if (u == 0 && h < H) dsum[(b * H + h) * N + n] = s;
   }
-}
-
-// ================================================================================================
-// Backward, two-warpgroup variant (N <= 256): one CTA per (b, h), 288 threads.
-//   warpgroup w (warps 4w..4w+3) owns q tile w: thread r holds row r's probabilities in registers between the
-//   S and dP phases, so S and dP share ONE 128-column TMEM buffer per warpgroup;
-//   warp 8 issues every TMA load and every tcgen05.mma and ping-pongs between the two warpgroups, so the tensor
-//   core runs one warpgroup's GEMMs while the other does its exp / dS math.
-// TMEM: SdP_0 [0,128) | SdP_1 [128,256) | dV_j [256,320) | dK_j [320,384) | dQ_0 [384,448) | dQ_1 [448,512)
-// smem: Q_i, dO_i, K_j, V_j tiles (T*64K) | PdS_0 (32K) | PdS_1 (32K) | barriers.  P_w and dS_w share one buffer:
-//       dS_w overwrites P_w once the dV MMA that reads P_w has retired (covered by the dP commit).
-// ================================================================================================
-struct Bwd2Smem {
-  static constexpr uint32_t QDO_OFF = 0;
-  static constexpr uint32_t KV_OFF = BWD_MAX_T * 2 * TILE_BYTES;
-  static constexpr uint32_t PDS_OFF = KV_OFF + BWD_MAX_T * 2 * TILE_BYTES;
-  static constexpr uint32_t BAR_OFF = PDS_OFF + 2 * 2 * TILE_BYTES;
-  static constexpr uint32_t BYTES = BAR_OFF + 256;
-};
-
-__global__ void __launch_bounds__(288, 1)
-attn_bwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                 const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                 int N, int H, float scale, long long* trace) {
-  using L = Bwd2Smem;
-  VITK_STAMP(0);
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bar_ld = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* bar_s = bar_ld + 1;        // [2] MMA -> WG: S_w ready
-  uint64_t* bar_p = bar_s + 2;         // [2] WG -> MMA: P_w written
-  uint64_t* bar_dp = bar_p + 2;        // [2] MMA -> WG: dP_w ready, P_w consumed
-  uint64_t* bar_ds = bar_dp + 2;       // [2] WG -> MMA: dS_w written
-  uint64_t* bar_drain = bar_ds + 2;    // MMA -> WGs: every MMA of kv tile j retired
-  uint64_t* bar_drained = bar_drain + 1;  // WGs -> MMA: dV_j / dK_j read out
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_drained + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int nt = (N + TILE - 1) / TILE;  // q tiles == kv tiles == active warpgroups
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0) {
-    mbar_init(bar_ld, 1);
-    for (int w = 0; w < 2; ++w) {
-      mbar_init(&bar_s[w], 1);
-      mbar_init(&bar_p[w], 128);
-      mbar_init(&bar_dp[w], 1);
-      mbar_init(&bar_ds[w], 128);
-    }
-    mbar_init(bar_drain, 1);
-    mbar_init(bar_drained, 128 * nt);
-    fence_mbar_init();
-  }
-  if (warp == 8) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
-  const float c2 = scale * LOG2E;
-
-  if (warp == 8) {
-    // ------------------------------ TMA + MMA control ------------------------------
-    if ((threadIdx.x & 31) == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      tma_prefetch_desc(&tm_do);
-      mbar_arrive_expect_tx(bar_ld, nt * 4 * TILE_BYTES);
-      for (int t = 0; t < nt; ++t) {
-        tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, h * HD, t * TILE, b);
-        tma_load_3d(smem + L::QDO_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_do, bar_ld, h * HD, t * TILE, b);
-        tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES, &tm_qkv, bar_ld, (H + h) * HD, t * TILE, b);
-        tma_load_3d(smem + L::KV_OFF + t * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, bar_ld, (2 * H + h) * HD, t * TILE, b);
-      }
-      const uint32_t sQDO = smem_u32(smem + L::QDO_OFF), sKV = smem_u32(smem + L::KV_OFF);
-      const uint32_t sPDS = smem_u32(smem + L::PDS_OFF);
-      auto issue_s = [&](int w, int j) {
-        const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
-        const uint32_t sQ = sQDO + w * 2 * TILE_BYTES, sK = sKV + j * 2 * TILE_BYTES;
-        const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16_ss(tmem_base + w * 128, umma_desc_kmajor(sQ + k * 32), umma_desc_kmajor(sK + k * 32), idesc, k > 0);
-        umma_commit(&bar_s[w]);
-      };
-      mbar_wait(bar_ld, 0);
-      tc_fence_after();
-      for (int w = 0; w < nt; ++w) issue_s(w, 0);
-      const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);   // A, B MN-major (P^T dO, dS^T Q)
-      const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);  // dS K
-      for (int j = 0; j < nt; ++j) {
-        const uint32_t n_eff = roundup16(min(TILE, N - j * TILE));
-        const uint32_t sK = sKV + j * 2 * TILE_BYTES, sV = sK + TILE_BYTES;
-        if (j > 0) {
-          mbar_wait(bar_drained, (j - 1) & 1);  // dV / dK of the previous kv tile were read out
-          tc_fence_after();
-        }
-        for (int w = 0; w < nt; ++w) {
-          const uint32_t q_eff = roundup16(min(TILE, N - w * TILE));
-          const uint32_t sQ = sQDO + w * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES, sP = sPDS + w * 2 * TILE_BYTES;
-          mbar_wait(&bar_p[w], j & 1);
-          tc_fence_after();
-          // dV_j += P_w^T dO_w
-          for (int k = 0; k < (int)q_eff / 16; ++k)
-            umma_bf16_ss(tm_dv, umma_desc_mnmajor(sP + k * 2048, TILE_BYTES), umma_desc_mnmajor(sDO + k * 2048, TILE_BYTES),
-                         idesc_t, (w > 0 || k > 0));
-          // dP_w = dO_w V_j^T  (overwrites S_w, which warpgroup w has already turned into register-resident P)
-          const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_bf16_ss(tmem_base + w * 128, umma_desc_kmajor(sDO + k * 32), umma_desc_kmajor(sV + k * 32), idesc, k > 0);
-          umma_commit(&bar_dp[w]);
-        }
-        for (int w = 0; w < nt; ++w) {
-          const uint32_t q_eff = roundup16(min(TILE, N - w * TILE));
-          const uint32_t sQ = sQDO + w * 2 * TILE_BYTES, sDS = sPDS + w * 2 * TILE_BYTES;
-          mbar_wait(&bar_ds[w], j & 1);
-          tc_fence_after();
-          // dK_j += dS_w^T Q_w
-          for (int k = 0; k < (int)q_eff / 16; ++k)
-            umma_bf16_ss(tm_dk, umma_desc_mnmajor(sDS + k * 2048, TILE_BYTES), umma_desc_mnmajor(sQ + k * 2048, TILE_BYTES),
-                         idesc_t, (w > 0 || k > 0));
-          // dQ_w += dS_w K_j
-          for (int k = 0; k < (int)n_eff / 16; ++k)
-            umma_bf16_ss(tm_dq + w * HD, umma_desc_kmajor(sDS + (k >> 2) * TILE_BYTES + (k & 3) * 32),
-                         umma_desc_mnmajor(sK + k * 2048, TILE_BYTES), idesc_q, (j > 0 || k > 0));
-          if (j + 1 < nt) issue_s(w, j + 1);  // SdP_w is free again: warpgroup w wrote dS_w after reading dP_w
-        }
-        umma_commit(bar_drain);
-      }
-    }
-  } else if (warp < 4 * nt) {
-    // ------------------------------ warpgroup w: rows of q tile w ------------------------------
-    const int w = warp >> 2;
-    const int r = threadIdx.x & 127;
-    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tm_sdp = tmem_base + w * 128 + lane_addr;
-    uint8_t* sPDS = smem + L::PDS_OFF + w * 2 * TILE_BYTES;
-    const int q = w * TILE + r;
-    const int qn = min(TILE, N - w * TILE);
-    const uint32_t q_eff = roundup16(qn);
-    const bool row_ok = r < qn;
-    float my_lse2 = 0.f, my_d = 0.f;
-    if (row_ok) {
-      my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
-      my_d = dsum[((long long)b * H + h) * N + q];
-    }
-    VITK_STAMP(1);
-
-    for (int j = 0; j < nt; ++j) {
-      const int kvn = min(TILE, N - j * TILE);
-      const uint32_t n_eff = roundup16(kvn);
-      const int nchunks = (int)(n_eff + 31) / 32;
-
-      // ---- phase 1: S -> P (registers + smem) ----
-      mbar_wait(&bar_s[w], j & 1);
-      tc_fence_after();
-      VITK_STAMP(2 + j * 6);
-#pragma unroll
-      for (int cb = 0; cb < 4; cb += 2) {
-        if (cb < nchunks) {
-          // two 32-column chunks per TMEM round trip
-          uint32_t sv[2][32];
-          tmem_ld_32x32(tm_sdp + cb * 32, sv[0]);
-          if (cb + 1 < nchunks) tmem_ld_32x32(tm_sdp + (cb + 1) * 32, sv[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = cb + cc;
-            if (c < nchunks && (uint32_t)r < q_eff) {
-              uint32_t pk[16];
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const bool ok0 = row_ok && (c * 32 + 2 * k < kvn), ok1 = row_ok && (c * 32 + 2 * k + 1 < kvn);
-                const float e0 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * k]), c2, -my_lse2));
-                const float e1 = ex2_approx(fmaf(__uint_as_float(sv[cc][2 * k + 1]), c2, -my_lse2));
-                pk[k] = pack_bf16x2(ok0 ? e0 : 0.f, ok1 ? e1 : 0.f);
-              }
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                if ((uint32_t)(c * 32 + g * 8) < n_eff)
-                  st_swz(sPDS, r, c * 4 + g, make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
-            }
-          }
-        }
-      }
-      VITK_STAMP(3 + j * 6);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&bar_p[w]);
-
-      // ---- phase 2: dP -> dS (smem, over P) ----
-      mbar_wait(&bar_dp[w], j & 1);
-      tc_fence_after();
-      VITK_STAMP(4 + j * 6);
-#pragma unroll
-      for (int cb = 0; cb < 4; cb += 2) {
-        if (cb < nchunks) {
-          uint32_t dv[2][32];
-          tmem_ld_32x32(tm_sdp + cb * 32, dv[0]);
-          if (cb + 1 < nchunks) tmem_ld_32x32(tm_sdp + (cb + 1) * 32, dv[1]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int c = cb + cc;
-            if (c < nchunks && (uint32_t)r < q_eff) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if ((uint32_t)(c * 32 + g * 8) < n_eff) {
-                  // P of this row is read back from its own smem slot (written in phase 1, consumed by the dV MMA)
-                  uint8_t* slot = sPDS + ((c * 4 + g) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + g) & 7) ^ (r & 7)) << 4);
-                  const uint4 pu = *reinterpret_cast<const uint4*>(slot);
-                  const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
-                  uint32_t ds[4];
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const float2 pp = unpack_bf16x2(pw[k]);
-                    ds[k] = pack_bf16x2(pp.x * (__uint_as_float(dv[cc][g * 8 + 2 * k]) - my_d) * scale,
-                                        pp.y * (__uint_as_float(dv[cc][g * 8 + 2 * k + 1]) - my_d) * scale);
-                  }
-                  *reinterpret_cast<uint4*>(slot) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
-                }
-              }
-            }
-          }
-        }
-      }
-      VITK_STAMP(5 + j * 6);
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&bar_ds[w]);
-
-      // ---- drain dV_j (warpgroup 0) / dK_j (warpgroup 1, or 0 when it is alone) ----
-      mbar_wait(bar_drain, j & 1);
-      tc_fence_after();
-      VITK_STAMP(6 + j * 6);
-      {
-        const int kv = j * TILE + r;
-        uint32_t a0[32], a1[32];
-        if (w == 0) {
-          tmem_ld_32x32(tm_dv + lane_addr, a0);
-          tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
-          tmem_ld_wait();
-          if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (2 * H + h) * HD, a0, a1);
-        }
-        if (w == nt - 1) {
-          tmem_ld_32x32(tm_dk + lane_addr, a0);
-          tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
-          tmem_ld_wait();
-          if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (H + h) * HD, a0, a1);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_drained);
-      VITK_STAMP(7 + j * 6);
-    }
-
-    // ---- dQ_w (the last bar_drain wait above covers every MMA) ----
-    {
-      uint32_t a0[32], a1[32];
-      tmem_ld_32x32(tm_dq + w * HD + lane_addr, a0);
-      tmem_ld_32x32(tm_dq + w * HD + lane_addr + 32, a1);
-      tmem_ld_wait();
-      if (row_ok) store_row_bf16_64(dqkv + ((long long)b * N + q) * (3 * H * HD) + h * HD, a0, a1);
-    }
-    VITK_STAMP(30);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-  VITK_STAMP(31);
 }
 
 // ================================================================================================
@@ -2093,334 +1254,11 @@ struct Bwd3Smem {
 };
 constexpr int BWD3_THREADS = 10 * 32;
 
-// 32 rows x 64 fp32 (one row per lane, two 32-column halves) -> bf16 -> global rows [row0, row0 + 32) of a tensor with
-// `pitch` elements per row, through a warp-private swizzled 4 KB tile: each store instruction writes 4 full rows.
-__device__ __forceinline__ void store_rows_coalesced(uint8_t* wst, int lane, const uint32_t (&a)[32], const uint32_t (&b)[32],
-                                                     __nv_bfloat16* dst, long long pitch, int rows_valid) {
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const uint32_t(&v)[32] = u < 4 ? a : b;
-    const int e = (u & 3) * 8;
-    uint4 q;
-    q.x = pack_bf16x2(__uint_as_float(v[e + 0]), __uint_as_float(v[e + 1]));
-    q.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-    q.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-    q.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
-    *reinterpret_cast<uint4*>(wst + lane * 128 + ((u ^ (lane & 7)) << 4)) = q;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + (lane >> 3), u = lane & 7;
-    const uint4 q = *reinterpret_cast<const uint4*>(wst + row * 128 + ((u ^ (row & 7)) << 4));
-    if (row < rows_valid) *reinterpret_cast<uint4*>(dst + (long long)row * pitch + u * 8) = q;
-  }
-  __syncwarp();
-}
-
-__global__ void __launch_bounds__(BWD3_THREADS, 1)
-attn_bwd3_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                 const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                 int B, int N, int H, float scale, long long* trace) {
-  using L = Bwd3Smem;
-  // timeline of item 2 of CTA 0 (tools/attn_trace3.py bwd): each role appends clock64() stamps to its own slot range
-  int tslot = 0;
-#define BWD3_STAMP(base) do { if (trace != nullptr && blockIdx.x == 0 && n == 2 && lane == 0 && tslot < 32) trace[(base) + tslot++] = clock64(); } while (0)
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [w] TMA -> MMA: Q_w, dO_w landed
-  uint64_t* bar_kv = bar_q + 2;                                       // [j] TMA -> MMA: K_j, V_j landed
-  uint64_t* empty_kv0 = bar_kv + 2;                                   // MMA -> TMA: K_0, V_0 no longer read
-  uint64_t* empty_rest = empty_kv0 + 1;                               // MMA -> TMA: the item's last MMA retired
-  uint64_t* bar_s = empty_rest + 1;                                   // [w] MMA -> WG: S_wj ready
-  uint64_t* bar_p = bar_s + 2;                                        // [w] WG -> MMA: P_wj in smem
-  uint64_t* bar_dp = bar_p + 2;                                       // [w] MMA -> WG: dP_wj ready, P_wj consumed
-  uint64_t* bar_ds = bar_dp + 2;                                      // [w] WG -> MMA: dS_wj in smem
-  uint64_t* bar_drain = bar_ds + 2;                                   // MMA -> WGs: every MMA of kv tile j retired
-  uint64_t* bar_drained = bar_drain + 1;                              // WGs -> MMA: accumulators read out
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_drained + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = B * H;
-  const uint32_t eff1 = roundup16(N - TILE);   // rows of q tile 1 == columns of kv tile 1, rounded up to the MMA K step
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_q[i], 1);
-      mbar_init(&bar_kv[i], 1);
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 4);
-      mbar_init(&bar_dp[i], 1);
-      mbar_init(&bar_ds[i], 4);
-    }
-    mbar_init(empty_kv0, 1);
-    mbar_init(empty_rest, 1);
-    mbar_init(bar_drain, 1);
-    mbar_init(bar_drained, 8);
-    fence_mbar_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
-
-  if (warp == 9) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      tma_prefetch_desc(&tm_do);
-      int n = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int h = it % H, b = it / H;
-        if (n > 0) mbar_wait(empty_kv0, (n - 1) & 1);
-        mbar_arrive_expect_tx(&bar_kv[0], 2 * TILE_BYTES);
-        tma_load_3d(smem + L::KV_OFF, &tm_qkv, &bar_kv[0], (H + h) * HD, 0, b);
-        tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, &bar_kv[0], (2 * H + h) * HD, 0, b);
-        if (n > 0) mbar_wait(empty_rest, (n - 1) & 1);
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          mbar_arrive_expect_tx(&bar_q[w], 2 * TILE_BYTES);
-          tma_load_3d(smem + L::QDO_OFF + w * 2 * TILE_BYTES, &tm_qkv, &bar_q[w], h * HD, w * TILE, b);
-          tma_load_3d(smem + L::QDO_OFF + w * 2 * TILE_BYTES + TILE_BYTES, &tm_do, &bar_q[w], h * HD, w * TILE, b);
-        }
-        mbar_arrive_expect_tx(&bar_kv[1], 2 * TILE_BYTES);
-        tma_load_3d(smem + L::KV_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_kv[1], (H + h) * HD, TILE, b);
-        tma_load_3d(smem + L::KV_OFF + 3 * TILE_BYTES, &tm_qkv, &bar_kv[1], (2 * H + h) * HD, TILE, b);
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------ MMA issuer (whole warp runs the loop, one elected lane issues) ------------------------------
-    const uint32_t sQDO = smem_u32(smem + L::QDO_OFF), sKV = smem_u32(smem + L::KV_OFF), sPDS = smem_u32(smem + L::PDS_OFF);
-    const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);    // A, B MN-major: P^T dO, dS^T Q
-    const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);   // dS K
-    // S_wj = Q_w K_j^T (what == 0) or dP_wj = dO_w V_j^T (what == 1) into SdP_w
-    auto issue_qk = [&](int w, int j, int what, uint64_t* bar) {
-      const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
-      const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
-      const uint64_t adesc = umma_desc_kmajor(sQDO + (w * 2 + what) * TILE_BYTES);
-      const uint64_t bdesc = umma_desc_kmajor(sKV + (j * 2 + what) * TILE_BYTES);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_base + w * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k > 0);
-        umma_commit(bar);
-      }
-      __syncwarp();
-    };
-    int n = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
-        if (j == 0) {
-          mbar_wait(&bar_kv[0], n & 1);
-          for (int w = 0; w < 2; ++w) {
-            mbar_wait(&bar_q[w], n & 1);
-            tc_fence_after();
-            issue_qk(w, 0, 0, &bar_s[w]);
-            BWD3_STAMP(0);
-          }
-        }
-        if (n > 0 || j > 0) {
-          mbar_wait(bar_drained, j ^ 1);   // dV / dK (and, across items, dQ) of the previous kv tile were read out
-          tc_fence_after();
-        }
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
-          const uint64_t pdesc = umma_desc_mnmajor(sPDS + w * 2 * TILE_BYTES, TILE_BYTES);
-          const uint64_t dodesc = umma_desc_mnmajor(sQDO + (w * 2 + 1) * TILE_BYTES, TILE_BYTES);
-          mbar_wait(&bar_p[w], j);
-          BWD3_STAMP(0);
-          tc_fence_after();
-          if (elect_one()) {   // dV_j += P_w^T dO_w
-            for (int k = 0; k < (int)q_eff / 16; ++k)
-              umma_bf16_ss(tm_dv, pdesc + (uint64_t)(k * 128), dodesc + (uint64_t)(k * 128), idesc_t, (w > 0 || k > 0));
-          }
-          __syncwarp();
-          issue_qk(w, j, 1, &bar_dp[w]);   // dP_wj over S_wj (warpgroup w has turned S into P)
-          BWD3_STAMP(0);
-        }
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
-          const uint32_t sDS = sPDS + w * 2 * TILE_BYTES;
-          const uint64_t dsdesc_t = umma_desc_mnmajor(sDS, TILE_BYTES);
-          const uint64_t qdesc = umma_desc_mnmajor(sQDO + w * 2 * TILE_BYTES, TILE_BYTES);
-          const uint64_t dsdesc_k = umma_desc_kmajor(sDS);
-          const uint64_t kdesc = umma_desc_mnmajor(sKV + j * 2 * TILE_BYTES, TILE_BYTES);
-          mbar_wait(&bar_ds[w], j);
-          BWD3_STAMP(0);
-          tc_fence_after();
-          if (elect_one()) {
-            for (int k = 0; k < (int)q_eff / 16; ++k)   // dK_j += dS_w^T Q_w
-              umma_bf16_ss(tm_dk, dsdesc_t + (uint64_t)(k * 128), qdesc + (uint64_t)(k * 128), idesc_t, (w > 0 || k > 0));
-            for (int k = 0; k < (int)n_eff / 16; ++k)   // dQ_w += dS_w K_j
-              umma_bf16_ss(tm_dq + w * HD, dsdesc_k + (uint64_t)((k >> 2) * (TILE_BYTES >> 4) + (k & 3) * 2), kdesc + (uint64_t)(k * 128),
-                           idesc_q, (j > 0 || k > 0));
-          }
-          __syncwarp();
-          if (j == 0) {
-            if (w == 0) mbar_wait(&bar_kv[1], n & 1);
-            issue_qk(w, 1, 0, &bar_s[w]);   // SdP_w is free: warpgroup w read dP before it wrote dS
-          }
-          BWD3_STAMP(0);
-        }
-        if (elect_one()) {
-          umma_commit(bar_drain);
-          if (j == 0) umma_commit(empty_kv0);
-          else umma_commit(empty_rest);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    // ------------------------------ warpgroup w: rows of q tile w ------------------------------
-    const int w = warp >> 2, r = threadIdx.x & 127;
-    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tm_sdp = tmem_base + w * 128 + lane_addr;
-    uint8_t* sPDS = smem + L::PDS_OFF + w * 2 * TILE_BYTES;
-    uint8_t* wst = smem + L::STG_OFF + warp * 4096;
-    const int q = w * TILE + r;
-    const bool row_ok = q < N;
-    const uint32_t q_eff = w == 0 ? (uint32_t)TILE : eff1;
-    const bool warp_active = (uint32_t)((warp & 3) * 32) < q_eff;   // some row of this warp is read by the dV / dK MMAs
-    const float c2 = scale * LOG2E;
-    const int D = H * HD;
-    int n = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int h = it % H, b = it / H;
-      float my_lse2 = 0.f, my_ds = 0.f;   // rows >= N: P = 2^S stays finite, dS = 0
-      if (row_ok) {
-        my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
-        my_ds = dsum[((long long)b * H + h) * N + q] * scale;
-      }
-      for (int j = 0; j < 2; ++j) {
-        const uint32_t n_eff = j == 0 ? (uint32_t)TILE : eff1;
-        const int nch = (int)(n_eff + 31) / 32;   // 32-column chunks (the last one may be half)
-
-        // ---- S -> P ----
-        mbar_wait(&bar_s[w], j);
-        tc_fence_after();
-        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
-        if (warp_active) {
-          uint32_t cur[32], nxt[32];
-          tmem_ld_32x32(tm_sdp, cur);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nch) {
-              if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, nxt);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  pk[i] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(cur[g * 8 + 2 * i]), c2, -my_lse2)),
-                                      ex2_approx(fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), c2, -my_lse2)));
-                st_swz(sPDS, r, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-              }
-              if (c + 1 < nch) {
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
-              }
-            }
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_p[w]);
-        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
-
-        // ---- dP -> dS (over P) ----
-        mbar_wait(&bar_dp[w], j);
-        tc_fence_after();
-        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
-        if (warp_active) {
-          uint32_t cur[32], nxt[32];
-          tmem_ld_32x32(tm_sdp, cur);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nch) {
-              if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, nxt);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint8_t* slot = sPDS + ((c * 4 + g) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + g) & 7) ^ (r & 7)) << 4);
-                const uint4 pu = *reinterpret_cast<const uint4*>(slot);
-                const uint32_t pw[4] = {pu.x, pu.y, pu.z, pu.w};
-                uint32_t ds[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 pp = unpack_bf16x2(pw[i]);
-                  ds[i] = pack_bf16x2(pp.x * fmaf(__uint_as_float(cur[g * 8 + 2 * i]), scale, -my_ds),
-                                      pp.y * fmaf(__uint_as_float(cur[g * 8 + 2 * i + 1]), scale, -my_ds));
-                }
-                *reinterpret_cast<uint4*>(slot) = make_uint4(ds[0], ds[1], ds[2], ds[3]);
-              }
-              if (c + 1 < nch) {
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
-              }
-            }
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_ds[w]);
-        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
-
-        // ---- drain dV_j (warpgroup 0) / dK_j (warpgroup 1), and dQ_w after the last kv tile ----
-        mbar_wait(bar_drain, j);
-        tc_fence_after();
-        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
-        {
-          const int kv0 = j * TILE + (warp & 3) * 32;   // first kv row of this warp
-          if (kv0 < N) {
-            uint32_t a0[32], a1[32];
-            const uint32_t src = (w == 0 ? tm_dv : tm_dk) + lane_addr;
-            tmem_ld_32x32(src, a0);
-            tmem_ld_32x32(src + 32, a1);
-            tmem_ld_wait();
-            store_rows_coalesced(wst, lane, a0, a1, dqkv + ((long long)b * N + kv0) * (3 * D) + ((w == 0 ? 2 : 1) * H + h) * HD,
-                                 3 * D, N - kv0);
-          }
-          const int q0 = w * TILE + (warp & 3) * 32;
-          if (j == 1 && q0 < N) {
-            uint32_t a0[32], a1[32];
-            tmem_ld_32x32(tm_dq + w * HD + lane_addr, a0);
-            tmem_ld_32x32(tm_dq + w * HD + lane_addr + 32, a1);
-            tmem_ld_wait();
-            store_rows_coalesced(wst, lane, a0, a1, dqkv + ((long long)b * N + q0) * (3 * D) + h * HD, 3 * D, N - q0);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_drained);
-        if ((warp & 3) == 0) BWD3_STAMP(32 + 16 * w);
-      }
-    }
-  }
-#undef BWD3_STAMP
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // ================================================================================================
-// Backward, ping-pong variant of attn_bwd3 (same roles, same smem / TMEM layout; 128 < N <= 256).
+// attn_bwd4: the ping-pong schedule on the roles and smem / TMEM layout above (128 < N <= 256).
 //
-// attn_bwd3 keeps the two warpgroups in lockstep (both do P, then both wait for the MMAs, then both do dS ...), so
-// the tensor core idles while the CUDA cores work and vice versa.  Here warpgroup 1 runs half a step behind
+// Keeping the two warpgroups in lockstep (both do P, then both wait for the MMAs, then both do dS ...) leaves
+// the tensor core idle while the CUDA cores work and vice versa.  Here warpgroup 1 runs half a step behind
 // warpgroup 0: while one warpgroup turns S into P (MUFU), the other turns dP into dS (FP32 pipe), and the MMA
 // warp serves them alternately in the fixed event order E1..E8 below.  What makes that possible with single
 // dV / dK accumulators (TMEM is full) is WHEN they are read out:
@@ -2501,19 +1339,19 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         const int h = it % H, b = it / H;
         if (n > 0) mbar_wait(empty_kv0, (n - 1) & 1);
         mbar_arrive_expect_tx(&bar_kv[0], 2 * TILE_BYTES);
-        tma_load_3d(smem + L::KV_OFF, &tm_qkv, &bar_kv[0], (H + h) * HD, 0, b);
-        tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, &bar_kv[0], (2 * H + h) * HD, 0, b);
+        tma_load_head(smem + L::KV_OFF, &tm_qkv, &bar_kv[0], H + h, 0, b);
+        tma_load_head(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, &bar_kv[0], 2 * H + h, 0, b);
         if (n > 0) mbar_wait(empty_q0, (n - 1) & 1);
         mbar_arrive_expect_tx(&bar_q[0], 2 * TILE_BYTES);
-        tma_load_3d(smem + L::QDO_OFF, &tm_qkv, &bar_q[0], h * HD, 0, b);
-        tma_load_3d(smem + L::QDO_OFF + TILE_BYTES, &tm_do, &bar_q[0], h * HD, 0, b);
+        tma_load_head(smem + L::QDO_OFF, &tm_qkv, &bar_q[0], h, 0, b);
+        tma_load_head(smem + L::QDO_OFF + TILE_BYTES, &tm_do, &bar_q[0], h, 0, b);
         if (n > 0) mbar_wait(empty_rest, (n - 1) & 1);
         mbar_arrive_expect_tx(&bar_q[1], 2 * TILE_BYTES);
-        tma_load_3d(smem + L::QDO_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_q[1], h * HD, TILE, b);
-        tma_load_3d(smem + L::QDO_OFF + 3 * TILE_BYTES, &tm_do, &bar_q[1], h * HD, TILE, b);
+        tma_load_head(smem + L::QDO_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_q[1], h, TILE, b);
+        tma_load_head(smem + L::QDO_OFF + 3 * TILE_BYTES, &tm_do, &bar_q[1], h, TILE, b);
         mbar_arrive_expect_tx(&bar_kv[1], 2 * TILE_BYTES);
-        tma_load_3d(smem + L::KV_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_kv[1], (H + h) * HD, TILE, b);
-        tma_load_3d(smem + L::KV_OFF + 3 * TILE_BYTES, &tm_qkv, &bar_kv[1], (2 * H + h) * HD, TILE, b);
+        tma_load_head(smem + L::KV_OFF + 2 * TILE_BYTES, &tm_qkv, &bar_kv[1], H + h, TILE, b);
+        tma_load_head(smem + L::KV_OFF + 3 * TILE_BYTES, &tm_qkv, &bar_kv[1], 2 * H + h, TILE, b);
       }
     }
   } else if (warp == 8) {
@@ -2676,7 +1514,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
         fence_proxy_async_smem();
         __syncwarp();
         if (elect_one()) {
-          tma_store_3d(&tm_dqkv, wst, (which * H + h) * HD, row_first, b);
+          tma_store_head(&tm_dqkv, wst, which * H + h, row_first, b);
           tma_store_commit();
         }
         __syncwarp();
@@ -2858,7 +1696,7 @@ struct BwdStreamSmem {
 __global__ void __launch_bounds__(128)
 attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                        const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                       float* __restrict__ dq32, int N, int H, float scale) {
+                       float* __restrict__ dq32, int N, int H, int hd, float scale) {
   using L = BwdStreamSmem;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -2907,8 +1745,8 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   auto load_q = [&](int i) {   // thread 0 only
     const int buf = i & 1;
     mbar_arrive_expect_tx(&bar_q[buf], 2 * TILE_BYTES);
-    tma_load_3d(smem + L::QDO_OFF + buf * 2 * TILE_BYTES, &tm_qkv, &bar_q[buf], h * HD, i * TILE, b);
-    tma_load_3d(smem + L::QDO_OFF + buf * 2 * TILE_BYTES + TILE_BYTES, &tm_do, &bar_q[buf], h * HD, i * TILE, b);
+    tma_load_head(smem + L::QDO_OFF + buf * 2 * TILE_BYTES, &tm_qkv, &bar_q[buf], h, i * TILE, b);
+    tma_load_head(smem + L::QDO_OFF + buf * 2 * TILE_BYTES + TILE_BYTES, &tm_do, &bar_q[buf], h, i * TILE, b);
   };
   // S = Q_i K_j^T and dP = dO_i V_j^T (warp 0, uniform control flow, one elected lane)
   auto issue_s_dp = [&](int i) {
@@ -2930,8 +1768,8 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_arrive_expect_tx(bar_kv, 2 * TILE_BYTES);
-    tma_load_3d(smem + L::KV_OFF, &tm_qkv, bar_kv, (H + h) * HD, j * TILE, b);
-    tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, (2 * H + h) * HD, j * TILE, b);
+    tma_load_head(smem + L::KV_OFF, &tm_qkv, bar_kv, H + h, j * TILE, b);
+    tma_load_head(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, 2 * H + h, j * TILE, b);
     load_q(0);
     if (nt > 1) load_q(1);
   }
@@ -3051,11 +1889,11 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     tmem_ld_32x32(tm_dv + lane_addr, a0);
     tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
     tmem_ld_wait();
-    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (2 * H + h) * HD, a0, a1);
+    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * hd) + (2 * H + h) * hd, a0, a1, hd);
     tmem_ld_32x32(tm_dk + lane_addr, a0);
     tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
     tmem_ld_wait();
-    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * HD) + (H + h) * HD, a0, a1);
+    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * hd) + (H + h) * hd, a0, a1, hd);
   }
   tc_fence_before();
   __syncthreads();
@@ -3065,327 +1903,28 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   }
 }
 
-// ================================================================================================
-// Backward for 256 < N <= 640, ping-pong variant of the streaming kernel: still one CTA per (b, h, kv tile j) with K_j /
-// V_j resident and dV_j / dK_j accumulating in TMEM over all q tiles, but the q tiles are split between two warpgroups
-// (group g takes tiles g, g+2, ...; thread = row) that run out of phase like in attn_bwd4: S and dP share one TMEM
-// buffer per group (S -> P, then dP -> dS over P in smem), warp 8 issues every MMA from two in-order event queues
-// (S_t | P_t -> dV +=, dP_t | dS_t -> dK +=, dQ_t) served in arrival order, warp 9 streams Q_i / dO_i through two
-// buffers per group.  dQ_ij is produced into a per-group TMEM scratch tile, read out and red.add'ed into the fp32
-// workspace while the MMA warp already works for the other group.
-// TMEM: SdP_0 [0,128) | SdP_1 [128,256) | dV_j [256,320) | dK_j [320,384) | dQ scratch 0 [384,448) | 1 [448,512)
-// smem: K_j V_j (32K) | group g: 2 x (Q_i dO_i) (2 x 64K) | PdS_0 PdS_1 (64K) | barriers
-// ================================================================================================
-struct Bwd5Smem {
-  static constexpr uint32_t KV_OFF = 0;
-  static constexpr uint32_t QDO_OFF = 2 * TILE_BYTES;    // [g][buffer][Q, dO]
-  static constexpr uint32_t PDS_OFF = 10 * TILE_BYTES;   // [g][2 chunks of 64 kv columns]
-  static constexpr uint32_t BAR_OFF = 14 * TILE_BYTES;
-  static constexpr uint32_t BYTES = BAR_OFF + 256;
-};
-
-__global__ void __launch_bounds__(BWD3_THREADS, 1)
-attn_bwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                 const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                 float* __restrict__ dq32, int N, int H, float scale) {
-  using L = Bwd5Smem;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* q_full = bar_kv + 1;      // [g][buf]
-  uint64_t* q_empty = q_full + 4;     // [g][buf]
-  uint64_t* bar_s = q_empty + 4;      // [g]
-  uint64_t* bar_p = bar_s + 2;        // [g] count 4
-  uint64_t* bar_dp = bar_p + 2;       // [g]
-  uint64_t* bar_ds = bar_dp + 2;      // [g] count 4
-  uint64_t* bar_dq = bar_ds + 2;      // [g] MMA -> group: dQ scratch ready
-  uint64_t* dq_free = bar_dq + 2;     // [g] count 4, group -> MMA: scratch read out
-  uint64_t* bar_final = dq_free + 2;  // MMA -> groups: dV_j, dK_j final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_final + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int QT = (N + TILE - 1) / TILE;
-  const int kvn = min(TILE, N - j * TILE);
-  const uint32_t n_eff = roundup16(kvn);
-  const int nch = (int)(n_eff + 31) / 32;
-  const int ntile[2] = {(QT + 1) / 2, QT / 2};   // q tiles of group 0 / 1
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0) {
-    mbar_init(bar_kv, 1);
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_p[i], 4);
-      mbar_init(&bar_dp[i], 1);
-      mbar_init(&bar_ds[i], 4);
-      mbar_init(&bar_dq[i], 1);
-      mbar_init(&dq_free[i], 4);
-    }
-    mbar_init(bar_final, 1);
-    fence_mbar_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_dv = tmem_base + 256, tm_dk = tmem_base + 320, tm_dq = tmem_base + 384;
-
-  if (warp == 9) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      tma_prefetch_desc(&tm_do);
-      mbar_arrive_expect_tx(bar_kv, 2 * TILE_BYTES);
-      tma_load_3d(smem + L::KV_OFF, &tm_qkv, bar_kv, (H + h) * HD, j * TILE, b);
-      tma_load_3d(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, (2 * H + h) * HD, j * TILE, b);
-      for (int t = 0; t < ntile[0]; ++t) {
-        for (int g = 0; g < 2; ++g) {
-          if (t >= ntile[g]) continue;
-          const int buf = t & 1, i = g + 2 * t;
-          if (t >= 2) mbar_wait(&q_empty[g * 2 + buf], ((t >> 1) & 1) ^ 1);
-          uint8_t* dst = smem + L::QDO_OFF + (g * 2 + buf) * 2 * TILE_BYTES;
-          mbar_arrive_expect_tx(&q_full[g * 2 + buf], 2 * TILE_BYTES);
-          tma_load_3d(dst, &tm_qkv, &q_full[g * 2 + buf], h * HD, i * TILE, b);
-          tma_load_3d(dst + TILE_BYTES, &tm_do, &q_full[g * 2 + buf], h * HD, i * TILE, b);
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ------------------------------ MMA issuer: two in-order event queues served in arrival order ------------------------------
-    const uint32_t sKV = smem_u32(smem + L::KV_OFF), sQDO = smem_u32(smem + L::QDO_OFF), sPDS = smem_u32(smem + L::PDS_OFF);
-    const uint32_t idesc_s = umma_idesc(TILE, n_eff, 1, false, false);
-    const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);    // A, B MN-major: P^T dO, dS^T Q
-    const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);   // dS K
-    const uint64_t kd = umma_desc_kmajor(sKV), vd = umma_desc_kmajor(sKV + TILE_BYTES), k_mn = umma_desc_mnmajor(sKV, TILE_BYTES);
-    int ev[2] = {0, 0};                 // queue position of group g: 3 * tile + {0: S, 1: P -> dV, dP, 2: dS -> dK, dQ}
-    bool dv_init = false, dk_init = false;
-    mbar_wait(bar_kv, 0);
-    while (ev[0] < 3 * ntile[0] || ev[1] < 3 * ntile[1]) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (ev[g] >= 3 * ntile[g]) continue;
-        const int t = ev[g] / 3, k = ev[g] - 3 * t, buf = t & 1;
-        const uint32_t par = t & 1;
-        const uint32_t sQ = sQDO + (g * 2 + buf) * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES, sP = sPDS + g * 2 * TILE_BYTES;
-        const uint32_t q_eff = roundup16(min(TILE, N - (g + 2 * t) * TILE));
-        bool ready;
-        if (k == 0) ready = mbar_test(&q_full[g * 2 + buf], (t >> 1) & 1);
-        else if (k == 1) ready = mbar_test(&bar_p[g], par) && (g == 0 || dv_init);
-        else ready = mbar_test(&bar_ds[g], par) && (t == 0 || mbar_test(&dq_free[g], (t - 1) & 1)) && (g == 0 || dk_init);
-        if (!ready) continue;
-        tc_fence_after();
-        if (k == 0) {
-          const uint64_t qd = umma_desc_kmajor(sQ);
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tmem_base + g * 128, qd + (uint64_t)(kk * 2), kd + (uint64_t)(kk * 2), idesc_s, kk > 0);
-            umma_commit(&bar_s[g]);
-          }
-        } else if (k == 1) {
-          const uint64_t p_mn = umma_desc_mnmajor(sP, TILE_BYTES), do_mn = umma_desc_mnmajor(sDO, TILE_BYTES), dod = umma_desc_kmajor(sDO);
-          const uint32_t acc0 = dv_init ? 1u : 0u;
-          if (elect_one()) {
-            for (int kk = 0; kk < (int)q_eff / 16; ++kk)
-              umma_bf16_ss(tm_dv, p_mn + (uint64_t)(kk * 128), do_mn + (uint64_t)(kk * 128), idesc_t, kk > 0 ? 1u : acc0);
-#pragma unroll
-            for (int kk = 0; kk < HD / 16; ++kk) umma_bf16_ss(tmem_base + g * 128, dod + (uint64_t)(kk * 2), vd + (uint64_t)(kk * 2), idesc_s, kk > 0);
-            umma_commit(&bar_dp[g]);
-          }
-          dv_init = true;
-        } else {
-          const uint64_t ds_mn = umma_desc_mnmajor(sP, TILE_BYTES), q_mn = umma_desc_mnmajor(sQ, TILE_BYTES), ds_k = umma_desc_kmajor(sP);
-          const uint32_t acc0 = dk_init ? 1u : 0u;
-          if (elect_one()) {
-            for (int kk = 0; kk < (int)q_eff / 16; ++kk)
-              umma_bf16_ss(tm_dk, ds_mn + (uint64_t)(kk * 128), q_mn + (uint64_t)(kk * 128), idesc_t, kk > 0 ? 1u : acc0);
-            for (int kk = 0; kk < (int)n_eff / 16; ++kk)
-              umma_bf16_ss(tm_dq + g * HD, ds_k + (uint64_t)((kk >> 2) * (TILE_BYTES >> 4) + (kk & 3) * 2), k_mn + (uint64_t)(kk * 128),
-                           idesc_q, kk > 0);
-            umma_commit(&bar_dq[g]);
-            umma_commit(&q_empty[g * 2 + buf]);
-          }
-          dk_init = true;
-        }
-        __syncwarp();
-        ++ev[g];
-      }
-    }
-    if (elect_one()) umma_commit(bar_final);
-    __syncwarp();
-  } else {
-    // ------------------------------ warpgroup g: rows of its q tiles ------------------------------
-    const int g = warp >> 2, r = threadIdx.x & 127;
-    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tm_sdp = tmem_base + g * 128 + lane_addr;
-    uint8_t* sPDS = smem + L::PDS_OFF + g * 2 * TILE_BYTES;
-    const float c2 = scale * LOG2E;
-    const int D = H * HD;
-    for (int t = 0; t < ntile[g]; ++t) {
-      const int i = g + 2 * t;
-      const int qn = min(TILE, N - i * TILE);
-      const uint32_t q_eff = roundup16(qn);
-      const bool warp_active = (uint32_t)((warp & 3) * 32) < q_eff;
-      const int q = i * TILE + r;
-      const bool row_ok = r < qn;
-      float my_lse2 = 0.f, my_ds = 0.f;   // rows >= N: P = 2^S stays finite, dS = 0
-      if (row_ok) {
-        my_lse2 = lse[((long long)b * H + h) * N + q] * LOG2E;
-        my_ds = dsum[((long long)b * H + h) * N + q] * scale;
-      }
-      // ---- S -> P ----
-      mbar_wait(&bar_s[g], t & 1);
-      tc_fence_after();
-      if (warp_active) {
-        uint32_t ra[32], rb[32];
-        auto p_chunk = [&](const uint32_t (&v)[32], int c) {
-#pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-              pk[x] = pack_bf16x2(ex2_approx(fmaf(__uint_as_float(v[gg * 8 + 2 * x]), c2, -my_lse2)),
-                                  ex2_approx(fmaf(__uint_as_float(v[gg * 8 + 2 * x + 1]), c2, -my_lse2)));
-            st_swz(sPDS, r, c * 4 + gg, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-          }
-        };
-        tmem_ld_32x32(tm_sdp, ra);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          if (c < nch) {
-            if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, rb);
-            p_chunk(ra, c);
-            if (c + 1 < nch) {
-              tmem_ld_wait();
-              if (c + 2 < nch) tmem_ld_32x32(tm_sdp + (c + 2) * 32, ra);
-              p_chunk(rb, c + 1);
-              if (c + 2 < nch) tmem_ld_wait();
-            }
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[g]);
-
-      // ---- dP -> dS (over P) ----
-      mbar_wait(&bar_dp[g], t & 1);
-      tc_fence_after();
-      if (warp_active) {
-        uint32_t ra[32], rb[32];
-        auto ds_chunk = [&](const uint32_t (&v)[32], int c) {
-          uint4 pall[4];
-#pragma unroll
-          for (int gg = 0; gg < 4; ++gg)
-            pall[gg] = *reinterpret_cast<const uint4*>(sPDS + ((c * 4 + gg) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + gg) & 7) ^ (r & 7)) << 4));
-#pragma unroll
-          for (int gg = 0; gg < 4; ++gg) {
-            const uint32_t pw[4] = {pall[gg].x, pall[gg].y, pall[gg].z, pall[gg].w};
-            uint32_t ds[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-              const float2 pp = unpack_bf16x2(pw[x]);
-              ds[x] = pack_bf16x2(pp.x * fmaf(__uint_as_float(v[gg * 8 + 2 * x]), scale, -my_ds),
-                                  pp.y * fmaf(__uint_as_float(v[gg * 8 + 2 * x + 1]), scale, -my_ds));
-            }
-            *reinterpret_cast<uint4*>(sPDS + ((c * 4 + gg) >> 3) * TILE_BYTES + r * 128 + ((((c * 4 + gg) & 7) ^ (r & 7)) << 4)) =
-                make_uint4(ds[0], ds[1], ds[2], ds[3]);
-          }
-        };
-        tmem_ld_32x32(tm_sdp, ra);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; c += 2) {
-          if (c < nch) {
-            if (c + 1 < nch) tmem_ld_32x32(tm_sdp + (c + 1) * 32, rb);
-            ds_chunk(ra, c);
-            if (c + 1 < nch) {
-              tmem_ld_wait();
-              if (c + 2 < nch) tmem_ld_32x32(tm_sdp + (c + 2) * 32, ra);
-              ds_chunk(rb, c + 1);
-              if (c + 2 < nch) tmem_ld_wait();
-            }
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_ds[g]);
-
-      // ---- dQ_ij: scratch -> registers (hand the scratch back) -> red.add into the fp32 workspace ----
-      mbar_wait(&bar_dq[g], t & 1);
-      tc_fence_after();
-      uint32_t a0[32], a1[32];
-      tmem_ld_32x32(tm_dq + g * HD + lane_addr, a0);
-      tmem_ld_32x32(tm_dq + g * HD + lane_addr + 32, a1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&dq_free[g]);
-      if (row_ok) {
-        float* dst = dq32 + ((long long)b * N + q) * D + h * HD;
-#pragma unroll
-        for (int gg = 0; gg < 8; ++gg) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + gg * 4), "f"(__uint_as_float(a0[gg * 4])),
-                       "f"(__uint_as_float(a0[gg * 4 + 1])), "f"(__uint_as_float(a0[gg * 4 + 2])), "f"(__uint_as_float(a0[gg * 4 + 3]))
-                       : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 32 + gg * 4), "f"(__uint_as_float(a1[gg * 4])),
-                       "f"(__uint_as_float(a1[gg * 4 + 1])), "f"(__uint_as_float(a1[gg * 4 + 2])), "f"(__uint_as_float(a1[gg * 4 + 3]))
-                       : "memory");
-        }
-      }
-    }
-    // ---- dV_j (group 0) / dK_j (group 1) ----
-    mbar_wait(bar_final, 0);
-    tc_fence_after();
-    {
-      uint32_t a0[32], a1[32];
-      const int kv = j * TILE + r;
-      const uint32_t src = (g == 0 ? tm_dv : tm_dk) + lane_addr;
-      tmem_ld_32x32(src, a0);
-      tmem_ld_32x32(src + 32, a1);
-      tmem_ld_wait();
-      if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * D) + ((g == 0 ? 2 : 1) * H + h) * HD, a0, a1);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// dqkv[row, 0:D] = bf16(dq32[row, 0:D])  (row pitch of dqkv is 3*D)
-__global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int D) {
+// dqkv[row, h * hd + c] = bf16(dq32[row, h * 64 + c]) for c < hd: the fp32 dQ workspace keeps the padded 64-wide heads of
+// the tiles, dqkv is the gradient of the qkv Linear output (row pitch 3 * H * hd)
+__global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int H, int hd) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int dv = D / 8;
-  if (idx >= rows * dv) return;
-  const long long row = idx / dv;
-  const int c = (int)(idx % dv) * 8;
-  const float4 a = *reinterpret_cast<const float4*>(dq32 + row * D + c);
-  const float4 b2 = *reinterpret_cast<const float4*>(dq32 + row * D + c + 4);
+  const int per_row = H * (hd / 8);
+  if (idx >= rows * per_row) return;
+  const long long row = idx / per_row;
+  const int rem = (int)(idx - row * per_row);
+  const int h = rem / (hd / 8), c = (rem - h * (hd / 8)) * 8;
+  const float* src = dq32 + (row * H + h) * HD + c;
+  const float4 a = *reinterpret_cast<const float4*>(src);
+  const float4 b2 = *reinterpret_cast<const float4*>(src + 4);
   uint4 u;
   u.x = pack_bf16x2(a.x, a.y);
   u.y = pack_bf16x2(a.z, a.w);
   u.z = pack_bf16x2(b2.x, b2.y);
   u.w = pack_bf16x2(b2.z, b2.w);
-  *reinterpret_cast<uint4*>(dqkv + row * 3 * D + c) = u;
+  *reinterpret_cast<uint4*>(dqkv + row * 3 * H * hd + h * hd + c) = u;
 }
 
 template <int T>
-int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
+int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
   auto kern = attn_fwd_kernel<T>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -3394,42 +1933,54 @@ int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H
     attr_set = true;
   }
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  kern<<<grid, 128, FwdSmem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, scale, g_trace_buf);
+  kern<<<grid, 128, FwdSmem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, hd, scale, g_trace_buf);
   return vitk_check_launch("attn_fwd");
 }
+
+// The attention tensors are mapped for TMA as (head_dim, head slot, token, image): a [rows][64] box of one head slot
+// arrives as a 128-byte-swizzled tile whose columns >= head_dim are zero-filled (and are clipped again on the way out),
+// so head_dim < 64 (my_vit_mini: 48) runs on the same 64-wide tiles; the zero columns add nothing to Q K^T or dO V^T
+// and produce zero columns of O / dQ / dK / dV.  slots = 3 H for qkv / dqkv, H for out / dout.
+int make_head_tmap(CUtensorMap* tm, const void* base, int slots, int hd, int N, int B, int box_rows) {
+  return vitk_make_tmap_4d(tm, base, 2, (uint64_t)hd, (uint64_t)slots, (uint64_t)N, (uint64_t)B, (uint64_t)hd,
+                           (uint64_t)slots * hd, (uint64_t)N * slots * hd, HD, 1, (uint32_t)box_rows, 1);
+}
+
+bool head_dim_ok(int hd) { return hd >= 16 && hd <= HD && hd % 8 == 0; }
 
 }  // namespace
 
 extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t head_dim,
                              float scale, void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_fwd: bad shape B=%d N=%d H=%d", B, N, H);
-  VITK_REQUIRE(head_dim == HD, VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d (only 64 is built)", head_dim);
+  VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d (built for multiples of 8 in [16, 64])", head_dim);
   VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_fwd: N=%d > %d", N, FWD_MAX_T * TILE);
   VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, VITK_ERR_ALIGN, "attn_fwd: unaligned");
-  CUtensorMap tm;
-  int rc = vitk_make_tmap_3d(&tm, qkv, 2, (uint64_t)3 * H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)3 * H * HD,
-                             (uint64_t)N * 3 * H * HD, HD, TILE, 1);
+  const int hd = head_dim;
+  CUtensorMap tm, tm_out;
+  int rc = make_head_tmap(&tm, qkv, 3 * H, hd, N, B, TILE);
   if (rc) return rc;
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
-  // VITK_ATTN_FWD: unset = warp-specialised persistent kernel (one thread per row) for 128 < N <= 256, tiled kernel
-  // otherwise; "1" = tiled one-CTA-per-q-tile kernel everywhere; "2" / "3" = older persistent kernels (for comparison)
+  // VITK_ATTN_FWD: unset = warp-specialised persistent kernel (one thread per row) for 128 < N <= 256, the flash-style
+  // kv-loop kernel above that, the tiled one-CTA-per-q-tile kernel for N <= 128; "1" = tiled kernel everywhere;
+  // "5" = the kv-loop kernel also at 128 < N <= 256 (comparison)
   static const int variant = [] {
     const char* e = getenv("VITK_ATTN_FWD");
     return e ? atoi(e) : 0;
   }();
-  if (variant == 0 && T == 2) return launch_fwd4(tm, out, lse, B, N, H, scale, s);
-  if (variant == 0 && T > 2) return launch_fwd5(tm, out, lse, B, N, H, scale, s);
-  if (variant == 3 && T == 2) return launch_fwd3(tm, out, lse, B, N, H, scale, s);
-  if (variant == 5 && T == 2) return launch_fwd5(tm, out, lse, B, N, H, scale, s);   // flash-style kv loop at short N (comparison)
-  if (variant == 2 && T == 1) return launch_fwd2<1>(tm, out, lse, B, N, H, scale, s);
-  if (variant == 2 && T == 2) return launch_fwd2<2>(tm, out, lse, B, N, H, scale, s);
+  if ((variant == 0 || variant == 5) && T >= 2) {
+    rc = make_head_tmap(&tm_out, out, H, hd, N, B, TILE);
+    if (rc) return rc;
+    if (variant == 0 && T == 2) return launch_fwd4(tm, tm_out, lse, B, N, H, scale, s);
+    return launch_fwd5(tm, tm_out, lse, B, N, H, scale, s);
+  }
   switch (T) {
-    case 1: return launch_fwd<1>(tm, out, lse, B, N, H, scale, s);
-    case 2: return launch_fwd<2>(tm, out, lse, B, N, H, scale, s);
-    case 3: return launch_fwd<3>(tm, out, lse, B, N, H, scale, s);
-    case 4: return launch_fwd<4>(tm, out, lse, B, N, H, scale, s);
-    default: return launch_fwd<5>(tm, out, lse, B, N, H, scale, s);
+    case 1: return launch_fwd<1>(tm, out, lse, B, N, H, hd, scale, s);
+    case 2: return launch_fwd<2>(tm, out, lse, B, N, H, hd, scale, s);
+    case 3: return launch_fwd<3>(tm, out, lse, B, N, H, hd, scale, s);
+    case 4: return launch_fwd<4>(tm, out, lse, B, N, H, hd, scale, s);
+    default: return launch_fwd<5>(tm, out, lse, B, N, H, hd, scale, s);
   }
 }
 
@@ -3440,9 +1991,10 @@ static int64_t dsum_bytes(int32_t B, int32_t N, int32_t H) {
 }
 
 extern "C" int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim) {
-  // D = rowsum(O * dO) [B, H, N] fp32, plus (N > 256) the fp32 dQ accumulator [B, N, H*hd]
+  // D = rowsum(O * dO) [B, H, N] fp32, plus (N > 256) the fp32 dQ accumulator [B, N, H, 64] (heads padded to the tile width)
+  (void)head_dim;
   int64_t bytes = dsum_bytes(B, N, H);
-  if (N > BWD_MAX_T * TILE) bytes += (int64_t)B * N * H * head_dim * (int64_t)sizeof(float);
+  if (N > BWD_MAX_T * TILE) bytes += (int64_t)B * N * H * HD * (int64_t)sizeof(float);
   return bytes;
 }
 
@@ -3450,28 +2002,21 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
                              void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
                              void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
-  VITK_REQUIRE(head_dim == HD, VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (only 64 is built)", head_dim);
+  VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (built for multiples of 8 in [16, 64])", head_dim);
   VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_bwd: N=%d > %d", N, FWD_MAX_T * TILE);
   VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
                VITK_ERR_ALIGN, "attn_bwd: unaligned");
+  const int hd = head_dim;
   CUtensorMap tm_qkv, tm_do;
-  int rc = vitk_make_tmap_3d(&tm_qkv, qkv, 2, (uint64_t)3 * H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)3 * H * HD,
-                             (uint64_t)N * 3 * H * HD, HD, TILE, 1);
+  int rc = make_head_tmap(&tm_qkv, qkv, 3 * H, hd, N, B, TILE);
   if (rc) return rc;
-  rc = vitk_make_tmap_3d(&tm_do, dout, 2, (uint64_t)H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)H * HD, (uint64_t)N * H * HD,
-                         HD, TILE, 1);
+  rc = make_head_tmap(&tm_do, dout, H, hd, N, B, TILE);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdSmem::BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd2Smem::BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
-    if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd5Smem::BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -3485,61 +2030,41 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
   {
     const long long rows = (long long)B * N;
     attn_dsum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, dsum,
-                                                                 rows, N, H);
+                                                                 rows, N, H, hd);
     rc = vitk_check_launch("attn_dsum");
     if (rc) return rc;
   }
   if (N > BWD_MAX_T * TILE) {
+    // one CTA per (b, h, kv tile): dQ partials are red.add'ed into the fp32 workspace (156 of the ~820 us per layer at
+    // ViT-L/384, B = 64, H = 16, N = 577; ~90 us are the memset / cast / D kernels around it)
     const long long rows = (long long)B * N;
-    const int D = H * HD;
-    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * D * sizeof(float), st);
+    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * H * HD * sizeof(float), st);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: memset: %s", cudaGetErrorString(e));
     dim3 grid((N + TILE - 1) / TILE, H, B);
-    // VITK_ATTN_BWD_LONG=5 selects the two-warpgroup ping-pong variant.  Measured at ViT-L/384 (B = 64, H = 16, N = 577):
-    // 816 us for both — each group's S -> P -> (dV, dP) -> dS -> (dK, dQ) chain is latency-bound (~8 k cycles per q tile),
-    // and 3 + 2 tiles on two groups are no shorter than 5 tiles at ~6 k on one; 156 us of either are the dQ red.adds
-    // (838 MB of fp32 atomics per layer), ~90 us the memset / cast / D kernels around it.
-    static const int long_variant = [] {
-      const char* e = getenv("VITK_ATTN_BWD_LONG");
-      return e ? atoi(e) : 0;
-    }();
-    if (long_variant != 5)
-      attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H,
-                                                                      scale);
-    else
-      attn_bwd5_kernel<<<grid, BWD3_THREADS, Bwd5Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H, scale);
+    attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H, hd,
+                                                                    scale);
     rc = vitk_check_launch("attn_bwd_stream");
     if (rc) return rc;
-    const long long n8 = rows * (D / 8);
-    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, D);
+    const long long n8 = rows * H * (hd / 8);
+    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, H, hd);
     return vitk_check_launch("attn_bwd_dq_cast");
   }
-  dim3 grid(H, B);
-  // VITK_ATTN_BWD: unset = warp-specialised persistent kernel for 128 < N <= 256, single-warpgroup kernel otherwise;
-  // "1" = single-warpgroup kernel everywhere; "2" = older two-warpgroup kernel (kept for comparison)
+  // VITK_ATTN_BWD: unset = warp-specialised persistent kernel for 128 < N <= 256, single-warpgroup kernel for N <= 128;
+  // "1" = single-warpgroup kernel everywhere
   static const int variant = [] {
     const char* e = getenv("VITK_ATTN_BWD");
     return e ? atoi(e) : 0;
   }();
-  if ((variant == 0 || variant == 3) && N > TILE) {
+  if (variant == 0 && N > TILE) {
     const int items = B * H;
     const int g3 = items < vitk_num_sms() ? items : vitk_num_sms();
-    if (variant == 3) {   // lockstep predecessor, kept for comparison
-      attn_bwd3_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, B, N, H, scale, g_trace_buf);
-      return vitk_check_launch("attn_bwd3");
-    }
     CUtensorMap tm_dqkv;   // 32-row boxes: one per warp-level read-out of dQ / dK / dV
-    rc = vitk_make_tmap_3d(&tm_dqkv, dqkv, 2, (uint64_t)3 * H * HD, (uint64_t)N, (uint64_t)B, (uint64_t)3 * H * HD,
-                           (uint64_t)N * 3 * H * HD, HD, 32, 1);
+    rc = make_head_tmap(&tm_dqkv, dqkv, 3 * H, hd, N, B, 32);
     if (rc) return rc;
     attn_bwd4_kernel<<<g3, BWD3_THREADS, Bwd3Smem::BYTES, st>>>(tm_qkv, tm_do, tm_dqkv, dsum, lse, B, N, H, scale, g_trace_buf);
     return vitk_check_launch("attn_bwd4");
   }
-  if (variant == 2) {
-    attn_bwd2_kernel<<<grid, 288, Bwd2Smem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, scale,
-                                                         g_trace_buf);
-    return vitk_check_launch("attn_bwd2");
-  }
-  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, scale, g_trace_buf);
+  dim3 grid(H, B);
+  attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, hd, scale, g_trace_buf);
   return vitk_check_launch("attn_bwd");
 }

@@ -59,8 +59,8 @@ __global__ void prefix_rows_kernel(float* __restrict__ x, const float* __restric
 
 // grid: (ceil(N*D/4 / 256), bchunks).  Thread owns one float4 column group of one token.
 __global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ gp,
-                                 float* __restrict__ dpos, float* __restrict__ dprefix, int B, int N,
-                                 int D, int prefix) {
+                                 float* __restrict__ dpos, float* __restrict__ dprefix0, float* __restrict__ dprefix1,
+                                 int B, int N, int D, int prefix) {
   const int dv = D / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * dv) return;
@@ -87,8 +87,9 @@ __global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __r
       float* o = dpos + (long long)n * D + c * 4;
       atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
     }
-    if (dprefix && n < prefix) {
-      float* o = dprefix + (long long)n * D + c * 4;
+    float* dpre = n == 0 ? dprefix0 : dprefix1;   // cls_token / dist_token gradient rows (may be NULL: frozen)
+    if (n < prefix && dpre != nullptr) {
+      float* o = dpre + c * 4;
       atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
     }
   }
@@ -356,7 +357,8 @@ struct AdamwHyper {
 };
 
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adamw_kernel(float* __restrict__ p, float* __restrict__ g, const __nv_bfloat16* __restrict__ g16,
+             const float* __restrict__ gscale_dev, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ shadow, float* __restrict__ ema, long long n,
              const uint8_t* __restrict__ chunk_group, int chunk, const __grid_constant__ AdamwHyper h) {
   // (__grid_constant__: h.lr[grp] is read straight from the parameter bank; without it the dynamic index makes the
@@ -366,14 +368,23 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m
   const int grp = chunk_group ? chunk_group[(unsigned long long)i4 < 0xffffffffull ? (unsigned)i4 / (unsigned)chunk : i4 / chunk] : 0;
   const float lr = h.lr[grp], wd = h.wd[grp];
   float4 pv = *reinterpret_cast<float4*>(p + i4);
-  float4 gv = *reinterpret_cast<float4*>(g + i4);
+  float4 gv;
+  if (g16 != nullptr) {   // the gradient as all-reduced in bf16 (data parallel); g is only zeroed below
+    const uint2 u = *reinterpret_cast<const uint2*>(g16 + i4);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    gv = make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    gv = *reinterpret_cast<float4*>(g + i4);
+  }
+  // 1/world of the gradient mean, times the clip coefficient left on the device by vitk_clip_coef (no host sync)
+  const float gscale = gscale_dev != nullptr ? h.grad_scale * __ldg(gscale_dev) : h.grad_scale;
   float4 mv = *reinterpret_cast<float4*>(m + i4);
   float4 vv = *reinterpret_cast<float4*>(v + i4);
   const float decay = 1.0f - lr * wd;
   const float step = lr * h.inv_bc1;
 #define VITK_ADAMW_ONE(P, G, M, V)                              \
   {                                                             \
-    const float gg = (G) * h.grad_scale;                        \
+    const float gg = (G) * gscale;                              \
     (P) *= decay;                                               \
     (M) = h.beta1 * (M) + (1.0f - h.beta1) * gg;                \
     (V) = h.beta2 * (V) + (1.0f - h.beta2) * gg * gg;           \
@@ -420,7 +431,77 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
+__global__ void sumsq_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float sh[CE_THREADS / 32];
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 7 < n) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + i);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      s += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+    } else {
+      for (long long j = i; j < n; ++j) { const float v = __bfloat162float(x[j]); s += v * v; }
+    }
+  }
+  s = block_reduce(s, false, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// coef = min(1, max_norm / (sqrt(sumsq) * grad_scale + 1e-6)): torch.nn.utils.clip_grad_norm_'s coefficient for the
+// gradient mean (= the all-reduced SUM times grad_scale = 1/world).  Stays on the device; AdamW multiplies it in.
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float grad_scale, float max_norm, float* __restrict__ coef,
+                                 float* __restrict__ norm) {
+  const float nrm = sqrtf(sumsq[0]) * grad_scale;
+  if (norm) norm[0] = nrm;
+  coef[0] = fminf(1.0f, max_norm / (nrm + 1e-6f));
+}
+
+__global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ scale, long long n) {
+  const float s = __ldg(scale);
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 v = *reinterpret_cast<float4*>(x + i4);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    *reinterpret_cast<float4*>(x + i4) = v;
+  } else {
+    for (long long i = i4; i < n; ++i) x[i] *= s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DropPath (timm drop_path, called from Block at /root/reference/models/vision_transformer.py:160-161, 172-178): every
+// per-sample keep mask of one forward pass in ONE launch.  rs[row, b] = Bernoulli(1 - p[row]) / (1 - p[row]), rows in
+// the order the reference draws them (block 0 attention branch, block 0 MLP branch, block 1 ...).  Counter-based
+// Philox4x32-10 keyed by (seed, offset): reproducible under torch.manual_seed, no state on the device.
+// ---------------------------------------------------------------------------------------------
+constexpr int DROPPATH_MAX_ROWS = 128;
+struct DropPathProbs { float p[DROPPATH_MAX_ROWS]; };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__global__ void droppath_masks_kernel(float* __restrict__ rs, int rows, int B, unsigned long long seed,
+                                      unsigned long long offset, const __grid_constant__ DropPathProbs probs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * B) return;
+  const float keep = 1.0f - probs.p[idx / B];
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)idx, 0u, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);   // uniform in [0, 1)
+  rs[idx] = (u < keep) ? (keep > 0.f ? 1.0f / keep : 1.0f) : 0.0f;
+}
 
 
 // ---------------------------------------------------------------------------------------------
@@ -545,13 +626,15 @@ extern "C" int vitk_prefix_rows(float* x, const float* prefix_tok, const float* 
   return vitk_check_launch("prefix_rows");
 }
 
-extern "C" int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix, int32_t B, int32_t N,
-                              int32_t D, int32_t prefix, void* stream) {
-  VITK_REQUIRE(B > 0 && N > 0 && D > 0 && D % 4 == 0 && prefix >= 0 && prefix <= N, VITK_ERR_SHAPE, "embed_bwd: bad shape");
+extern "C" int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix0, float* dprefix1, int32_t B,
+                              int32_t N, int32_t D, int32_t prefix, void* stream) {
+  VITK_REQUIRE(B > 0 && N > 0 && D > 0 && D % 4 == 0 && prefix >= 0 && prefix <= 2 && prefix <= N, VITK_ERR_SHAPE,
+               "embed_bwd: bad shape (prefix must be 0, 1 or 2)");
   const long long total = (long long)N * (D / 4);
   const int bchunks = B >= 32 ? 8 : 1;
   dim3 grid(blocks_for(total, 256), bchunks);
-  embed_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)gp_bf16, dpos, dprefix, B, N, D, prefix);
+  embed_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)gp_bf16, dpos, dprefix0, dprefix1, B, N, D,
+                                                           prefix);
   return vitk_check_launch("embed_bwd");
 }
 
@@ -628,10 +711,10 @@ extern "C" int vitk_cast_bf16(const float* in, void* out_bf16, int64_t n, void* 
   return vitk_scale_cast_bf16(in, nullptr, out_bf16, n, stream);
 }
 
-extern "C" int vitk_adamw_flat(float* p, float* g, float* m, float* v, void* shadow_bf16, float* ema, int64_t n,
-                               const uint8_t* chunk_group, int32_t chunk, int32_t num_groups, const float* lr,
-                               const float* wd, float beta1, float beta2, float eps, int64_t step, float grad_scale,
-                               float ema_decay, int32_t zero_grad, void* stream) {
+extern "C" int vitk_adamw_flat(float* p, float* g, const void* g_bf16, const float* grad_scale_dev, float* m, float* v,
+                               void* shadow_bf16, float* ema, int64_t n, const uint8_t* chunk_group, int32_t chunk,
+                               int32_t num_groups, const float* lr, const float* wd, float beta1, float beta2, float eps,
+                               int64_t step, float grad_scale, float ema_decay, int32_t zero_grad, void* stream) {
   VITK_REQUIRE(n >= 0 && n % 4 == 0, VITK_ERR_SHAPE, "adamw: n=%lld must be a multiple of 4", (long long)n);
   VITK_REQUIRE(num_groups >= 1 && num_groups <= ADAMW_MAX_GROUPS, VITK_ERR_SHAPE, "adamw: num_groups=%d not in [1,%d]", num_groups, ADAMW_MAX_GROUPS);
   VITK_REQUIRE(chunk_group == nullptr || (chunk > 0 && chunk % 4 == 0), VITK_ERR_SHAPE, "adamw: chunk must be a positive multiple of 4");
@@ -649,9 +732,37 @@ extern "C" int vitk_adamw_flat(float* p, float* g, float* m, float* v, void* sha
   h.inv_bc1 = (float)(1.0 / bc1);
   h.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   h.grad_scale = grad_scale; h.ema_decay = ema_decay; h.zero_grad = zero_grad;
-  adamw_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)shadow_bf16, ema, n,
-                                                                          chunk_group, chunk > 0 ? chunk : 4, h);
+  VITK_REQUIRE(g_bf16 == nullptr || ((uintptr_t)g_bf16 & 7) == 0, VITK_ERR_ALIGN, "adamw: g_bf16 must be 8-byte aligned");
+  adamw_kernel<<<blocks_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(p, g, (const __nv_bfloat16*)g_bf16, grad_scale_dev, m, v,
+                                                                          (__nv_bfloat16*)shadow_bf16, ema, n, chunk_group,
+                                                                          chunk > 0 ? chunk : 4, h);
   return vitk_check_launch("adamw");
+}
+
+extern "C" int vitk_clip_coef(const float* sumsq, float grad_scale, float max_norm, float* coef, float* norm, void* stream) {
+  VITK_REQUIRE(sumsq && coef && max_norm > 0.f, VITK_ERR_SHAPE, "clip_coef: bad args");
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, grad_scale, max_norm, coef, norm);
+  return vitk_check_launch("clip_coef");
+}
+
+extern "C" int vitk_scale_f32(float* x, const float* scale_dev, int64_t n, void* stream) {
+  VITK_REQUIRE(n >= 0 && scale_dev, VITK_ERR_SHAPE, "scale_f32: bad args");
+  VITK_REQUIRE(((uintptr_t)x & 15) == 0, VITK_ERR_ALIGN, "scale_f32: unaligned");
+  if (n == 0) return VITK_OK;
+  scale_f32_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, scale_dev, n);
+  return vitk_check_launch("scale_f32");
+}
+
+extern "C" int vitk_droppath_masks(float* rs, const float* drop_probs, int32_t rows, int32_t B, uint64_t seed, uint64_t offset,
+                                   void* stream) {
+  VITK_REQUIRE(rs && drop_probs && rows > 0 && rows <= DROPPATH_MAX_ROWS && B > 0, VITK_ERR_SHAPE,
+               "droppath_masks: rows=%d (max %d) B=%d", rows, DROPPATH_MAX_ROWS, B);
+  DropPathProbs pr;
+  for (int i = 0; i < DROPPATH_MAX_ROWS; ++i) pr.p[i] = i < rows ? drop_probs[i] : 0.f;
+  for (int i = 0; i < rows; ++i)
+    VITK_REQUIRE(pr.p[i] >= 0.f && pr.p[i] <= 1.f, VITK_ERR_SHAPE, "droppath_masks: drop_probs[%d]=%f not in [0,1]", i, pr.p[i]);
+  droppath_masks_kernel<<<blocks_for((long long)rows * B, 256), 256, 0, (cudaStream_t)stream>>>(rs, rows, B, seed, offset, pr);
+  return vitk_check_launch("droppath_masks");
 }
 
 extern "C" int vitk_sumsq(const float* x, int64_t n, float* out, void* stream) {
@@ -663,6 +774,18 @@ extern "C" int vitk_sumsq(const float* x, int64_t n, float* out, void* stream) {
   if (blocks < 1) blocks = 1;
   sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
   return vitk_check_launch("sumsq");
+}
+
+extern "C" int vitk_sumsq_bf16(const void* x_bf16, int64_t n, float* out, void* stream) {
+  VITK_REQUIRE(n >= 0 && out, VITK_ERR_SHAPE, "sumsq_bf16: bad args");
+  VITK_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, VITK_ERR_ALIGN, "sumsq_bf16: unaligned");
+  if (n == 0) return VITK_OK;
+  long long blocks = (n / 8 + 255) / 256;
+  const long long cap = (long long)vitk_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  sumsq_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, n, out);
+  return vitk_check_launch("sumsq_bf16");
 }
 
 extern "C" int vitk_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, double lam, int32_t use_cutmix,

@@ -5,12 +5,15 @@
 rewrites the no-decay group — SURVEY Appendix D #1), ``loss / update_freq``, backward, step every
 ``update_freq`` micro-batches, ``zero_grad``, optional EMA, meters, returned ``{meter: global_avg}``.
 What changes underneath: model, criterion and optimizer run on the vitk sm_100a kernels, gradient
-averaging across ranks is the bucketed NCCL all-reduce of ``parallel.DataParallel`` overlapped with
-backward, and the device is only synchronised when a metric is actually read (every ``log_freq`` steps)
-instead of after every step (engine.py:278-279, 290-299).
+averaging across ranks is the NCCL all-reduce of ``parallel.DataParallel`` (one bf16 all-reduce of the flat
+gradient right after backward by default, per-block buckets overlapped with backward as an option; micro-batches
+that do not end in ``optimizer.step()`` run under ``no_sync()``), gradient clipping acts on the reduced
+gradient, and the device is only synchronised when a metric is actually read (every ``log_freq`` steps) instead
+of after every step (engine.py:278-279, 290-299).
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import time
 from typing import Iterable, Optional
@@ -83,21 +86,26 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
                     wd = param_group.get("weight_decay", None)
                     if (wd is not None) if wd_quirk else (wd is not None and wd > 0):
                         param_group["weight_decay"] = wd_schedule_values[it]
-        if mixup_fn is not None:
-            samples, targets = mixup_fn(samples, targets)
+        # the device-side Mixup / CutMix (mixup.Mixup) works on the batch where it will be consumed
         samples = samples.to(device, non_blocking=True)
         targets = targets.to(device, non_blocking=True)
+        if mixup_fn is not None:
+            samples, targets = mixup_fn(samples, targets)
 
         output = model(samples)
         loss = criterion(output, targets)
-        loss = loss / update_freq
-        loss.backward()
-        if (data_iter_step + 1) % update_freq == 0:
+        if update_freq != 1:
+            loss = loss / update_freq
+        stepping = (data_iter_step + 1) % update_freq == 0
+        # gradients of micro-batches that do not end in a step are only accumulated locally (DDP's no_sync)
+        with (model.no_sync() if not stepping and hasattr(model, "no_sync") else contextlib.nullcontext()):
+            loss.backward()
+        if stepping:
             if max_norm and max_norm > 0:
                 clip_grad_norm_(optimizer, max_norm)
             optimizer.step()
             optimizer.zero_grad()
-            if model_ema is not None:
+            if model_ema is not None and hasattr(model_ema, "update"):   # (an EMA fused into FusedAdamW needs no call)
                 model_ema.update(model)
         last_loss = loss
 
@@ -122,24 +130,31 @@ def train_one_epoch(model: torch.nn.Module, criterion: torch.nn.Module, data_loa
 
 
 def clip_grad_norm_(optimizer, max_norm: float) -> torch.Tensor:
-    """Global-L2 gradient clipping over the flat gradient buffer(s) (vitk_sumsq), no host sync: the clip
-    coefficient stays on the device and is folded into the gradients with one in-place multiply."""
+    """``torch.nn.utils.clip_grad_norm_`` semantics on the flat gradient buffer(s), for the gradient the optimizer will
+    actually apply: the data-parallel all-reduce is completed first (``optimizer.sync_gradients()``; idempotent, so
+    ``step()`` does not reduce again), the global L2 norm is that of the gradient MEAN over the replicas, and every
+    rank derives the same coefficient.  Nothing is read back and the gradients are not rewritten: the coefficient
+    ``min(1, max_norm / (norm + 1e-6))`` stays on the device and the AdamW kernel multiplies it in.  Returns the norm
+    (device scalar).  (The reference's TPU branch clips the local gradient BEFORE the cross-replica mean,
+    /root/reference/engine.py:175-185 — SURVEY Appendix D #4; its eager branch never clips.)"""
     from . import _lib as L
     from .optim_factory import FusedAdamW
 
     if not isinstance(optimizer, FusedAdamW):
         raise NotImplementedError("clip_grad_norm_ is built for FusedAdamW")
-    if optimizer._plan is None:
+    if optimizer._plan is None or any(not e["store"].valid() for e in optimizer._plan):
         optimizer._build_plan()
+    optimizer.sync_gradients()
     dev = optimizer._plan[0]["store"].device
-    total = torch.zeros(1, device=dev)
-    for e in optimizer._plan:
-        L.sumsq(e["store"].grad, total)
-    norm = total.sqrt() * optimizer.grad_scale
-    coef = (max_norm / (norm + 1e-6)).clamp(max=1.0)
-    for e in optimizer._plan:
-        e["store"].grad.mul_(coef)
-    return norm
+    buf = torch.zeros(3, device=dev)   # [sum of squares, coefficient, norm]
+    if optimizer.grad_lowp is not None:
+        L.sumsq(optimizer.grad_lowp, buf[0:1])
+    else:
+        for e in optimizer._plan:
+            L.sumsq(e["store"].grad, buf[0:1])
+    L.clip_coef(buf[0:1], optimizer.grad_scale, float(max_norm), buf[1:2], buf[2:3])
+    optimizer.grad_scale_dev = buf[1:2]
+    return buf[2]
 
 
 @torch.no_grad()

@@ -8,7 +8,7 @@ from .vision_transformer import VisionTransformer, _create_vision_transformer
 
 @register_model
 def my_vit_mini(pretrained: bool = False, **kwargs) -> VisionTransformer:
-    """ViT-Mini/16 — ~3.3 M params (head_dim 48: not served by the 64-wide attention kernel -> raises)."""
+    """ViT-Mini/16 — ~3.3 M params (head_dim 48: runs on the 64-wide attention tiles, zero-padded by TMA)."""
     model_args = dict(patch_size=16, embed_dim=144, depth=12, num_heads=3)
     return _create_vision_transformer("my_vit_mini", pretrained=pretrained, **dict(model_args, **kwargs))
 
@@ -22,7 +22,7 @@ def my_vit_ti(pretrained: bool = False, **kwargs) -> VisionTransformer:
 
 @register_model
 def my_vit_xs(pretrained: bool = False, **kwargs) -> VisionTransformer:
-    """ViT-XS/16 — ~11 M params (head_dim 72: not served by the 64-wide attention kernel -> raises)."""
+    """ViT-XS/16 — ~11 M params (head_dim 72 > 64: wider than the attention kernels' head tile -> raises)."""
     model_args = dict(patch_size=16, embed_dim=288, depth=12, num_heads=4)
     return _create_vision_transformer("my_vit_xs", pretrained=pretrained, **dict(model_args, **kwargs))
 

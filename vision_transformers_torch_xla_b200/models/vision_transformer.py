@@ -133,8 +133,9 @@ class Attention(nn.Module):
             raise NotImplementedError("Attention: attn_drop / proj_drop > 0 are not built (all reference configs use 0)")
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
-        if self.head_dim != 64:
-            raise NotImplementedError(f"Attention: head_dim={self.head_dim}; the sm_100a attention kernel is built for 64")
+        if self.head_dim % 8 != 0 or not 16 <= self.head_dim <= 64:
+            raise NotImplementedError(f"Attention: head_dim={self.head_dim}; the sm_100a attention kernels run on 64-wide head "
+                                      "tiles (head_dim a multiple of 8 in [16, 64]; narrower heads are zero-padded by TMA)")
         self.scale = self.head_dim ** -0.5
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.q_norm = nn.Identity()
@@ -207,6 +208,11 @@ class Block(nn.Module):
         self.ls2 = LayerScale(dim, init_values=init_values) if init_values else nn.Identity()
         self.drop_path2 = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
         self._vitk_tag = "block"
+        self._vitk_index = 0
+
+    def _drop_probs(self):
+        return (self.drop_path1.drop_prob if isinstance(self.drop_path1, DropPath) else 0.0,
+                self.drop_path2.drop_prob if isinstance(self.drop_path2, DropPath) else 0.0)
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         if attn_mask is not None:
@@ -216,11 +222,16 @@ class Block(nn.Module):
             st.sync_shadow()
             st.attach_grads()
             st.__dict__["_last_rs"] = None
-        B = x.shape[0]
-        dp1 = self.drop_path1.drop_prob if isinstance(self.drop_path1, DropPath) else 0.0
-        dp2 = self.drop_path2.drop_prob if isinstance(self.drop_path2, DropPath) else 0.0
-        rs1 = ops.drop_path_scale(dp1, self.training, B, x.device)
-        rs2 = ops.drop_path_scale(dp2, self.training, B, x.device)
+        dp1, dp2 = self._drop_probs()
+        masks = st.__dict__.get("_dp_masks") if st.__dict__.get("_in_root") is not None else None
+        if masks is not None:      # drawn once per forward by the root model: rows 2i, 2i+1 belong to block i
+            i = self._vitk_index
+            rs1 = masks[2 * i] if dp1 > 0.0 else None
+            rs2 = masks[2 * i + 1] if dp2 > 0.0 else None
+        else:
+            own = ops.drop_path_masks([dp1, dp2], x.shape[0], x.device) if self.training else None
+            rs1 = own[0] if own is not None and dp1 > 0.0 else None
+            rs2 = own[1] if own is not None and dp2 > 0.0 else None
         prev_rs = st.__dict__.get("_last_rs")
         out = ops.BlockFn.apply(x, st.anchor, self, st, rs1, rs2, prev_rs, torch.is_grad_enabled(), self._vitk_tag)
         st.__dict__["_last_rs"] = rs2
@@ -325,6 +336,7 @@ class VisionTransformer(nn.Module):
             for i in range(depth)])
         for i, blk in enumerate(self.blocks):
             blk._vitk_tag = f"blocks.{i}."
+            blk._vitk_index = i
         self.feature_info = [dict(module=f"blocks.{i}", num_chs=embed_dim, reduction=patch_size) for i in range(depth)]
         self.norm = norm_layer(embed_dim) if final_norm and not use_fc_norm else nn.Identity()
         self.attn_pool = None
@@ -390,11 +402,15 @@ class VisionTransformer(nn.Module):
         x = x if x.is_contiguous() else x.contiguous()
         x = ops.EmbedFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
         st.__dict__["_in_root"] = self
+        # every DropPath mask of this pass in one launch, in the reference's draw order (Block.forward :175-178)
+        st.__dict__["_dp_masks"] = (ops.drop_path_masks([p for blk in self.blocks for p in blk._drop_probs()],
+                                                        x.shape[0], x.device) if self.training else None)
         try:
             for blk in self.blocks:
                 x = blk(x)
         finally:
             st.__dict__["_in_root"] = None
+            st.__dict__["_dp_masks"] = None
         return x
 
     def forward_features(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -86,12 +86,11 @@ class EmbedFn(torch.autograd.Function):
         store.chain.pop(g.data_ptr(), None)
         dev = g.device
         gp = _empty((B * P, D), torch.bfloat16, dev)
-        dpre = torch.zeros((prefix, D), dtype=torch.float32, device=dev)
-        L.embed_bwd(g, gp, store.grad_of(model.pos_embed).view(N, D), dpre, B, N, D, prefix)
         toks = [model.cls_token] + ([model.dist_token] if prefix == 2 else [])
-        for j, tok in enumerate(toks):
-            if tok.requires_grad:
-                store.grad_of(tok).view(D).add_(dpre[j])
+        # the token gradients are summed over the batch straight into their rows of the flat gradient buffer
+        dpre = [store.grad_of(tok).view(D) if tok.requires_grad else None for tok in toks] + [None]
+        dpos = store.grad_of(model.pos_embed).view(N, D) if model.pos_embed.requires_grad else None
+        L.embed_bwd(g, gp, dpos, dpre[0], dpre[1], B, N, D, prefix)
         L.gemm(gp, ctx.patches, store.grad_of(pe.proj.weight).view(D, K), M=D, N=K, K=B * P,
                epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
                colsum=None if pe.proj.bias is None else store.grad_of(pe.proj.bias))
@@ -286,8 +285,9 @@ class HeadFn(torch.autograd.Function):
             L.gemm(dlb, feats[j], gr(head.weight), M=C, N=D, K=B, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, lda=Cp,
                    colsum=None if head.bias is None else gr(head.bias))
             df = _empty((B, D), torch.bfloat16, dev)
-            # K = Cp: the extra weight rows read past head.weight are multiplied by the zero pad columns
-            L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=Cp, epilogue=L.EPI_BF16, b_mn=True)
+            # K = C with row pitch Cp: both tensor maps end at the true class count, so TMA zero-fills the k >= C part
+            # of the last k-block on both operands and nothing past head.weight is ever read
+            L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=C, epilogue=L.EPI_BF16, b_mn=True, lda=Cp)
             mean, rstd = stats[j]
             if not has_norm:
                 raise NotImplementedError("final_norm=False head backward is not built")
@@ -327,24 +327,48 @@ class CEFn(torch.autograd.Function):
         dl = _empty((B, C), torch.float32, dev)
         scratch = _empty((B,), torch.float32, dev)
         L.ce_fwd_bwd(logits, soft, labels, smoothing, teacher, alpha, temp, loss, dl, scratch)
-        ctx.save_for_backward(dl)
+        ctx.dl = dl
         return loss.view(())
 
     @staticmethod
     def backward(ctx, gout):
-        (dl,) = ctx.saved_tensors
-        return dl * gout, None, None, None, None, None, None
+        dl, ctx.dl = ctx.dl, None
+        if dl is None:
+            raise L.VitkError("the fused loss keeps one gradient buffer: backward() can run once per forward")
+        gout = gout.to(torch.float32)
+        L.scale_f32_(dl, gout if gout.is_contiguous() else gout.contiguous())   # upstream grad (e.g. 1/update_freq): device scalar
+        return dl, None, None, None, None, None, None
+
+
+#: test hook: callable(drop_probs, B, device) -> fp32 [len(drop_probs), B] of mask / keep_prob factors, used INSTEAD of
+#: the Philox kernel (the parity tests replay the masks the reference drew; tests/test_gpu_ref_fixtures.py)
+mask_source = None
+_mask_calls = 0
+
+
+def drop_path_masks(drop_probs, B: int, device) -> Optional[torch.Tensor]:
+    """All per-sample DropPath factors (mask / keep_prob, timm drop_path semantics: SURVEY A.2) of one forward pass in one
+    launch: row r of the result belongs to ``drop_probs[r]``, rows in the order the reference draws them (block 0
+    attention branch, block 0 MLP branch, block 1 ...).  Seeded from torch's CUDA generator seed (``torch.manual_seed``)
+    plus a per-process call counter, so runs are reproducible without any device-side RNG state."""
+    global _mask_calls
+    if not any(p > 0.0 for p in drop_probs):
+        return None
+    if mask_source is not None:
+        rs = mask_source(list(drop_probs), B, device)
+        assert rs.shape == (len(drop_probs), B) and rs.dtype == torch.float32 and rs.is_cuda
+        return rs.contiguous()
+    rs = _empty((len(drop_probs), B), torch.float32, device)
+    _mask_calls += 1
+    L.droppath_masks(rs, drop_probs, torch.cuda.initial_seed(), _mask_calls)
+    return rs
 
 
 def drop_path_scale(drop_prob: float, training: bool, B: int, device) -> Optional[torch.Tensor]:
-    """Per-sample DropPath factor mask/keep_prob, same RNG recipe as timm's drop_path."""
+    """One DropPath's factor (stand-alone DropPath module)."""
     if drop_prob == 0.0 or not training:
         return None
-    keep = 1.0 - drop_prob
-    rs = torch.empty(B, dtype=torch.float32, device=device).bernoulli_(keep)
-    if keep > 0.0:
-        rs.div_(keep)
-    return rs
+    return drop_path_masks([drop_prob], B, device)[0]
 
 
 # ================================================================================================

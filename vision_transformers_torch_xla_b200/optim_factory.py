@@ -56,10 +56,29 @@ class FusedAdamW(torch.optim.Optimizer):
         self._plan = None
         self._step = 0
         self._grads_zeroed = False
+        #: callbacks(optimizer) that complete the gradient (data-parallel all-reduce); run ONCE per step, by
+        #: ``sync_gradients()`` — called from ``step()``, or earlier by gradient clipping, which needs the reduced gradient
         self.pre_step_hooks = []
+        self._synced = False
+        #: set by the data-parallel layer for one step: bf16 copy of the summed gradient that the kernel reads instead
+        self.grad_lowp: Optional[torch.Tensor] = None
+        #: set by ``engine.clip_grad_norm_`` for one step: device scalar multiplied into the gradient (clip coefficient)
+        self.grad_scale_dev: Optional[torch.Tensor] = None
+
+    def sync_gradients(self) -> None:
+        """Run the pre-step hooks (gradient all-reduce) if they have not run for this step yet."""
+        if not self._synced:
+            for hook in self.pre_step_hooks:
+                hook(self)
+            self._synced = True
 
     # ---- plan: which store, which chunk belongs to which group ----
     def _build_plan(self):
+        old_plan, old_ema = self._plan, self.ema
+        # moments that already exist (a plan rebuilt after model.to() / reset_classifier, or a state loaded before the
+        # store existed) are carried over by parameter instead of being silently reset
+        carried = {id(p): (st_["exp_avg"].detach().clone(), st_["exp_avg_sq"].detach().clone())
+                   for p, st_ in self.state.items() if "exp_avg" in st_ and "exp_avg_sq" in st_}
         stores: Dict[int, ParamStore] = {}
         owner: Dict[int, int] = {}
         for gi, group in enumerate(self.param_groups):
@@ -77,6 +96,8 @@ class FusedAdamW(torch.optim.Optimizer):
             for p in group["params"]:
                 st = getattr(p, "_vitk_store_ref", None)
                 st = st() if st is not None else None
+                if st is not None and not st.valid():
+                    st = None
                 if st is None or id(p) not in st.offsets:
                     raise L.VitkError("FusedAdamW: a parameter is not in a vitk ParamStore. Run one forward pass "
                                       "(or store.get_store(model)) before optimizer.step(); there is no eager fallback")
@@ -105,9 +126,23 @@ class FusedAdamW(torch.optim.Optimizer):
             for p in st.params:
                 if id(p) in owner:
                     o, n = st.offsets[id(p)]
-                    self.state[p] = {"step": torch.tensor(0.0), "exp_avg": m[o:o + n].view(p.shape),
+                    self.state[p] = {"step": torch.tensor(float(self._step)), "exp_avg": m[o:o + n].view(p.shape),
                                      "exp_avg_sq": v[o:o + n].view(p.shape)}
+                    if id(p) in carried and carried[id(p)][0].numel() == n:
+                        self.state[p]["exp_avg"].copy_(carried[id(p)][0].to(m.device).view(p.shape))
+                        self.state[p]["exp_avg_sq"].copy_(carried[id(p)][1].to(v.device).view(p.shape))
         self._plan = plan
+        if old_ema is not None and old_plan is not None:
+            # the fused EMA follows the parameters into the new flat layout (new parameters start from their weights)
+            if len(plan) != 1:
+                raise NotImplementedError("EMA with several stores")
+            new_st, old_st = plan[0]["store"], old_plan[0]["store"]
+            ema = new_st.flat.clone()
+            for p in new_st.params:
+                if id(p) in old_st.offsets and old_st.offsets[id(p)][1] == new_st.offsets[id(p)][1]:
+                    (oo, n), (no, _) = old_st.offsets[id(p)], new_st.offsets[id(p)]
+                    ema[no:no + n].copy_(old_ema[oo:oo + n].to(ema.device))
+            self.ema = ema
 
     def enable_ema(self, decay: float):
         """Keep ``ema = decay*ema + (1-decay)*p`` inside the AdamW launch (timm ModelEma semantics)."""
@@ -127,11 +162,13 @@ class FusedAdamW(torch.optim.Optimizer):
                 loss = closure()
         if self._plan is None or any(not e["store"].valid() for e in self._plan):
             self._build_plan()
-        for hook in self.pre_step_hooks:
-            hook(self)
+        self.sync_gradients()
+        self._synced = False
         self._step += 1
         b1, b2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
+        if self.grad_lowp is not None and len(self._plan) != 1:
+            raise NotImplementedError("a low-precision gradient copy with several stores")
         for e in self._plan:
             st = e["store"]
             lrs = [float(g["lr"]) for g in self.param_groups]
@@ -141,8 +178,10 @@ class FusedAdamW(torch.optim.Optimizer):
                 wds.append(0.0)
             L.adamw_flat(st.flat, st.grad, e["m"], e["v"], st.shadow, self.ema, e["table"], ALIGN, lrs, wds, b1, b2, eps,
                          self._step, grad_scale=self.grad_scale, ema_decay=self.ema_decay,
-                         zero_grad=self.fused_zero_grad)
+                         zero_grad=self.fused_zero_grad, g_bf16=self.grad_lowp, grad_scale_dev=self.grad_scale_dev)
             st.mark_shadow_current()
+        self.grad_lowp = None
+        self.grad_scale_dev = None
         self._grads_zeroed = self.fused_zero_grad
         for p_state in self.state.values():
             p_state["step"] = torch.tensor(float(self._step))
@@ -159,9 +198,15 @@ class FusedAdamW(torch.optim.Optimizer):
             e["store"].grad.zero_()
 
     def load_state_dict(self, state_dict):
+        """Works before the model's first forward too (the reference resume order: create model -> create optimizer ->
+        auto_load_model): if the parameters are not in a ParamStore yet, the loaded moments stay in ``self.state`` and
+        are moved into the flat buffers when the plan is built."""
         if self._plan is None:
-            self._build_plan()
-        views = {id(p): dict(s) for p, s in self.state.items()}
+            try:
+                self._build_plan()
+            except L.VitkError:
+                self._plan = None
+        views = {id(p): dict(s) for p, s in self.state.items()} if self._plan is not None else {}
         super().load_state_dict(state_dict)
         steps = []
         for p, s in list(self.state.items()):

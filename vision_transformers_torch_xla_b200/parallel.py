@@ -11,6 +11,11 @@ on GPU — with a bucketed all-reduce driven by the fused backward stages:
   * the optimizer's pre-step hook waits for the outstanding buckets; the 1/world_size of the mean is folded
     into the AdamW kernel (``grad_scale``), so averaging costs no extra pass over the gradients.
 
+Wire format (``VITK_DP_GRAD``): ``bf16`` (default) casts the flat fp32 gradient into a persistent bf16 buffer (one
+vitk cast kernel, 0.09 ms for ViT-B), all-reduces THAT (173 MB instead of 346 MB for ViT-B) and lets the AdamW kernel
+read the summed gradient from it; ``fp32`` all-reduces the fp32 buffer in place.  bf16 applies to the ``step`` schedule
+(the overlapped ones reduce slices of the fp32 buffer while backward is still accumulating into other slices).
+
 Two schedules (``VITK_DP_SYNC``): ``block`` is the bucketed, overlapped one described above; ``step`` (default) reduces
 the whole flat gradient once, right after backward.  Measured at 8 B200, ViT-B/16, batch 256/GPU, same box, back to back:
 ``step`` 34.98 ms/step (58 545 img/s, 96 % of 8 x the 1-GPU rate) vs ``block`` 36.17 ms (56 622 img/s, 93 %): over
@@ -58,6 +63,11 @@ class DataParallel(nn.Module):
         # from blocks.K to the head in one all-reduce that overlaps the backward of blocks K-1 .. 0 and the embedding,
         # the rest after backward
         self.sync_mode = os.environ.get("VITK_DP_SYNC", "step")
+        self.grad_wire = os.environ.get("VITK_DP_GRAD", "bf16")
+        if self.grad_wire not in ("bf16", "fp32"):
+            raise ValueError(f"VITK_DP_GRAD={self.grad_wire!r}: expected 'bf16' or 'fp32'")
+        self._grad16 = None     # persistent bf16 wire buffer (allocated on first use)
+        self._optimizer = None
         self._tail_tag = None
         if self.sync_mode.startswith("tail:"):
             k = int(self.sync_mode.split(":", 1)[1])
@@ -102,6 +112,7 @@ class DataParallel(nn.Module):
     def attach_optimizer(self, optimizer):
         optimizer.grad_scale = 1.0 / self.world_size
         optimizer.pre_step_hooks.append(lambda opt: self.finish_gradient_sync())
+        self._optimizer = optimizer
 
     def _on_grad_ready(self, tag: str):
         if not self.require_sync or self.world_size == 1:
@@ -121,10 +132,19 @@ class DataParallel(nn.Module):
         self._works.append(dist.all_reduce(self.store.grad[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
 
     def finish_gradient_sync(self):
+        """Complete the gradient SUM over the replicas (idempotent: a second call before the next backward is a no-op)."""
         if self._pending:
             self._pending = False
             if self.sync_mode == "tail" and self._works:
                 dist.all_reduce(self.store.grad[:self._tail_lo], op=dist.ReduceOp.SUM)
+            elif self.grad_wire == "bf16" and self._optimizer is not None and self.store.grad.is_cuda:
+                from . import _lib as L
+
+                if self._grad16 is None or self._grad16.numel() != self.store.grad.numel():
+                    self._grad16 = torch.empty_like(self.store.grad, dtype=torch.bfloat16)
+                L.cast_bf16(self.store.grad, self._grad16)
+                dist.all_reduce(self._grad16, op=dist.ReduceOp.SUM)
+                self._optimizer.grad_lowp = self._grad16   # AdamW reads the summed gradient from here (this step only)
             else:
                 dist.all_reduce(self.store.grad, op=dist.ReduceOp.SUM)
         for w in self._works:

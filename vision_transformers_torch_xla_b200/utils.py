@@ -56,18 +56,20 @@ def init_distributed_mode(args=None, backend: str = "nccl"):
 
 def cosine_scheduler(base_value, final_value, epochs, niter_per_ep, warmup_epochs=0, start_warmup_value=0,
                      warmup_steps=-1):
-    """Per-iteration cosine schedule with linear warm-up (/root/reference/utils/__init__.py:667-684)."""
-    warmup_schedule = np.array([])
-    warmup_iters = warmup_epochs * niter_per_ep
-    if warmup_steps > 0:
-        warmup_iters = warmup_steps
-    if warmup_epochs > 0:
-        warmup_schedule = np.linspace(start_warmup_value, base_value, warmup_iters)
-    iters = np.arange(epochs * niter_per_ep - warmup_iters)
-    schedule = np.array(
-        [final_value + 0.5 * (base_value - final_value) * (1 + math.cos(math.pi * i / (len(iters)))) for i in iters])
-    schedule = np.concatenate((warmup_schedule, schedule))
-    assert len(schedule) == epochs * niter_per_ep
+    """Per-iteration schedule: linear warm-up, then half a cosine from ``base_value`` to ``final_value``.
+
+    Same values as /root/reference/utils/__init__.py:667-684, element for element (pinned bit-for-bit by
+    tests/test_ref_fixtures.py against arrays the reference function itself produced), computed as one vector
+    expression.  The reference's two conventions are kept: ``warmup_steps > 0`` overrides the warm-up LENGTH, but the
+    ramp is only emitted when ``warmup_epochs > 0`` (otherwise the lengths no longer add up and the assert fires)."""
+    total = int(epochs * niter_per_ep)
+    n_warm = int(warmup_steps if warmup_steps > 0 else warmup_epochs * niter_per_ep)
+    ramp = np.linspace(start_warmup_value, base_value, n_warm) if warmup_epochs > 0 else np.empty(0)
+    n_cos = total - n_warm
+    phase = math.pi * np.arange(n_cos) / max(n_cos, 1)
+    tail = final_value + 0.5 * (base_value - final_value) * (1 + np.cos(phase))
+    schedule = np.concatenate((ramp, tail))
+    assert len(schedule) == total
     return schedule
 
 
@@ -291,6 +293,13 @@ def auto_load_model(args, model, model_without_ddp, optimizer, loss_scaler, mode
         raise NotImplementedError("remote checkpoints are not fetched (no network dependency on the training path)")
     checkpoint = torch.load(args.resume, map_location="cpu", weights_only=False)
     model_without_ddp.load_state_dict(checkpoint["model"])
+    if next(model_without_ddp.parameters()).is_cuda:
+        # the reference's resume order is create model -> create optimizer -> auto_load_model, before any forward: make
+        # sure the flat parameter store exists so that the optimizer state lands in its flat moment buffers directly
+        from .parallel import DataParallel
+        from .store import get_store
+
+        get_store(DataParallel._find_root(model_without_ddp))
     if "optimizer" in checkpoint and "epoch" in checkpoint:
         optimizer.load_state_dict(checkpoint["optimizer"])
         if not isinstance(checkpoint["epoch"], str):
