@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Headline benchmark: ViT-B/16 224px bf16 training images/sec (BASELINE.json `metric`).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--model NAME] [--batch B] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5 | --model NAME --batch B] [--impl ours|reference]
+
+--config selects one of BASELINE.json's configs as written (default 3 = the headline: vit_base_patch16_224, batch 256/GPU):
+  1 vit_tiny_patch16_224 batch 8            2 vit_small_patch16_224 batch 256        3 vit_base_patch16_224 batch 256
+  4 deit_base_distilled_patch16_224 batch 256, StudentWithDistillation(student, frozen RegNetY-16GF teacher, channels-last
+    bf16, no_grad) + DistillationLoss(hard) with distilled_training on   5 vit_large_patch16_384 batch 64
 
 One process per GPU (torchrun for N>1).  A step = forward + loss + backward + AdamW on one synthetic batch.
 Prints ONE JSON line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the public
@@ -94,9 +99,42 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build(model_name, batch, device, drop_path):
+#: BASELINE.json `configs`, in order: (model, per-GPU batch, distillation teacher)
+CONFIGS = {
+    1: ("vit_tiny_patch16_224", 8, None),
+    2: ("vit_small_patch16_224", 256, None),
+    3: ("vit_base_patch16_224", 256, None),
+    4: ("deit_base_distilled_patch16_224", 256, "regnet_y_16gf"),
+    5: ("vit_large_patch16_384", 64, None),
+}
+
+
+class Teacher(torch.nn.Module):
+    """Frozen forward-only distillation teacher (/root/reference/main.py:691-742): torchvision RegNetY-16GF (83.6 M
+    parameters, random init: there is no network for checkpoints), channels-last bf16, eval mode.  Library (cuDNN)
+    convolutions: the teacher is not a custom-kernel target; its time is reported separately."""
+
+    def __init__(self, name, device):
+        super().__init__()
+        import torchvision
+
+        torch.backends.cudnn.benchmark = True   # grouped 3x3 convolutions: let cuDNN time its algorithms once
+        self.net = getattr(torchvision.models, name)(weights=None, num_classes=1000).to(device).eval()
+        self.net = self.net.to(memory_format=torch.channels_last).bfloat16()
+        for p in self.net.parameters():
+            p.requires_grad = False
+
+    def train(self, mode=True):   # stays in eval mode inside the training wrapper (main.py:737-740)
+        return super().train(False)
+
+    @torch.no_grad()
+    def forward(self, x):
+        return self.net(x.to(dtype=torch.bfloat16, memory_format=torch.channels_last)).float()
+
+
+def build(model_name, batch, device, drop_path, teacher=None):
     from vision_transformers_torch_xla_b200 import optim_factory
-    from vision_transformers_torch_xla_b200.losses import SoftTargetCrossEntropy
+    from vision_transformers_torch_xla_b200.losses import DistillationLoss, SoftTargetCrossEntropy, StudentWithDistillation
     from vision_transformers_torch_xla_b200.models import create_model
 
     torch.manual_seed(0)
@@ -109,17 +147,34 @@ def build(model_name, batch, device, drop_path):
     class Args:
         opt, lr, weight_decay, opt_eps, opt_betas = "adamw", 1e-3, 0.05, 1e-8, None
 
-    opt = optim_factory.create_optimizer(Args, model)
-    return model, opt, SoftTargetCrossEntropy()
+    opt = optim_factory.create_optimizer(Args, model)   # (main.py:868-878: the optimizer sees the student only)
+    crit = SoftTargetCrossEntropy()
+    if teacher is None:
+        return model, model, opt, crit
+    if hasattr(model, "set_distilled_training"):
+        model.set_distilled_training(True)              # (cls, dist) heads -> DeiT hard distillation
+    wrapped = StudentWithDistillation(model, Teacher(teacher, device))
+    wrapped.train()
+    return model, wrapped, opt, DistillationLoss(crit, alpha=0.5, temperature=1.0, hard=True)
+
+
+def soft_targets(labels, num_classes=1000, lam=0.7, smoothing=0.1):
+    """Mixup-style soft targets made on the host for the synthetic batches: lam * onehot_s(y) + (1 - lam) * onehot_s(y.flip(0))
+    with timm's smoothed one-hot (on 1 - eps + eps / C, off eps / C)."""
+    off = smoothing / num_classes
+    on = 1.0 - smoothing + off
+
+    def one_hot(y):
+        return torch.full((y.shape[0], num_classes), off).scatter_(1, y.view(-1, 1), on)
+
+    return lam * one_hot(labels) + (1.0 - lam) * one_hot(labels.flip(0))
 
 
 def synth_batch(batch, img, gen):
-    """ImageNet-shaped synthetic batch: N(0,1) images, mixup-style soft targets (smoothing 0.1)."""
-    from oracle.vit_oracle import mixup_soft_targets  # data recipe only (host side, shared with the CPU arm)
-
+    """ImageNet-shaped synthetic batch: N(0,1) images, mixup-style soft targets (smoothing 0.1), hard labels."""
     x = torch.randn(batch, 3, img, img, generator=gen)
-    y = mixup_soft_targets(torch.randint(0, 1000, (batch,), generator=gen), 1000, 0.7, 0.1)
-    return x, y
+    labels = torch.randint(0, 1000, (batch,), generator=gen)
+    return x, soft_targets(labels), labels
 
 
 def run_reference(args):
@@ -141,7 +196,7 @@ def run_reference(args):
     crit = O.SoftTargetCrossEntropy()
     img = model.patch_embed.img_size[0]
     gen = torch.Generator().manual_seed(0)
-    x, y = synth_batch(sample_b, img, gen)
+    x, y, _ = synth_batch(sample_b, img, gen)
     for _ in range(args.warmup):
         O.train_step(model, crit, opt, x, y)
     t0 = time.perf_counter()
@@ -175,7 +230,7 @@ def cpu_baseline(model_name, batch):
     opt = O.create_optimizer(model, lr=1e-3, weight_decay=0.05)
     crit = O.SoftTargetCrossEntropy()
     img = model.patch_embed.img_size[0]
-    x, y = synth_batch(sample_b, img, torch.Generator().manual_seed(0))
+    x, y, _ = synth_batch(sample_b, img, torch.Generator().manual_seed(0))
     O.train_step(model, crit, opt, x, y)
     n, t0 = 0, time.perf_counter()
     while n < 3 or (time.perf_counter() - t0 < 8 and n < 20):
@@ -187,26 +242,34 @@ def cpu_baseline(model_name, batch):
                       f"({dt * 1e3:.0f} ms/step)"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant GEMM, from the committed `ncu --set full`
-# capture of the same kernel at the same shape (ViT-B/16, batch 256): algorithmic bytes are A 77.5 + W 4.7 + two bf16
-# outputs 2 x 309.9 = 702 MB, so nothing is re-read from HBM.
-NCU_TRAFFIC = {"gemm.fprop.epi1 50432x3072x768": (651.7e6, "profiles/r01_ncu_gemm_fc1_gelu_v3.txt")}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant GEMM from a committed `ncu --set full` capture of
+# the same kernel at the same shape, keyed by GEMM family: (bytes, capture file, build id of the library that was profiled).
+# Read from profiles/ncu_traffic.json so that a new capture updates the number without touching this file; a capture taken
+# from a different build of the library is still reported but flagged (`traffic_build` != `build`).
+def ncu_traffic():
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
 
 
-def roofline(by_shape, family_tf, n_launches, gemm_ms_per_step, pk, args):
+def roofline(by_shape, family_tf, n_launches, gemm_ms_per_step, pk, build_id):
     """The dominant kernel = the GEMM role/shape with the largest summed device time inside the timed region; every
     launch was bracketed by CUDA events on the launching stream.  `family_*` is the same over all gemm_kernel launches."""
     if not by_shape:
         return None
     fam, (fl, ms, n) = max(by_shape.items(), key=lambda kv: kv[1][1])
     tf = fl / (ms * 1e-3) / 1e12
-    traffic, src = NCU_TRAFFIC.get(fam, (None, None))
+    t = ncu_traffic().get(fam, {})
     return {"bound": "tensor", "kernel": f"vitk gemm_kernel (tcgen05 cta_group::2) {fam}", "achieved": tf, "peak": pk["tf"],
-            "unit": "TFLOP/s", "frac": tf / pk["tf"], "traffic": traffic, "traffic_source": src,
+            "unit": "TFLOP/s", "frac": tf / pk["tf"], "traffic": t.get("bytes"), "traffic_source": t.get("source"),
+            "traffic_build": t.get("build_id"), "build": build_id,
             "launches_timed": n, "us_per_launch": ms * 1e3 / n, "flop_per_launch": fl / n,
             "peak_source": f"bf16_tflops_sustained, {pk['src']}",
             "family_achieved": family_tf, "family_frac": (family_tf / pk["tf"]) if family_tf else None,
-            "family_launches_timed": n_launches, "family_ms_per_step": gemm_ms_per_step}
+            "family_launches_timed": n_launches, "family_ms_per_step": gemm_ms_per_step,
+            "by_shape_us": {k: round(v[1] * 1e3 / v[2], 1) for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:8]}}
 
 
 def main():
@@ -214,8 +277,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--model", default="vit_base_patch16_224")
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--config", type=int, default=None, choices=sorted(CONFIGS), help="BASELINE.json config number")
+    ap.add_argument("--model", default=None)
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch")
+    ap.add_argument("--teacher", default=None, help="torchvision model name of a frozen distillation teacher")
     ap.add_argument("--drop-path", type=float, default=0.1, help="reference launch value (run_train.sh:58)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +288,12 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="print a per-kernel-family time table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg_model, cfg_batch, cfg_teacher = CONFIGS[args.config if args.config is not None else 3]
+    if args.config is None and args.model is not None:
+        cfg_teacher = None
+    args.model = args.model or cfg_model
+    args.batch = args.batch or cfg_batch
+    args.teacher = args.teacher or cfg_teacher
 
     if args.impl == "reference":
         run_reference(args)
@@ -230,6 +301,7 @@ def main():
 
     from vision_transformers_torch_xla_b200 import _lib as L
     from vision_transformers_torch_xla_b200 import engine, utils
+    from vision_transformers_torch_xla_b200.mixup import Mixup
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,18 +309,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     distributed = utils.init_distributed_mode(None, backend="nccl") if world > 1 else False
-    L.load()
+    lib = L.load()
+    build_id = lib.vitk_build_id().decode()
 
-    model, opt, crit = build(args.model, args.batch, dev, args.drop_path)
-    train_model = model
+    model, step_model, opt, crit = build(args.model, args.batch, dev, args.drop_path, args.teacher)
+    train_model = step_model
     if distributed:
         from vision_transformers_torch_xla_b200.parallel import DataParallel
 
-        train_model = DataParallel(model, optimizer=opt)
+        train_model = DataParallel(step_model, optimizer=opt)
     img = model.patch_embed.img_size[0]
     gen = torch.Generator().manual_seed(1234 + rank)
     host = [tuple(t.pin_memory() for t in synth_batch(args.batch, img, gen)) for _ in range(2)]
-    dev_batches = [(x.to(dev), y.to(dev)) for x, y in host]
+    dev_batches = [(x.to(dev), y.to(dev)) for x, y, _ in host]
 
     def step(i):
         x, y = dev_batches[i % 2]
@@ -292,28 +365,52 @@ def main():
     value = world * args.batch * args.steps / (ms / 1e3)
     final_loss = float(loss.item())
 
+    # the frozen teacher's forward alone (library convolutions), so that the student's share of the step is visible
+    teacher_ms = None
+    if args.teacher is not None:
+        x = dev_batches[0][0]
+        for _ in range(2):
+            step_model.teacher(x)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            step_model.teacher(x)
+        e1.record()
+        barrier()
+        teacher_ms = e0.elapsed_time(e1) / 5
+
     # ---------------- timed region 2: end to end through engine.train_one_epoch ----------------
+    # what a user of the reference runs per step (engine.py:259-274): pinned host batch of fp32 images + int64 labels ->
+    # H2D -> Mixup / CutMix + label smoothing on the device (timm.data.Mixup as main.py:622-629 builds it) -> model ->
+    # criterion -> backward -> step, with the loss read back every step
     e2e = None
     if not args.no_e2e:
         fetch_times = []
+        mixup_fn = Mixup(mixup_alpha=0.8, cutmix_alpha=1.0, prob=1.0, switch_prob=0.5, mode="batch", label_smoothing=0.1,
+                         num_classes=1000)
 
         class _Loader:   # pinned host batches; notes when the engine asks for each one (diagnostics on stderr only)
+            def __init__(self, n):
+                self.n = n
+
             def __len__(self):
-                return args.steps
+                return self.n
 
             def __iter__(self):
-                for i in range(args.steps):
+                for i in range(self.n):
                     fetch_times.append(time.perf_counter())
-                    yield host[i % 2]
+                    x, _, labels = host[i % 2]
+                    yield x, labels
 
-        loader = _Loader()
         # untimed warm-up of the end-to-end path itself (the engine's own small torch ops, the prefetcher's buffers and
         # stream, pinned read-back buffers: first use costs 0.2-0.5 s of lazy CUDA module loading and allocation)
-        engine.train_one_epoch(train_model, crit, [host[i % 2] for i in range(args.warmup)], opt, dev, 0, None,
-                               log_freq=1, update_freq=1, quiet=True)
+        engine.train_one_epoch(train_model, crit, _Loader(args.warmup), opt, dev, 0, None, mixup_fn=mixup_fn, log_freq=1,
+                               update_freq=1, quiet=True)
+        fetch_times.clear()
         barrier()
         e0.record()
-        engine.train_one_epoch(train_model, crit, loader, opt, dev, 0, None, log_freq=1, update_freq=1, quiet=True)
+        engine.train_one_epoch(train_model, crit, _Loader(args.steps), opt, dev, 0, None, mixup_fn=mixup_fn, log_freq=1,
+                               update_freq=1, quiet=True)
         e1.record()
         barrier()
         if rank == 0 and len(fetch_times) > 2:
@@ -323,10 +420,12 @@ def main():
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if distributed:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        h2d = sum(v.numel() * v.element_size() for v in host[0])
+        h2d = host[0][0].numel() * host[0][0].element_size() + host[0][2].numel() * host[0][2].element_size()
         e2e = {"value": world * args.batch * args.steps / (float(t.item()) / 1e3), "unit": "img/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
-               "api": "engine.train_one_epoch(model, SoftTargetCrossEntropy, pinned-host loader -> side-stream H2D prefetch, FusedAdamW, log_freq=1: loss+metric read back every step, one step deferred)"}
+               "api": "engine.train_one_epoch(model, criterion, pinned-host loader of (fp32 images, int64 labels) -> side-stream "
+                      "H2D prefetch -> device Mixup/CutMix + label smoothing -> fwd/bwd -> FusedAdamW, log_freq=1: loss read "
+                      "back every step, one step deferred)"}
 
     if args.breakdown and rank == 0:
         L.breakdown_begin()
@@ -344,21 +443,27 @@ def main():
     pk = peaks()
     gflop_img = TRAIN_GFLOP_PER_IMG.get(args.model)
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    loss_name = "SoftTargetCE" if args.teacher is None else \
+        f"DistillationLoss(hard, SoftTargetCE base) with a frozen {args.teacher} teacher forward (channels-last bf16)"
     out = {
         "metric": "train images/sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.model} train step (fwd + SoftTargetCE + bwd + AdamW), {img}x{img}, batch "
-                               f"{args.batch}/GPU, drop_path {args.drop_path}", "global_batch": world * args.batch,
-                   "parallelism": f"dp{world}", "l2": "per-step working set (>10 GB of activations) >> 126 MB L2",
-                   "final_loss": final_loss},
+        "config": {"workload": f"{args.model} train step (fwd + {loss_name} + bwd + AdamW), {img}x{img}, batch "
+                               f"{args.batch}/GPU, drop_path {args.drop_path}",
+                   "baseline_config": args.config if args.config is not None else (3 if args.model == CONFIGS[3][0] and args.batch == CONFIGS[3][1] else None),
+                   "global_batch": world * args.batch,
+                   "parallelism": f"dp{world}", "grad_allreduce": os.environ.get("VITK_DP_GRAD", "bf16") + "/" + os.environ.get("VITK_DP_SYNC", "step") if world > 1 else None,
+                   "l2": "per-step working set (>10 GB of activations) >> 126 MB L2",
+                   "final_loss": final_loss, "teacher_fwd_ms_per_step": teacher_ms},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline(gemm_by_shape, achieved_tf, gemm_n, gemm_ms / args.steps, pk, args),
+        "roofline": roofline(gemm_by_shape, achieved_tf, gemm_n, gemm_ms / args.steps, pk, build_id),
     }
     if gflop_img:
         step_tf = value / world * gflop_img * 1e9 / 1e12
         out["model_flops"] = {"train_gflop_per_img": gflop_img, "achieved_tflops_per_gpu": step_tf,
-                              "frac_of_measured_sustained": step_tf / pk["tf"], "frac_of_nominal_2250": step_tf / 2250.0}
+                              "frac_of_measured_sustained": step_tf / pk["tf"], "frac_of_nominal_2250": step_tf / 2250.0,
+                              "counts": "student GEMMs + attention only (SURVEY section 8 formula)" + ("; the teacher forward is extra, uncounted work inside the step" if args.teacher else "")}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.model, args.batch)
     emit(json.dumps(out))

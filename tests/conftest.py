@@ -18,7 +18,18 @@ def cuda_device():
 
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    # the oracle runs next to the kernels as the fp32 reference: keep TF32 out of its matmuls and convolutions
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     return torch.device("cuda:0")
+
+
+def report(name, a, b):
+    """One line with every metric the tolerances are stated in, so that the margin is visible in the test log."""
+    line = (f"[parity] {name}: max/rms {rel_err(a, b):.3e}  elem {elem_err(a, b):.3e}  rms {rms_err(a, b):.3e}  "
+            f"cos {cos_sim(a, b):.6f}")
+    print(line)
+    return line
 
 
 def rel_err(a, b):

@@ -74,6 +74,24 @@ def _worker(rank, world, port, q):
         with dp.no_sync():
             st.fire_grad_ready("head")
         assert len(dp._works) == 0 and float(st.grad[0]) == float(rank + 1)
+        # 4b) update_freq = 2 the way engine.train_one_epoch drives it: micro-batch 1 under no_sync(), micro-batch 2
+        #     synchronised -> every schedule reduces the ACCUMULATED gradient exactly once (a bucket reduced per
+        #     micro-batch would count the first micro-batch world_size times)
+        for mode in ("block", "step", "tail"):
+            dp.sync_mode = mode
+            st.grad.zero_()
+            with dp.no_sync():
+                st.grad.add_(float(rank + 1))
+                for tag in ("head", "blocks.1.", "blocks.0.", "embed"):
+                    st.fire_grad_ready(tag)
+            assert len(dp._works) == 0 and not dp._pending
+            st.grad.add_(10.0 * (rank + 1))
+            for tag in ("head", "blocks.1.", "blocks.0.", "embed"):
+                st.fire_grad_ready(tag)
+            dp.finish_gradient_sync()
+            dp.finish_gradient_sync()   # idempotent: clipping syncs first, step() must not reduce again
+            opt.step()
+            assert torch.equal(st.grad, torch.full_like(st.grad, 11.0 * sum(range(1, world + 1)))), mode
         # 5) metric meters reduce across ranks like the reference's SmoothedValue.synchronize_between_processes
         sv = utils.SmoothedValue()
         sv.update(float(rank + 1), n=1)

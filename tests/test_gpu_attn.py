@@ -29,21 +29,22 @@ def _ref(qkv, B, N, H, hd, dout=None):
 @pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 577, 4), (1, 300, 2),
                                    (1, 129, 1), (2, 144, 2), (1, 255, 3), (32, 197, 12), (13, 198, 12), (8, 577, 16), (5, 640, 7),
                                    (9, 385, 5), (3, 257, 4)])
-def test_attn_fwd(cuda_device, B, N, H):
+def test_attn_fwd(cuda_device, B, N, H, hd=64):
     from vision_transformers_torch_xla_b200 import _lib as L
-    hd = 64
     torch.manual_seed(0)
     qkv = torch.randn(B, N, 3 * H * hd, device=cuda_device).bfloat16()
     out = torch.full((B, N, H * hd), float("nan"), device=cuda_device, dtype=torch.bfloat16)
     lse = torch.full((B, H, N), float("nan"), device=cuda_device)
     L.attn_fwd(qkv, out, lse, B, N, H, hd, hd ** -0.5)
     ref, ref_lse, _ = _ref(qkv, B, N, H, hd)
+    # narrower heads: a score is a sum of hd (not 64) products, so the same bf16 roundings weigh sqrt(64 / hd) more
+    narrow = (64 / hd) ** 0.5 * (1.0 if hd == 64 else 1.15)
     # P is rounded to bf16 before P*V (as in every flash-attention bf16 kernel) and the output is bf16
-    assert elem_err(out.float(), ref) < 1e-2
+    assert elem_err(out.float(), ref) < 1e-2 * narrow
     # max|err| / rms: one bf16 rounding of the largest output element alone is 2^-9 * max|ref| (a 10-sigma outlier in a
     # 5M-element tensor), so the bound scales with max|ref| / rms
     half_ulp_of_max = 2.0 ** -9 * float(ref.abs().max() / ref.pow(2).mean().sqrt())
-    assert rel_err(out.float(), ref) < max(3e-2, 1.5 * half_ulp_of_max)
+    assert rel_err(out.float(), ref) < max(3e-2, 1.5 * half_ulp_of_max) * narrow
     # and never worse than 2x the error torch's own bf16 SDPA makes against the same fp32 reference
     q, k, v = qkv.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
     lib = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, H * hd)
@@ -54,9 +55,8 @@ def test_attn_fwd(cuda_device, B, N, H):
 @pytest.mark.parametrize("B,N,H", [(2, 128, 2), (2, 197, 3), (3, 198, 12), (1, 64, 1), (2, 256, 2), (1, 100, 2),
                                    (2, 577, 4), (1, 300, 2), (1, 640, 1), (1, 129, 1), (2, 144, 2), (1, 255, 3),
                                    (32, 197, 12), (13, 198, 12)])
-def test_attn_bwd(cuda_device, B, N, H):
+def test_attn_bwd(cuda_device, B, N, H, hd=64):
     from vision_transformers_torch_xla_b200 import _lib as L
-    hd = 64
     torch.manual_seed(1)
     qkv = torch.randn(B, N, 3 * H * hd, device=cuda_device).bfloat16()
     dout = torch.randn(B, N, H * hd, device=cuda_device).bfloat16()
@@ -68,27 +68,38 @@ def test_attn_bwd(cuda_device, B, N, H):
     _, _, ref = _ref(qkv, B, N, H, hd, dout)
     d = dqkv.float().view(B, N, 3, H * hd)
     r = ref.view(B, N, 3, H * hd)
+    narrow = (64 / hd) ** 0.5   # see test_attn_fwd
     for i, name in enumerate("qkv"):
         # P and dS are rounded to bf16 before the dV/dK/dQ GEMMs; outputs are bf16
-        assert elem_err(d[:, :, i], r[:, :, i]) < 2.5e-2, f"d{name}"
+        assert elem_err(d[:, :, i], r[:, :, i]) < 2.5e-2 * narrow, f"d{name}"
         # max|err| / rms grows with the largest element of the tensor (its own bf16 rounding is 2^-9 * max|ref|)
         half_ulp_of_max = 2.0 ** -9 * float(r[:, :, i].abs().max() / r[:, :, i].pow(2).mean().sqrt())
-        assert rel_err(d[:, :, i], r[:, :, i]) < max(6e-2, 3 * half_ulp_of_max), f"d{name}"
+        assert rel_err(d[:, :, i], r[:, :, i]) < max(6e-2, 3 * half_ulp_of_max) * narrow, f"d{name}"
+
+
+@pytest.mark.parametrize("hd", [48, 32, 16, 56])
+@pytest.mark.parametrize("B,N,H", [(3, 197, 3), (2, 100, 2), (2, 577, 3), (40, 197, 5)])
+def test_attn_narrow_heads(cuda_device, B, N, H, hd):
+    """head_dim < 64 (my_vit_mini: 48, /root/reference/models/my_vit.py:85-95): same kernels, the tensor maps describe
+    (head_dim, head slot, token, image) and TMA zero-fills / clips the columns up to the 64-wide tile; all three
+    regimes (N <= 128, 128 < N <= 256, N > 256), forward and backward."""
+    test_attn_fwd(cuda_device, B, N, H, hd)
+    test_attn_bwd(cuda_device, B, N, H, hd)
 
 
 def test_attn_unsupported_raises(cuda_device):
     from vision_transformers_torch_xla_b200 import _lib as L
-    qkv = torch.zeros(1, 16, 3 * 32, device=cuda_device, dtype=torch.bfloat16)
-    out = torch.zeros(1, 16, 32, device=cuda_device, dtype=torch.bfloat16)
+    qkv = torch.zeros(1, 16, 3 * 72, device=cuda_device, dtype=torch.bfloat16)
+    out = torch.zeros(1, 16, 72, device=cuda_device, dtype=torch.bfloat16)
     lse = torch.zeros(1, 1, 16, device=cuda_device)
     with pytest.raises(L.VitkError):
-        L.attn_fwd(qkv, out, lse, 1, 16, 1, 32, 32 ** -0.5)
+        L.attn_fwd(qkv, out, lse, 1, 16, 1, 72, 72 ** -0.5)   # wider than the 64-wide head tile
 
 
-@pytest.mark.parametrize("variant", ["1", "2", "3"])
-def test_attn_older_kernels_still_agree(cuda_device, variant, monkeypatch):
-    """The kernels the defaults replaced stay selectable (VITK_ATTN_FWD / VITK_ATTN_BWD are read once per process, so
-    this runs them in a child process) and must give the same answers."""
+@pytest.mark.parametrize("variant", ["1"])
+def test_attn_tiled_kernels_still_agree(cuda_device, variant, monkeypatch):
+    """The simple one-CTA-per-tile kernels (the N <= 128 path) stay selectable for every N <= 256 (VITK_ATTN_FWD /
+    VITK_ATTN_BWD = 1, read once per process, so this runs them in a child process) and must give the same answers."""
     import os
     import subprocess
     import sys
@@ -109,29 +120,4 @@ def test_attn_older_kernels_still_agree(cuda_device, variant, monkeypatch):
         "assert e1 < 2e-2 and e2 < 3e-2, (e1, e2)\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     env = dict(os.environ, VITK_ATTN_FWD=variant, VITK_ATTN_BWD=variant)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0, r.stderr[-2000:]
-
-
-def test_attn_long_sequence_pingpong_variant(cuda_device):
-    """VITK_ATTN_BWD_LONG=5 (two-warpgroup variant of the N > 256 backward) gives the same gradients."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import torch, sys; sys.path.insert(0, %r)\n"
-        "from vision_transformers_torch_xla_b200 import _lib as L\n"
-        "torch.manual_seed(0); B, N, H = 3, 577, 5\n"
-        "qkv = torch.randn(B, N, 3 * H * 64, device='cuda').bfloat16(); dout = torch.randn(B, N, H * 64, device='cuda').bfloat16()\n"
-        "out = torch.empty(B, N, H * 64, device='cuda', dtype=torch.bfloat16); lse = torch.empty(B, H, N, device='cuda')\n"
-        "dqkv = torch.empty_like(qkv)\n"
-        "L.attn_fwd(qkv, out, lse, B, N, H, 64, 0.125); L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, 64, 0.125)\n"
-        "q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0)\n"
-        "q.requires_grad_(True); k.requires_grad_(True); v.requires_grad_(True)\n"
-        "o = torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v\n"
-        "o.transpose(1, 2).reshape(B, N, H * 64).backward(dout.float())\n"
-        "g = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B, N, 3 * H * 64)\n"
-        "e2 = ((dqkv.float() - g).abs().max() / g.abs().max()).item()\n"
-        "assert e2 < 3e-2, e2\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VITK_ATTN_BWD_LONG="5"), capture_output=True, text=True,
-                       timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]

@@ -110,11 +110,15 @@ def test_prefix_pool_embed_bwd(cuda_device):
     gg = torch.randn(B, N, D, device=cuda_device)
     gp = torch.empty(B * (N - prefix), D, device=cuda_device, dtype=torch.bfloat16)
     dpos = torch.zeros(N, D, device=cuda_device)
-    dpre = torch.zeros(prefix, D, device=cuda_device)
-    L.embed_bwd(gg, gp, dpos, dpre, B, N, D, prefix)
+    # the two token gradients live in separate rows of the flat gradient buffer and are ACCUMULATED into
+    dcls, ddist = torch.ones(D, device=cuda_device), torch.full((D,), 2.0, device=cuda_device)
+    L.embed_bwd(gg, gp, dpos, dcls, ddist, B, N, D, prefix)
     assert torch.equal(gp.view(B, N - prefix, D), gg[:, prefix:].bfloat16())
     assert rel_err(dpos, gg.sum(0)) < 1e-5
-    assert rel_err(dpre, gg[:, :prefix].sum(0)) < 1e-5
+    assert rel_err(dcls - 1.0, gg[:, 0].sum(0)) < 1e-5 and rel_err(ddist - 2.0, gg[:, 1].sum(0)) < 1e-5
+    dpos.zero_()
+    L.embed_bwd(gg, gp, dpos, None, None, B, N, D, prefix)   # frozen tokens
+    assert rel_err(dpos, gg.sum(0)) < 1e-5
 
 
 @pytest.mark.parametrize("rows,cols", [(1576, 576), (5000, 3072), (100, 1000), (7, 768)])
@@ -232,3 +236,43 @@ def test_sumsq(cuda_device):
     out = torch.zeros(1, device=cuda_device)
     L.sumsq(x, out)
     assert abs(out.item() - x.double().pow(2).sum().item()) < 1e-3 * x.numel() ** 0.5 * 10
+    xb = torch.randn(1_000_008, device=cuda_device).bfloat16()[:1_000_003].clone()
+    out.zero_()
+    L.sumsq(xb, out)
+    assert abs(out.item() - xb.double().pow(2).sum().item()) < 1e-3 * xb.numel() ** 0.5 * 10
+
+
+def test_adamw_bf16_gradient_source_and_device_scale(cuda_device):
+    """vitk_adamw_flat reading the gradient from the bf16 copy the data-parallel layer all-reduces, times a device-side
+    scalar (the clip coefficient): equals torch.optim.AdamW fed bf16(g) * grad_scale * coef; the fp32 buffer is zeroed."""
+    from vision_transformers_torch_xla_b200 import _lib as L
+    torch.manual_seed(0)
+    n = 64 * 21
+    p0 = torch.randn(n, device=cuda_device)
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pr], lr=1e-2, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+    p, m, v = p0.clone(), torch.zeros(n, device=cuda_device), torch.zeros(n, device=cuda_device)
+    coef = torch.tensor([0.37], device=cuda_device)
+    for step in range(1, 4):
+        g = torch.randn(n, device=cuda_device)
+        g16 = (g * 8.0).bfloat16()
+        pr.grad = g16.float() * 0.125 * 0.37
+        opt.step()
+        junk = torch.full((n,), 123.0, device=cuda_device)   # the fp32 buffer must not be read, only zeroed
+        L.adamw_flat(p, junk, m, v, None, None, None, 64, [1e-2], [0.05], 0.9, 0.999, 1e-8, step, grad_scale=0.125,
+                     zero_grad=True, g_bf16=g16, grad_scale_dev=coef)
+        assert float(junk.abs().max()) == 0.0
+        assert rel_err(p, pr.detach()) < 1e-5
+
+
+def test_scale_f32_and_clip_coef(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    x = torch.randn(1003, device=cuda_device)
+    want = x * 0.25
+    L.scale_f32_(x, torch.tensor(0.25, device=cuda_device))
+    assert torch.equal(x, want)
+    buf = torch.tensor([16.0, 0.0, 0.0], device=cuda_device)          # sum of squares 16 -> norm of the SUM 4
+    L.clip_coef(buf[0:1], 0.5, 1.0, buf[1:2], buf[2:3])               # mean over 2 replicas: norm 2 -> coef 1 / (2 + 1e-6)
+    assert abs(buf[2].item() - 2.0) < 1e-6 and abs(buf[1].item() - 1.0 / (2.0 + 1e-6)) < 1e-6
+    L.clip_coef(buf[0:1], 0.5, 10.0, buf[1:2], None)
+    assert buf[1].item() == 1.0

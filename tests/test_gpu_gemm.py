@@ -6,7 +6,7 @@ and K=3072 accumulate-order noise included); bf16 outputs add one bf16 rounding 
 import pytest
 import torch
 
-from conftest import elem_err, rel_err
+from conftest import elem_err, rel_err, rms_err
 
 pytestmark = pytest.mark.gpu
 
@@ -74,6 +74,48 @@ def test_fprop_gelu_dual(cuda_device):
     g.sum().backward()
     assert elem_err(out.float(), g) < BF16_TOL
     assert elem_err(aux.float(), h.grad) < BF16_TOL  # aux = gelu'(h)
+
+
+@pytest.mark.parametrize("M,N,K", [(500, 3072, 768), (394, 768, 192), (50432, 1536, 384), (130, 256, 64), (2049, 4096, 1024)])
+def test_gelu_q8_round_trip(cuda_device, M, N, K):
+    """VITK_EPI_GELU_Q8 / VITK_EPI_DGELU_Q8: gelu'(h) travels as one byte on the grid (q - 27) / 200.  The forward's
+    activation output is unchanged; the stored derivative is within half a grid step (0.0025) of gelu'(h), exactly 0 /
+    1 for saturated units; the backward multiplies by the decoded byte."""
+    from vision_transformers_torch_xla_b200 import _lib as L
+    a = _mk((M, K), cuda_device, seed=1).bfloat16()
+    w = _mk((N, K), cuda_device, 2.0 / K ** 0.5, seed=2).bfloat16()   # pre-activations of std ~2: both tails saturate
+    bias = _mk((N,), cuda_device, seed=3)
+    out = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    aux = torch.full((M, N), 255, device=cuda_device, dtype=torch.uint8)
+    L.gemm(a, w, out, M=M, N=N, K=K, epilogue=L.EPI_GELU_Q8, bias=bias, aux=aux)
+    h = (a.float() @ w.float().t() + bias).requires_grad_(True)
+    g = torch.nn.functional.gelu(h)
+    g.sum().backward()
+    assert elem_err(out.float(), g) < BF16_TOL
+    dec = (aux.float() - 27.0) / 200.0
+    # (+ the fp32 accumulation-order noise of h, amplified by |gelu''| <= 0.8)
+    assert float((dec - h.grad).abs().max()) <= 0.0025 + 2e-4
+    assert float(dec[h.detach() > 6].sub(1.0).abs().max()) == 0.0 and float(dec[h.detach() < -6].abs().max()) == 0.0
+    # backward: dh = (dy @ W2) * gelu'
+    dy = _mk((M, K), cuda_device, seed=4).bfloat16()
+    w2 = _mk((K, N), cuda_device, 0.05, seed=5).bfloat16()
+    dh = torch.empty((M, N), device=cuda_device, dtype=torch.bfloat16)
+    rs = None
+    L.gemm(dy, w2, dh, M=M, N=N, K=K, epilogue=L.EPI_DGELU_Q8, b_mn=True, aux=aux, rowscale=rs)
+    assert elem_err(dh.float(), (dy.float() @ w2.float()) * dec) < BF16_TOL
+    # and against the exact derivative: the quantisation adds at most 0.0025 * |dy W2| per element
+    exact = (dy.float() @ w2.float()) * h.grad
+    assert rms_err(dh.float(), exact) < 6e-3
+
+
+def test_gelu_q8_rejects_other_widths(cuda_device):
+    from vision_transformers_torch_xla_b200 import _lib as L
+    a = torch.zeros(256, 64, device=cuda_device, dtype=torch.bfloat16)
+    w = torch.zeros(576, 64, device=cuda_device, dtype=torch.bfloat16)
+    out = torch.zeros(256, 576, device=cuda_device, dtype=torch.bfloat16)
+    aux = torch.zeros(256, 576, device=cuda_device, dtype=torch.uint8)
+    with pytest.raises(L.VitkError):
+        L.gemm(a, w, out, M=256, N=576, K=64, epilogue=L.EPI_GELU_Q8, aux=aux)
 
 
 # K <= 1536 takes the TMA residual-ring epilogue (panels prefetched across tiles, TMA stores), larger K the

@@ -18,7 +18,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvitk.so")
 
-EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_ATOMIC, EPI_PATCH = range(7)
+EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_ATOMIC, EPI_PATCH, EPI_GELU_Q8, EPI_DGELU_Q8 = range(9)
 
 #: every symbol include/vitk.h declares (tests check the library exports exactly these)
 EXPORTED_SYMBOLS = (
@@ -275,6 +275,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     for t, nm in ((bias, "bias"), (resid, "resid"), (rowscale, "rowscale"), (colscale, "colscale"), (pos, "pos")):
         if t is not None:
             _req(t, torch.float32, f"gemm {nm}")
+    if epilogue in (EPI_GELU, EPI_DGELU, EPI_GELU_Q8, EPI_DGELU_Q8):
+        if aux is None:
+            raise VitkError("gemm: the GELU epilogues need the aux (derivative) buffer")
+        _req(aux, torch.uint8 if epilogue in (EPI_GELU_Q8, EPI_DGELU_Q8) else torch.bfloat16, "gemm aux")
     role = "wgrad" if epilogue == EPI_ATOMIC else ("dgrad" if b_mn else "fprop")
     with _Timed(f"gemm.{role}.epi{epilogue} {M}x{N}x{K}", 2.0 * M * N * K):
         _check(load().vitk_gemm_bf16(ctypes.byref(args), _stream()), "vitk_gemm_bf16")

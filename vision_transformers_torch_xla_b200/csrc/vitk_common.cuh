@@ -42,6 +42,8 @@ int vitk_make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
 int vitk_make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                       uint64_t ld1_elems, uint64_t ld2_elems, uint64_t ld3_elems, uint32_t b0, uint32_t b1, uint32_t b2,
                       uint32_t b3);
+int vitk_make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
+                         uint32_t box_inner, uint32_t box_outer);
 int vitk_make_tmap_2d_sw64(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
                            uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer);
 int vitk_num_sms();
@@ -463,6 +465,19 @@ __device__ __forceinline__ void gelu_fwd_bwd(float h, float& act, float& deriv) 
 #else
   gelu_fwd_bwd_exact(h, act, deriv);
 #endif
+}
+
+// gelu'(h) on a fixed one-byte grid: q = round(200 g) + 27, g ~= (q - 27) / 200.  The range [-0.135, 1.14] covers
+// gelu' (min -0.1290, max 1.1290) and 0 and 1 land exactly on grid points, so saturated units keep exactly gelu' = 0 / 1.
+// Rounding without F2I: adding 2^23 puts the rounded integer (round-to-nearest-even) into the low mantissa bits.
+__device__ __forceinline__ uint32_t gelu_q8_bits(float g) { return __float_as_uint(fmaf(g, 200.0f, 8388608.0f + 27.0f)); }
+__device__ __forceinline__ uint32_t gelu_q8_pack4(float g0, float g1, float g2, float g3) {
+  const uint32_t lo = __byte_perm(gelu_q8_bits(g0), gelu_q8_bits(g1), 0x0040);   // bytes: g0.b0, g1.b0
+  const uint32_t hi = __byte_perm(gelu_q8_bits(g2), gelu_q8_bits(g3), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ float gelu_q8_decode(uint32_t word, int byte) {
+  return fmaf((float)((word >> (8 * byte)) & 0xffu), 0.005f, -0.135f);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -62,8 +62,12 @@ template <int EPI>
 constexpr uint32_t kStgBytes = (EPI == EPI_BF16) ? 2048u : 4096u;
 // GELU / x GELU' epilogues with 64 columns per epilogue warp leave (and, for the aux operand, enter) through TMA:
 // two [32 rows][64 B] panels per warp in the 64-byte-swizzle layout (see the epilogue branch of gemm_kernel).
+template <int EPI>
+constexpr bool kGeluFwd = (EPI == EPI_GELU || EPI == EPI_GELU_Q8);
+template <int EPI>
+constexpr bool kGeluBwd = (EPI == EPI_DGELU || EPI == EPI_DGELU_Q8);
 template <int EPI, int PART_N>
-constexpr bool kTmaEpi = (EPI == EPI_GELU || EPI == EPI_DGELU) && PART_N == 64;
+constexpr bool kTmaEpi = (kGeluFwd<EPI> || kGeluBwd<EPI>) && PART_N == 64;
 // Residual epilogue through TMA: every epilogue warp owns a ring of three [32 rows][128 B] fp32 panels (128-byte
 // swizzle).  The residual panels of the warp's tile sequence are loaded up to two panels ahead (across tile
 // boundaries: the tile schedule is static), the sum is formed in place and leaves by a TMA store, so the epilogue
@@ -680,7 +684,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       float rs = 1.0f;
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_TMA || EPI == EPI_RESID || EPI == EPI_RESID_TMA || EPI == EPI_DGELU) {
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_TMA || EPI == EPI_RESID || EPI == EPI_RESID_TMA || kGeluBwd<EPI>) {
         if (p.rowscale != nullptr && row < p.M) rs = __ldg(p.rowscale + row / p.rows_per_group);
       }
       if constexpr (kTmaEpi<EPI, PART_N>) {
@@ -692,7 +696,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int row0 = m_blk * TILE_M + (int)rank * BLOCK_M + quad * 32;
         const int colp = n_blk * BLOCK_N + part * PART_N;
         const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BLOCK_N + part * PART_N;
-        if constexpr (EPI == EPI_DGELU) {
+        if constexpr (EPI == EPI_DGELU_Q8) {
+          // aux = gelu'(h) as one byte per element: this warp's [32 rows][64 B] box (64-byte swizzle) lands in the UPPER
+          // half of the warp's 4 KB panel while the tile's MMAs still run; every lane copies its 64-byte row into
+          // registers, and only after the whole warp has done so is the panel overwritten by the [32 rows][128 B] bf16
+          // output rows (128-byte swizzle) that leave as one TMA box
+          if (elect_one()) {
+            tma_store_wait_read();   // the previous tile's output panel has left the buffer
+            mbar_arrive_expect_tx(&aux_bar[ew], 2048);
+            tma_load_2d(buf1, &tmAux, &aux_bar[ew], colp, row0);
+          }
+          __syncwarp();
+          mbar_wait(&tmem_full[as], aphase);
+          tc_fence_after();
+          uint32_t acc0[32], acc1[32];
+          tmem_ld_32x32(tacc, acc0);
+          tmem_ld_32x32(tacc + 32, acc1);
+          mbar_wait(&aux_bar[ew], tphase);
+          uint4 dq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dq[u] = *reinterpret_cast<const uint4*>(buf1 + stg_b16(lane, u));
+          tmem_ld_wait();
+          release_acc();
+          __syncwarp();   // every lane holds its derivative row: the panel may be overwritten
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t* a = (u < 4 ? acc0 : acc1) + (u & 3) * 8;
+            const uint4 dw = dq[u >> 1];
+            const uint32_t w0 = (u & 1) ? dw.z : dw.x, w1 = (u & 1) ? dw.w : dw.y;   // 8 derivative bytes of this chunk
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(a[0]) * (gelu_q8_decode(w0, 0) * rs), __uint_as_float(a[1]) * (gelu_q8_decode(w0, 1) * rs));
+            o.y = pack_bf16x2(__uint_as_float(a[2]) * (gelu_q8_decode(w0, 2) * rs), __uint_as_float(a[3]) * (gelu_q8_decode(w0, 3) * rs));
+            o.z = pack_bf16x2(__uint_as_float(a[4]) * (gelu_q8_decode(w1, 0) * rs), __uint_as_float(a[5]) * (gelu_q8_decode(w1, 1) * rs));
+            o.w = pack_bf16x2(__uint_as_float(a[6]) * (gelu_q8_decode(w1, 2) * rs), __uint_as_float(a[7]) * (gelu_q8_decode(w1, 3) * rs));
+            *reinterpret_cast<uint4*>(buf0 + lane * 128 + ((u ^ (lane & 7)) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (elect_one()) {
+            tma_store_2d(&tmOut, buf0, colp, row0);
+            tma_store_commit();
+          }
+          __syncwarp();
+          tphase ^= 1;
+        } else if constexpr (EPI == EPI_DGELU) {
           // aux = gelu'(h) of this warp's [32 rows][64 columns] is fetched while the tile's MMAs still run: ONE box of
           // 128-byte rows (128-byte swizzle: chunk u of row r at u ^ (r & 7)), multiplied in place and stored as one box,
           // so every row segment that reaches L2 is a whole line (with two 64-byte boxes per row the L2 write hit
@@ -749,7 +796,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
             tmem_ld_wait();
             if (hf == 1) release_acc();
-            uint32_t act[16], der[16];
+            constexpr bool Q8 = (EPI == EPI_GELU_Q8);
+            uint32_t act[16], der[Q8 ? 8 : 16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float a0, a1, a2, a3, g0, g1, g2, g3;
@@ -759,16 +807,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               gelu_fwd_bwd(__uint_as_float(acc[j * 4 + 3]) + bb[j].w, a3, g3);
               act[j * 2] = pack_bf16x2(a0, a1);
               act[j * 2 + 1] = pack_bf16x2(a2, a3);
-              der[j * 2] = pack_bf16x2(g0, g1);
-              der[j * 2 + 1] = pack_bf16x2(g2, g3);
+              if constexpr (Q8) {
+                der[j] = gelu_q8_pack4(g0, g1, g2, g3);
+              } else {
+                der[j * 2] = pack_bf16x2(g0, g1);
+                der[j * 2 + 1] = pack_bf16x2(g2, g3);
+              }
             }
             // the panels of the previous half (or tile) must have been read by the TMA unit before they are overwritten
             if (elect_one()) tma_store_wait_read();
             __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 4; ++u)
               *reinterpret_cast<uint4*>(buf0 + stg_b16(lane, u)) = make_uint4(act[u * 4], act[u * 4 + 1], act[u * 4 + 2], act[u * 4 + 3]);
-              *reinterpret_cast<uint4*>(buf1 + stg_b16(lane, u)) = make_uint4(der[u * 4], der[u * 4 + 1], der[u * 4 + 2], der[u * 4 + 3]);
+            if constexpr (Q8) {   // [32 rows][32 B], 32-byte swizzle: 16-byte chunk u of row r at u ^ ((r >> 2) & 1)
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                *reinterpret_cast<uint4*>(buf1 + lane * 32 + ((u ^ ((lane >> 2) & 1)) << 4)) =
+                    make_uint4(der[u * 4], der[u * 4 + 1], der[u * 4 + 2], der[u * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(buf1 + stg_b16(lane, u)) = make_uint4(der[u * 4], der[u * 4 + 1], der[u * 4 + 2], der[u * 4 + 3]);
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -980,11 +1040,18 @@ inline bool bf16_tma_ok(const vitk_gemm_args* a) {
   return enabled && ((uintptr_t)a->out & 15) == 0 && a->ld_out % 8 == 0 && a->N % 8 == 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool CTA2>
+// Short-K launches (K <= VITK_GEMM_EW16_MAXK, e.g. ViT-S: K = 384 is six k-blocks per tile) are bound by the epilogue,
+// not the main loop: the bf16 TMA epilogue then runs with 16 warps (one 64-column box per warp) instead of 8.
+int ew16_max_k() {
+  static const int v = [] { const char* e = getenv("VITK_GEMM_EW16_MAXK"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, bool CTA2, bool WIDE_EPI = false>
 int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   // 16 epilogue warps for the GELU epilogues (~20 instructions per element); 8 elsewhere.  With BLOCK_N = 192 and
   // 16 warps a warp's share is 48 columns, which is not a whole number of 32-column panels -> keep 8 there.
-  constexpr int EW = ((EPI == EPI_GELU || EPI == EPI_DGELU) && BLOCK_N != 192) ? 16 : 8;
+  constexpr int EW = (((kGeluFwd<EPI> || kGeluBwd<EPI>) && BLOCK_N != 192) || WIDE_EPI) ? 16 : 8;
   using Cfg = TileCfg<BLOCK_N, EW, kStgBytesFor<EPI, BLOCK_N, CTA2>, CTA2>;
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap tmA, tmB;
@@ -1009,8 +1076,18 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
     rc = vitk_make_tmap_2d(&tmAux, a->resid, 4, a->N, a->M, a->ld_resid, 32, 32);
     if (rc) return rc;
   }
+  if ((EPI == EPI_GELU_Q8 || EPI == EPI_DGELU_Q8) && !kTmaEpi<EPI, BLOCK_N / (EW / 4)>)
+    return vitk_set_error(VITK_ERR_UNSUPPORTED, "gemm: the one-byte GELU' epilogues need N %% 256 == 0 (N=%d)", a->N);
   if (kTmaEpi<EPI, BLOCK_N / (EW / 4)>) {
-    if (EPI == EPI_DGELU) {   // [32 rows][128 B] boxes, 128-byte swizzle
+    if (EPI == EPI_DGELU_Q8) {  // out: [32 rows][128 B] bf16, 128-byte swizzle; aux: [32 rows][64 B] uint8, 64-byte swizzle
+      rc = vitk_make_tmap_2d(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 64, 32);
+      if (rc) return rc;
+      rc = vitk_make_tmap_2d_u8(&tmAux, a->aux, a->N, a->M, a->ld_aux, 64, 32);
+    } else if (EPI == EPI_GELU_Q8) {  // out: [32 rows][64 B] bf16 (64-byte swizzle); aux: [32 rows][32 B] uint8 (32-byte swizzle)
+      rc = vitk_make_tmap_2d_sw64(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 32, 32);
+      if (rc) return rc;
+      rc = vitk_make_tmap_2d_u8(&tmAux, a->aux, a->N, a->M, a->ld_aux, 32, 32);
+    } else if (EPI == EPI_DGELU) {   // [32 rows][128 B] boxes, 128-byte swizzle
       rc = vitk_make_tmap_2d(&tmOut, a->out, 2, a->N, a->M, a->ld_out, 64, 32);
       if (rc) return rc;
       rc = vitk_make_tmap_2d(&tmAux, a->aux, 2, a->N, a->M, a->ld_aux, 64, 32);
@@ -1082,11 +1159,17 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
   if (!amn && !bmn) {
     switch (a->epilogue) {
       case EPI_BF16:
+        if constexpr (BLOCK_N == 256) {
+          if (bf16_tma_ok(a) && a->K <= ew16_max_k()) return launch_gemm<BLOCK_N, false, false, EPI_BF16_TMA, CTA2, true>(a, stream);
+        }
         if constexpr (BLOCK_N % 128 == 0) {
           if (bf16_tma_ok(a)) return launch_gemm<BLOCK_N, false, false, EPI_BF16_TMA, CTA2>(a, stream);
         }
         return launch_gemm<BLOCK_N, false, false, EPI_BF16, CTA2>(a, stream);
       case EPI_GELU:  return launch_gemm<BLOCK_N, false, false, EPI_GELU, CTA2>(a, stream);
+      case EPI_GELU_Q8:
+        if constexpr (BLOCK_N == 256) return launch_gemm<BLOCK_N, false, false, EPI_GELU_Q8, CTA2>(a, stream);
+        break;
       case EPI_RESID:
         if constexpr (CTA2 || BLOCK_N < 256) {
           if (a->K <= kResidTmaMaxK && resid_tma_ok(a)) return launch_gemm<BLOCK_N, false, false, EPI_RESID_TMA, CTA2>(a, stream);
@@ -1098,11 +1181,17 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
   } else if (!amn && bmn) {
     switch (a->epilogue) {
       case EPI_BF16:
+        if constexpr (BLOCK_N == 256) {
+          if (bf16_tma_ok(a) && a->K <= ew16_max_k()) return launch_gemm<BLOCK_N, false, true, EPI_BF16_TMA, CTA2, true>(a, stream);
+        }
         if constexpr (BLOCK_N % 128 == 0) {
           if (bf16_tma_ok(a)) return launch_gemm<BLOCK_N, false, true, EPI_BF16_TMA, CTA2>(a, stream);
         }
         return launch_gemm<BLOCK_N, false, true, EPI_BF16, CTA2>(a, stream);
       case EPI_DGELU: return launch_gemm<BLOCK_N, false, true, EPI_DGELU, CTA2>(a, stream);
+      case EPI_DGELU_Q8:
+        if constexpr (BLOCK_N == 256) return launch_gemm<BLOCK_N, false, true, EPI_DGELU_Q8, CTA2>(a, stream);
+        break;
       case EPI_F32:   return launch_gemm<BLOCK_N, false, true, EPI_F32, CTA2>(a, stream);
     }
   }
@@ -1134,6 +1223,9 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream_) {
   VITK_REQUIRE(a->ld_out % 8 == 0 || a->epilogue == EPI_F32, VITK_ERR_ALIGN, "gemm: ld_out must be a multiple of 8");
   if (a->epilogue == EPI_GELU || a->epilogue == EPI_DGELU)
     VITK_REQUIRE(a->aux != nullptr && a->ld_aux % 8 == 0, VITK_ERR_ALIGN, "gemm: aux pointer/ld required for GELU epilogues");
+  if (a->epilogue == EPI_GELU_Q8 || a->epilogue == EPI_DGELU_Q8)
+    VITK_REQUIRE(a->aux != nullptr && a->ld_aux % 16 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && a->N % 256 == 0,
+                 VITK_ERR_ALIGN, "gemm: one-byte GELU' epilogues need a 16-byte aligned aux, ld_aux %% 16 == 0 and N %% 256 == 0");
   if (a->epilogue == EPI_RESID)
     VITK_REQUIRE(a->resid != nullptr && a->ld_resid % 4 == 0, VITK_ERR_ALIGN, "gemm: resid pointer/ld required");
   if (a->epilogue == EPI_PATCH)

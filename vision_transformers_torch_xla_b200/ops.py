@@ -14,6 +14,7 @@ next stage's backward so that no separate cast pass is needed.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -24,6 +25,25 @@ from .store import ParamStore
 
 def _empty(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
+
+
+#: storage of gelu'(fc1 out) between forward and backward: "bf16" = two bytes per element (default); "q8" = one byte on a
+#: fixed grid of step 0.005 that holds 0 and 1 exactly (include/vitk.h: VITK_EPI_GELU_Q8; |error| <= 0.0025, what a bf16
+#: rounding costs at gelu' ~ 1; needs a hidden width that is a multiple of 256).  q8 saves 1.9 GB of activations per ViT-B
+#: step and 25 % of fc1's output bytes, but measured on B200 (same box, alternating runs, profiles/r02_ab_gelu_q8.txt) it
+#: buys no time where it was meant to: ViT-B fc1 fprop 234.8 -> 235.4 us, fc2 dgrad 218.7 -> 222.4 us (7 975 / 8 021 vs
+#: 8 001 / 7 974 img/s); ViT-S fc2 dgrad 67.7 -> 80.8 us (the decode costs issue slots the short-K epilogue does not have);
+#: only ViT-L/384's fc1 fprop gains (267 -> 241 us, 666 -> 670 img/s).  The GELU epilogues are not byte-bound.
+GELU_AUX = os.environ.get("VITK_GELU_AUX", "bf16")
+if GELU_AUX not in ("q8", "bf16"):
+    raise ValueError(f"VITK_GELU_AUX={GELU_AUX!r}: expected 'q8' or 'bf16'")
+
+
+def _gelu_codes(F: int):
+    """(forward epilogue, backward epilogue, dtype of the saved derivative) for a hidden width F."""
+    if GELU_AUX == "q8" and F % 256 == 0:
+        return L.EPI_GELU_Q8, L.EPI_DGELU_Q8, torch.uint8
+    return L.EPI_GELU, L.EPI_DGELU, torch.bfloat16
 
 
 def _require_f32_cuda(x: torch.Tensor, what: str) -> torch.Tensor:
@@ -133,9 +153,10 @@ class BlockFn(torch.autograd.Function):
         ln2 = _empty((M, D), torch.bfloat16, dev)
         mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
         L.layernorm_fwd(x_mid, blk.norm2.weight.data, blk.norm2.bias.data, ln2, mean2, rstd2, M, D, eps)
-        h = _empty((M, F), torch.bfloat16, dev)  # receives gelu'(fc1 out): all the backward needs of it
+        epi_gelu, _, aux_dtype = _gelu_codes(F)
+        h = _empty((M, F), aux_dtype, dev)  # receives gelu'(fc1 out): all the backward needs of it
         act = _empty((M, F), torch.bfloat16, dev)
-        L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=L.EPI_GELU, bias=bias(blk.mlp.fc1), aux=h)
+        L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=epi_gelu, bias=bias(blk.mlp.fc1), aux=h)
         x_out = _empty((B, N, D), torch.float32, dev)
         L.gemm(act, sh(blk.mlp.fc2.weight), x_out, M=M, N=D, K=F, epilogue=L.EPI_RESID, bias=bias(blk.mlp.fc2),
                resid=x_mid, rowscale=rs2, rows_per_group=N, colscale=g2)
@@ -180,7 +201,7 @@ class BlockFn(torch.autograd.Function):
         wgrad(gb2, act, blk.mlp.fc2, D, F)
         ls_bwd_grad(blk.ls2, blk.mlp.fc2)
         dh = act  # reuse: gelu output is dead after the fc2 wgrad above
-        L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
+        L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=_gelu_codes(F)[1], b_mn=True, aux=h)
         del gb2, h
         wgrad(dh, ln2, blk.mlp.fc1, F, D)
         dln2 = ln2  # reuse: ln2 output is dead after the fc1 wgrad above
@@ -492,9 +513,9 @@ class MlpFn(torch.autograd.Function):
         dev = x.device
         sh = store.shadow_of
         xb = _to_bf16(x).view(M, D)
-        h = _empty((M, F), torch.bfloat16, dev)
+        h = _empty((M, F), _gelu_codes(F)[2], dev)
         act = _empty((M, F), torch.bfloat16, dev)
-        L.gemm(xb, sh(mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=L.EPI_GELU,
+        L.gemm(xb, sh(mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=_gelu_codes(F)[0],
                bias=None if mlp.fc1.bias is None else mlp.fc1.bias.data, aux=h)
         out = _empty(x.shape[:-1] + (O,), torch.float32, dev)
         L.gemm(act, sh(mlp.fc2.weight), out, M=M, N=O, K=F, epilogue=L.EPI_F32,
@@ -515,7 +536,7 @@ class MlpFn(torch.autograd.Function):
         L.gemm(dyb, act, gr(mlp.fc2.weight), M=O, N=F, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
                colsum=None if mlp.fc2.bias is None else gr(mlp.fc2.bias))
         dh = act
-        L.gemm(dyb, sh(mlp.fc2.weight), dh, M=M, N=F, K=O, epilogue=L.EPI_DGELU, b_mn=True, aux=h)
+        L.gemm(dyb, sh(mlp.fc2.weight), dh, M=M, N=F, K=O, epilogue=_gelu_codes(F)[1], b_mn=True, aux=h)
         L.gemm(dh, xb, gr(mlp.fc1.weight), M=F, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
                colsum=None if mlp.fc1.bias is None else gr(mlp.fc1.bias))
         dx = _empty(ctx.shape, torch.float32, dy.device)
