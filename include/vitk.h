@@ -56,7 +56,8 @@ enum vitk_epilogue {
   VITK_EPI_F32 = 3,    /* out_f32 = acc + bias                                        (head)       */
   VITK_EPI_DGELU = 4,  /* out_bf16 = rowscale[m/g] * acc * aux_bf16[m,n], aux = gelu'(h) (fc2 dgrad)  */
   VITK_EPI_ATOMIC = 5, /* out_f32 += acc   via red.global.add (split-K)               (wgrad)      */
-  VITK_EPI_PATCH = 6,  /* out_f32[b*(P+prefix)+prefix+t, n] = acc + bias[n] + pos[prefix+t, n]     */
+  VITK_EPI_PATCH = 6,  /* out_f32[b*(P+prefix)+prefix+t, n] = acc + bias[n] + pos[prefix+t, n]; rows are patches (b, t), or
+                          the padded rows (b, gy, gx') of an a_image operand                         */
   /* GELU / x GELU' with the derivative kept in ONE byte per element: aux_u8 = round(200 * gelu'(h)) + 27, i.e. a fixed
    * grid of step 0.005 over [-0.135, 1.14] that represents gelu'(h) = 0 and 1 exactly (|error| <= 0.0025: what a bf16
    * rounding costs at gelu' ~ 1); fc1 writes 3 instead of 4 bytes per hidden element, fc2's dgrad reads 1 instead of 2.
@@ -89,6 +90,16 @@ typedef struct vitk_gemm_args {
   int32_t block_n;     /* 0 = auto; otherwise 128, 192 or 256                                      */
   float* colsum_out;   /* ATOMIC with MN-major A: colsum_out[m] += sum_k A[k, m] (the bias gradient of the same
                           wgrad, summed out of the staged smem tiles by the epilogue warps), or NULL */
+  /* im2col-free patch embedding (PatchEmbed = Conv2d(k = s = patch), vision_transformer.py:552-560): an operand may be a
+   * bf16 NCHW image batch [B, img_c, img_h, img_w] read through TMA AS its patch matrix, never materialised:
+   *   row    = (b * (img_h / patch) + gy) * img_gwp + gx'   gx' in [0, img_gwp); gx' >= img_w / patch are zero rows
+   *   column = (c * patch + py) * patch + px                == proj.weight.view(D, -1) column order
+   * img_gwp = the patch-grid width rounded up to a multiple of 8 (TMA boxes cover 8 neighbouring patches); patch = 16.
+   * a_image: A is such an image (K-major use; with VITK_EPI_PATCH the epilogue maps row -> token and skips the pad rows),
+   *          M = B * (img_h / patch) * img_gwp, K = img_c * patch * patch.
+   * b_image: B is such an image in MN-major use (the weight gradient dW[D, K'] += gp^T patches), K = rows as above. */
+  int32_t a_image, b_image;
+  int32_t img_c, img_h, img_w, img_patch, img_gwp;
 } vitk_gemm_args;
 
 int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);
@@ -127,7 +138,8 @@ int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const floa
  * Patch embedding helpers (PatchEmbed + _pos_embed: vision_transformer.py:552-560, 743-780)
  * patchify: fp32 NCHW image -> bf16 [B*P, C*ps*ps] rows in (c, ph, pw) order == proj.weight.view(D,-1)
  * prefix_rows: x[b, j, :] = prefix_tok[j, :] + pos[j, :] for j < prefix (cls / dist tokens)
- * embed_bwd: from g fp32 [B, N, D]: gp_bf16 [B*P, D] (patch rows), dpos[N, D] += sum_b g,
+ * embed_bwd: from g fp32 [B, N, D]: gp_bf16 [B*P, D] (patch rows; with gw > 0 the padded row order of an image operand:
+ *            [B * (P / gw) * gwp, D], row (b, gy, gx'), zeros for gx' >= gw), dpos[N, D] += sum_b g,
  *            dprefix0[D] += sum_b g[b, 0, :] (cls_token), dprefix1[D] += sum_b g[b, 1, :] (dist_token, prefix == 2);
  *            either may be NULL (frozen token)
  * ---------------------------------------------------------------------------------------------- */
@@ -136,7 +148,7 @@ int vitk_patchify(const float* img, void* patches_bf16, int32_t B, int32_t C, in
 int vitk_prefix_rows(float* x, const float* prefix_tok, const float* pos, int32_t B, int32_t N,
                      int32_t D, int32_t prefix, void* stream);
 int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix0, float* dprefix1, int32_t B,
-                   int32_t N, int32_t D, int32_t prefix, void* stream);
+                   int32_t N, int32_t D, int32_t prefix, int32_t gw, int32_t gwp, void* stream);
 
 /* DropPath (timm drop_path as called by Block, vision_transformer.py:160-161, 172-178): all per-sample keep masks of one
  * forward pass in one launch.  rs fp32 [rows, B]: rs[r, b] = Bernoulli(1 - drop_probs[r]) / (1 - drop_probs[r]).

@@ -210,3 +210,49 @@ def test_gemm_rejects_bad_args(cuda_device):
     assert float(out.abs().max()) == 0.0
     with pytest.raises(L.VitkError):
         L.gemm(a, a, out, M=0, N=16, K=64, epilogue=L.EPI_F32)  # empty
+
+
+@pytest.mark.parametrize("B,C,img,ps,D", [(3, 3, 224, 16, 192), (2, 3, 384, 16, 1024), (64, 3, 224, 16, 768), (1, 3, 32, 16, 64),
+                                          (5, 1, 64, 16, 128), (7, 4, 112, 16, 256)])
+def test_patch_embed_image_operand(cuda_device, B, C, img, ps, D):
+    """im2col-free PatchEmbed (Conv2d k = s = patch, /root/reference/models/vision_transformer.py:552-560): the bf16 NCHW
+    image is the GEMM's A operand through a 4-D tensor map (rows (b, gy, gx'), the patch-grid width padded to a multiple of 8), and
+    its B operand in the weight gradient.  Against the explicit im2col path (vitk_patchify + the same GEMM), which runs
+    the same MMAs in the same order on the same bf16 values, and against conv2d in fp32."""
+    from vision_transformers_torch_xla_b200 import _lib as L
+    from vision_transformers_torch_xla_b200.ops import _patch_grid_pad
+    gh = gw = img // ps
+    gwp = _patch_grid_pad(gw)
+    P, K, prefix = gh * gw, C * ps * ps, 1
+    N = P + prefix
+    x = _mk((B, C, img, img), cuda_device, seed=1)
+    w = _mk((D, K), cuda_device, 0.03, seed=2).bfloat16()
+    bias = _mk((D,), cuda_device, seed=3)
+    pos = _mk((N, D), cuda_device, seed=4)
+    xb = x.bfloat16()
+    geom = (C, img, img, ps, gwp)
+    out = torch.full((B, N, D), 7.0, device=cuda_device)
+    L.gemm(xb, w, out, M=B * gh * gwp, N=D, K=K, epilogue=L.EPI_PATCH, bias=bias, pos=pos, tokens_per_img=P, prefix=prefix,
+           image=("a",) + geom)
+    patches = torch.empty((B * P, K), device=cuda_device, dtype=torch.bfloat16)
+    L.patchify(x, patches, ps)
+    ref = torch.full((B, N, D), 7.0, device=cuda_device)
+    L.gemm(patches, w, ref, M=B * P, N=D, K=K, epilogue=L.EPI_PATCH, bias=bias, pos=pos, tokens_per_img=P, prefix=prefix)
+    assert torch.equal(out[:, :prefix], ref[:, :prefix]) and float(out[:, 0].min()) == 7.0   # prefix rows untouched
+    assert rel_err(out[:, prefix:], ref[:, prefix:]) < 1e-6
+    conv = torch.nn.functional.conv2d(xb.float(), w.float().view(D, C, ps, ps), bias, stride=ps).flatten(2).transpose(1, 2) + pos[prefix:]
+    assert rel_err(out[:, prefix:], conv) < F32_TOL
+    # weight gradient: dW[D, K] += gp^T patches, gp in the padded row order (pad rows zero)
+    g = _mk((B, N, D), cuda_device, seed=5)
+    gp_pad = torch.full((B * gh * gwp, D), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    dpos = torch.zeros(N, D, device=cuda_device)
+    L.embed_bwd(g, gp_pad, dpos, None, None, B, N, D, prefix, gw, gwp)
+    v = gp_pad.view(B, gh, gwp, D)
+    assert torch.equal(v[:, :, :gw].reshape(B, P, D), g[:, prefix:].bfloat16()) and float(v[:, :, gw:].float().abs().sum()) == 0.0
+    dW = torch.zeros(D, K, device=cuda_device)
+    db = torch.zeros(D, device=cuda_device)
+    L.gemm(gp_pad, xb, dW, M=D, N=K, K=B * gh * gwp, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, colsum=db, image=("b",) + geom)
+    gp = g[:, prefix:].bfloat16().reshape(B * P, D)
+    want = gp.float().t() @ patches.float()
+    assert rel_err(dW, want) < F32_TOL
+    assert rel_err(db, gp.float().sum(0)) < F32_TOL

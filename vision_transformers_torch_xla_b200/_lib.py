@@ -60,6 +60,8 @@ class GemmArgs(Structure):
         ("rowscale", c_void_p), ("rows_per_group", c_int32), ("colscale", c_void_p),
         ("pos", c_void_p), ("tokens_per_img", c_int32), ("prefix", c_int32),
         ("splits", c_int32), ("block_n", c_int32), ("colsum_out", c_void_p),
+        ("a_image", c_int32), ("b_image", c_int32),
+        ("img_c", c_int32), ("img_h", c_int32), ("img_w", c_int32), ("img_patch", c_int32), ("img_gwp", c_int32),
     ]
 
 
@@ -111,7 +113,7 @@ def load() -> ctypes.CDLL:
     lib.vitk_patchify.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_prefix_rows.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]
     lib.vitk_embed_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
-                                   c_void_p]
+                                   c_int32, c_int32, c_void_p]
     lib.vitk_droppath_masks.argtypes = [c_void_p, POINTER(c_float), c_int32, c_int32, c_uint64, c_uint64, c_void_p]
     lib.vitk_scale_f32.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.vitk_clip_coef.argtypes = [c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]
@@ -251,8 +253,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          rowscale: Optional[torch.Tensor] = None, rows_per_group: int = 1,
          colscale: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
          tokens_per_img: int = 0, prefix: int = 0, splits: int = 0, block_n: int = 0,
-         colsum: Optional[torch.Tensor] = None) -> None:
-    """D[M,N] = opA(a) @ opB(b)^T with a fused epilogue; see ``enum vitk_epilogue`` in include/vitk.h."""
+         colsum: Optional[torch.Tensor] = None, image: Optional[tuple] = None) -> None:
+    """D[M,N] = opA(a) @ opB(b)^T with a fused epilogue; see ``enum vitk_epilogue`` in include/vitk.h.
+
+    ``image = (which, C, H, W, patch, gwp)`` makes operand ``which`` ('a' or 'b') a bf16 NCHW image batch read through TMA
+    as its patch matrix (im2col-free; ``struct vitk_gemm_args``: a_image / b_image)."""
     _req(a, torch.bfloat16, "gemm A")
     _req(b, torch.bfloat16, "gemm B")
     args = GemmArgs()
@@ -270,6 +275,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     args.pos, args.tokens_per_img, args.prefix = _ptr(pos), tokens_per_img, prefix
     args.splits, args.block_n = splits, block_n
     args.colsum_out = _ptr(colsum)
+    if image is not None:
+        which, ic, ih, iw, ips, gwp = image
+        args.a_image, args.b_image = int(which == "a"), int(which == "b")
+        args.img_c, args.img_h, args.img_w, args.img_patch, args.img_gwp = ic, ih, iw, ips, gwp
+        if which == "a":
+            args.lda = 8      # unused for an image operand (the tensor map comes from the geometry); keeps the checks happy
+        else:
+            args.ldb = 8
     if colsum is not None:
         _req(colsum, torch.float32, "gemm colsum")
     for t, nm in ((bias, "bias"), (resid, "resid"), (rowscale, "rowscale"), (colscale, "colscale"), (pos, "pos")):
@@ -364,15 +377,17 @@ def prefix_rows(x: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor, B: int, N
 
 
 def embed_bwd(g: torch.Tensor, gp: Optional[torch.Tensor], dpos: Optional[torch.Tensor],
-              dprefix0: Optional[torch.Tensor], dprefix1: Optional[torch.Tensor], B: int, N: int, D: int, prefix: int) -> None:
-    """dpos / dprefix0 / dprefix1 are ACCUMULATED into (pos_embed / cls_token / dist_token gradient rows)."""
+              dprefix0: Optional[torch.Tensor], dprefix1: Optional[torch.Tensor], B: int, N: int, D: int, prefix: int,
+              gw: int = 0, gwp: int = 0) -> None:
+    """dpos / dprefix0 / dprefix1 are ACCUMULATED into (pos_embed / cls_token / dist_token gradient rows).  ``gw > 0``: gp
+    is laid out in the padded row order of an image operand, [B * (P / gw) * gwp, D], pad rows zeroed."""
     _req(g, torch.float32, "embed_bwd g")
     for t in (dpos, dprefix0, dprefix1):
         if t is not None:
             _req(t, torch.float32, "embed_bwd gradient row")
     with _Timed("embed_bwd"):
         _check(load().vitk_embed_bwd(g.data_ptr(), _ptr(gp), _ptr(dpos), _ptr(dprefix0), _ptr(dprefix1), B, N, D, prefix,
-                                     _stream()), "vitk_embed_bwd")
+                                     gw, gwp, _stream()), "vitk_embed_bwd")
     _count()
 
 

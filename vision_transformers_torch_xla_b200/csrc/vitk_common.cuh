@@ -41,7 +41,7 @@ int vitk_make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
                       uint32_t b2);
 int vitk_make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                       uint64_t ld1_elems, uint64_t ld2_elems, uint64_t ld3_elems, uint32_t b0, uint32_t b1, uint32_t b2,
-                      uint32_t b3);
+                      uint32_t b3, int swizzle_bytes = 128);
 int vitk_make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_bytes,
                          uint32_t box_inner, uint32_t box_outer);
 int vitk_make_tmap_2d_sw64(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
@@ -357,6 +357,23 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D tile loads (the patch view of an NCHW image: vitk_gemm.cu), plain and crediting the pair leader's barrier
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorMap* m, uint32_t bar_addr, int32_t c0,
+                                                 int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n"
@@ -372,16 +389,25 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4     bits [46,48) version = 1
-//   bits [61,64) layout type (2 = SWIZZLE_128B)
+//   bits [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B, 0 = none)
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
+}
+// 32-byte-swizzle operand tiles (the patch view of an image, vitk_gemm.cu): 8-row atoms of [8 rows][32 B] (256 B).
+//   K-major : rows of 16 bf16 (one k-step); atoms of consecutive 8-row groups `sbo_bytes` apart
+//   MN-major: k-rows of 16 bf16 along MN; 16-wide MN chunks `lbo_bytes` apart, 8-k-row groups `sbo_bytes` apart
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw32(uint32_t saddr, uint32_t sbo_bytes) {
+  return umma_smem_desc(saddr, 16, sbo_bytes, 6);
+}
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_smem_desc(saddr, lbo_bytes, sbo_bytes, 6);
 }
 // K-major operand tile: [rows][64 bf16] rows of 128 B, 8-row swizzle atoms of 1024 B.
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {

@@ -58,9 +58,10 @@ __global__ void prefix_rows_kernel(float* __restrict__ x, const float* __restric
 }
 
 // grid: (ceil(N*D/4 / 256), bchunks).  Thread owns one float4 column group of one token.
+// gw > 0: gp is written in the padded row order of an image operand, row (b, gy, gx') = (b * gh + gy) * gwp + gx'.
 __global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ gp,
                                  float* __restrict__ dpos, float* __restrict__ dprefix0, float* __restrict__ dprefix1,
-                                 int B, int N, int D, int prefix) {
+                                 int B, int N, int D, int prefix, int gw, int gwp) {
   const int dv = D / 4;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * dv) return;
@@ -70,6 +71,12 @@ __global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __r
   const int b0 = blockIdx.y * bper;
   const int b1 = min(B, b0 + bper);
   const int P = N - prefix;
+  long long prow = n - prefix, rows_per_img = P;   // patch row inside the image, rows of gp per image
+  if (gw > 0 && n >= prefix) {
+    const int t = n - prefix, gy = t / gw;
+    prow = (long long)gy * gwp + (t - gy * gw);
+    rows_per_img = (long long)(P / gw) * gwp;
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int b = b0; b < b1; ++b) {
@@ -79,7 +86,7 @@ __global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __r
       uint2 o;
       o.x = pack_bf16x2(v.x, v.y);
       o.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(gp + ((long long)b * P + (n - prefix)) * D + c * 4) = o;
+      *reinterpret_cast<uint2*>(gp + ((long long)b * rows_per_img + prow) * D + c * 4) = o;
     }
   }
   if (b1 > b0) {
@@ -93,6 +100,19 @@ __global__ void embed_bwd_kernel(const float* __restrict__ g, __nv_bfloat16* __r
       atomicAdd(o + 0, acc.x); atomicAdd(o + 1, acc.y); atomicAdd(o + 2, acc.z); atomicAdd(o + 3, acc.w);
     }
   }
+}
+
+// zero rows gx' in [gw, gwp) of every (b, gy) group of the padded gp: they multiply zero-filled image rows in the weight
+// gradient, and 0 * garbage must not be NaN.  One thread per 8 bytes.
+__global__ void embed_bwd_pad_kernel(__nv_bfloat16* __restrict__ gp, long long groups, int D, int gw, int gwp) {
+  const int dv = D / 4, pad = gwp - gw;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= groups * pad * dv) return;
+  const int c = (int)(idx % dv);
+  const long long r = idx / dv;
+  const long long grp = r / pad;
+  const int k = (int)(r - grp * pad);
+  *reinterpret_cast<uint2*>(gp + (grp * gwp + gw + k) * D + c * 4) = make_uint2(0u, 0u);
 }
 
 // pooled[b, d] = mean_{t >= prefix} x[b, t, d]   (mode 0)  or  x[b, 0, d]  (mode 1)
@@ -627,15 +647,22 @@ extern "C" int vitk_prefix_rows(float* x, const float* prefix_tok, const float* 
 }
 
 extern "C" int vitk_embed_bwd(const float* g, void* gp_bf16, float* dpos, float* dprefix0, float* dprefix1, int32_t B,
-                              int32_t N, int32_t D, int32_t prefix, void* stream) {
+                              int32_t N, int32_t D, int32_t prefix, int32_t gw, int32_t gwp, void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && D > 0 && D % 4 == 0 && prefix >= 0 && prefix <= 2 && prefix <= N, VITK_ERR_SHAPE,
                "embed_bwd: bad shape (prefix must be 0, 1 or 2)");
+  VITK_REQUIRE(gw == 0 || (gw > 0 && gwp >= gw && (N - prefix) % gw == 0), VITK_ERR_SHAPE,
+               "embed_bwd: padded layout needs gwp >= gw > 0 and a whole number of patch-grid rows (gw=%d gwp=%d)", gw, gwp);
   const long long total = (long long)N * (D / 4);
   const int bchunks = B >= 32 ? 8 : 1;
   dim3 grid(blocks_for(total, 256), bchunks);
   embed_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, (__nv_bfloat16*)gp_bf16, dpos, dprefix0, dprefix1, B, N, D,
-                                                           prefix);
-  return vitk_check_launch("embed_bwd");
+                                                           prefix, gw, gwp);
+  int rc = vitk_check_launch("embed_bwd");
+  if (rc || gp_bf16 == nullptr || gw == 0 || gwp == gw) return rc;
+  const long long groups = (long long)B * ((N - prefix) / gw);
+  embed_bwd_pad_kernel<<<blocks_for(groups * (gwp - gw) * (D / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      (__nv_bfloat16*)gp_bf16, groups, D, gw, gwp);
+  return vitk_check_launch("embed_bwd_pad");
 }
 
 extern "C" int vitk_pool_fwd(const float* x, float* pooled, int32_t B, int32_t N, int32_t D, int32_t prefix,

@@ -53,7 +53,28 @@ struct GemmParams {
   int prefix;
   int ragged;  // EPI_F32 only: N % 8 != 0 or unaligned rows -> scalar epilogue stores
   float* colsum_out;  // EPI_ATOMIC only: += column sums of A (bias gradient), or null
+  // im2col-free patch view of a bf16 NCHW image (see include/vitk.h): which operand, and its geometry
+  int a_image, b_image;
+  int img_c, img_gh, img_gw, img_gwp, img_ps;
 };
+
+// One [8 patch rows][64 columns] piece of the patch matrix of an NCHW image (patch 16) = one TMA box (px, gx, y, bc) =
+// (16, 8, 4, 1): four image rows of eight neighbouring patches of one channel.  With the 32-byte swizzle (a swizzle
+// narrower than the box's inner dimension would pad every 32-byte row to the swizzle span: tools/tma_probe.cu) it lands
+// as [py 4][gx' 8][32 B] = four 256-byte atoms, which tcgen05 reads either as a K-major SW32 tile (8 rows x one 16-wide
+// k-step per atom: the forward's A operand) or as an MN-major SW32 tile (8 k-rows x 16 columns per atom: the weight
+// gradient's B operand).  Columns gx' >= gw of a patch-grid row and groups past the last image are zero-filled by TMA.
+//   row_group8 = rows / 8 of the padded row order (b, gy, gx'), col0 = first of the 64 columns (c, py, px)
+template <bool CTA2>
+__device__ __forceinline__ void tma_load_patch_box(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t bar_addr,
+                                                   const GemmParams& p, int row_group8, int col0) {
+  const int per_row = p.img_gwp >> 3;                    // 8-patch groups per patch-grid row
+  const int bgy = row_group8 / per_row, part = row_group8 - bgy * per_row;
+  const int b = bgy / p.img_gh, gy = bgy - b * p.img_gh;
+  const int c = col0 >> 8, py0 = (col0 & 255) >> 4;      // patch 16: 256 columns per channel, 16 per image row
+  if constexpr (CTA2) tma_load_4d_2cta(dst, tm, bar_addr, 0, part * 8, gy * 16 + py0, b * p.img_c + c);
+  else tma_load_4d(dst, tm, bar, 0, part * 8, gy * 16 + py0, b * p.img_c + c);
+}
 
 // Epilogue staging: every epilogue warp owns a private [32 rows][32 columns] panel in smem (4 KB for fp32
 // columns, 2 KB for bf16) through which accumulator rows (thread = row) are transposed into row-contiguous
@@ -178,8 +199,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t (&a
       if constexpr (EPI == EPI_RESID) addp = p.resid + (long long)row * p.ld_resid + c;
       if constexpr (EPI == EPI_PATCH) {
         // row = b * P + patch  ->  output token row b * (P + prefix) + prefix + patch
-        const int b = row / p.tokens_per_img;
-        const int t = row - b * p.tokens_per_img;
+        int b = row / p.tokens_per_img;
+        int t = row - b * p.tokens_per_img;
+        if (p.a_image) {   // padded rows (b, gy, gx'): gx' >= gw are zero padding, not tokens
+          const int grp = row / p.img_gwp, gx = row - grp * p.img_gwp;
+          if (gx >= p.img_gw) return;
+          b = grp / p.img_gh;
+          t = (grp - b * p.img_gh) * p.img_gw + gx;
+        }
         orow = (long long)b * (p.tokens_per_img + p.prefix) + p.prefix + t;
         addp = p.pos + (long long)(p.prefix + t) * p.N + c;
       }
@@ -416,7 +443,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   // consumer of every smem stage.  Once the MMAs of a stage have retired (mma_done) they add up the columns of the
   // A tile (= dY) straight out of shared memory and only then hand the slot back to the TMA producer.
   constexpr bool CS = (EPI == EPI_ATOMIC) && A_MN;
-  static_assert(!CTA2 || (BLOCK_N % 128 == 0), "CTA pairs need BLOCK_N in {128, 256}");
+  // CTA pairs: each CTA stages half of the B tile.  MN-major B is loaded in 64-column chunks (BLOCK_N / 2 must be a
+  // multiple of 64); K-major B is one box of BLOCK_N / 2 rows, so 192 works there too (96 rows per CTA)
+  static_assert(!CTA2 || (BLOCK_N % 128 == 0) || (BLOCK_N == 192 && !B_MN), "CTA pairs need BLOCK_N in {128, 256} (192: K-major B only)");
   constexpr int PARTS = EW / 4;             // column partitions of the tile among epilogue warps
   constexpr int PART_N = BLOCK_N / PARTS;   // columns per epilogue warp
   constexpr int W = (PART_N % 32 == 0) ? 32 : 16;
@@ -506,7 +535,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             else mbar_arrive_remote(&full_bar[stage], 0);
             const uint32_t bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
             if constexpr (!A_MN) {
-              tma_load_2d_2cta(sA, &tmA, bar, kb * BLOCK_K, a_row);
+              if (p.a_image) {
+                for (int j = 0; j < BLOCK_M / 8; ++j)
+                  tma_load_patch_box<true>(sA + j * 1024, &tmA, nullptr, bar, p, a_row / 8 + j, kb * BLOCK_K);
+              } else {
+                tma_load_2d_2cta(sA, &tmA, bar, kb * BLOCK_K, a_row);
+              }
             } else {
 #pragma unroll
               for (int c = 0; c < BLOCK_M / 64; ++c)
@@ -516,13 +550,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d_2cta(sB, &tmB, bar, kb * BLOCK_K, b_row);
             } else {
 #pragma unroll
-              for (int c = 0; c < Cfg::B_ROWS / 64; ++c)
-                tma_load_2d_2cta(sB + c * (BLOCK_K * 128), &tmB, bar, b_row + c * 64, kb * BLOCK_K);
+              for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
+                if (p.b_image) {   // [8 k-row groups][B_ROWS / 64 column chunks][1 KB box]
+                  for (int j = 0; j < BLOCK_K / 8; ++j)
+                    tma_load_patch_box<true>(sB + j * (Cfg::B_ROWS / 64) * 1024 + c * 1024, &tmB, nullptr, bar, p,
+                                             kb * (BLOCK_K / 8) + j, b_row + c * 64);
+                } else {
+                  tma_load_2d_2cta(sB + c * (BLOCK_K * 128), &tmB, bar, b_row + c * 64, kb * BLOCK_K);
+                }
+              }
             }
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if constexpr (!A_MN) {
-              tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, a_row);
+              if (p.a_image) {
+                for (int j = 0; j < BLOCK_M / 8; ++j)
+                  tma_load_patch_box<false>(sA + j * 1024, &tmA, &full_bar[stage], 0u, p, a_row / 8 + j, kb * BLOCK_K);
+              } else {
+                tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, a_row);
+              }
             } else {
 #pragma unroll
               for (int c = 0; c < BLOCK_M / 64; ++c)
@@ -532,8 +578,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_2d(sB, &tmB, &full_bar[stage], kb * BLOCK_K, b_row);
             } else {
 #pragma unroll
-              for (int c = 0; c < BLOCK_N / 64; ++c)
-                tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], b_row + c * 64, kb * BLOCK_K);
+              for (int c = 0; c < BLOCK_N / 64; ++c) {
+                if (p.b_image) {
+                  for (int j = 0; j < BLOCK_K / 8; ++j)
+                    tma_load_patch_box<false>(sB + j * (BLOCK_N / 64) * 1024 + c * 1024, &tmB, &full_bar[stage], 0u, p,
+                                              kb * (BLOCK_K / 8) + j, b_row + c * 64);
+                } else {
+                  tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], b_row + c * 64, kb * BLOCK_K);
+                }
+              }
             }
           }
           }
@@ -553,10 +606,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // Descriptors are built once; per stage / per k-step only the 14-bit start-address field moves
       // (units of 16 B, never carries out of the field: smem < 256 KB).
       const uint32_t s0 = smem_u32(smem);
-      const uint64_t adesc0 = A_MN ? umma_desc_mnmajor(s0, BLOCK_K * 128) : umma_desc_kmajor(s0);
-      const uint64_t bdesc0 = B_MN ? umma_desc_mnmajor(s0 + Cfg::A_BYTES, BLOCK_K * 128) : umma_desc_kmajor(s0 + Cfg::A_BYTES);
+      // an image operand (32-byte-swizzle boxes, see tma_load_patch_box): A K-major = [16 row groups][4 k-steps][256 B],
+      // B MN-major = [8 k-row groups][column chunks of 64][4 x 256 B]
+      constexpr uint32_t B_SBO_IMG = (Cfg::B_ROWS / 64) * 1024;
+      const uint64_t adesc0 = A_MN ? umma_desc_mnmajor(s0, BLOCK_K * 128)
+                                   : (p.a_image ? umma_desc_kmajor_sw32(s0, 1024) : umma_desc_kmajor(s0));
+      const uint64_t bdesc0 = B_MN ? (p.b_image ? umma_desc_mnmajor_sw32(s0 + Cfg::A_BYTES, 256, B_SBO_IMG)
+                                                : umma_desc_mnmajor(s0 + Cfg::A_BYTES, BLOCK_K * 128))
+                                   : umma_desc_kmajor(s0 + Cfg::A_BYTES);
       // K-major: 16 elements = 32 B inside the 128 B swizzle row.  MN-major: 16 k-rows = 2 swizzle atoms = 2048 B.
-      constexpr uint32_t A_KSTEP = (A_MN ? 2048 : 32) >> 4, B_KSTEP = (B_MN ? 2048 : 32) >> 4;
+      // Image operands: one k-step = the next 256-byte atom (A), or two 8-k-row groups further (B).
+      const uint32_t A_KSTEP = (A_MN ? 2048 : (p.a_image ? 256 : 32)) >> 4;
+      const uint32_t B_KSTEP = (B_MN ? (p.b_image ? 2 * B_SBO_IMG : 2048) : 32) >> 4;
       for (int unit = unit0; unit < total_units; unit += ustride) {
         const int split = unit % p.splits;
         const int kb0 = (int)(((long long)split * p.num_k_blocks) / p.splits);
@@ -1006,6 +1067,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+// number of images behind an image operand: its rows are (b, gy, gx') groups of img_gwp
+inline long long image_batch(const vitk_gemm_args* a) {
+  const long long rows = a->a_image ? a->M : a->K;
+  const long long per_img = (long long)(a->img_h / a->img_patch) * a->img_gwp;
+  return per_img > 0 ? (rows + per_img - 1) / per_img : 0;
+}
+
 bool use_cta_pairs() {
   static const bool on = [] {
     const char* e = getenv("VITK_GEMM_2CTA");  // tuning knob: "0" forces the single-CTA kernel
@@ -1014,16 +1082,20 @@ bool use_cta_pairs() {
   return on;
 }
 
-int pick_splits(int tiles, int num_k_blocks, int slots) {
-  // choose the split-K factor that fills whole waves of `slots` CTAs (or CTA pairs); prefer fewer splits on ties
+int pick_splits(int tiles, int num_k_blocks, int slots, int block_n) {
+  // Split-K factor of a weight gradient.  Cost model fitted to measurements (profiles/r02_wgrad_splits.txt): a CTA pair
+  // runs its units one after the other; a unit costs its k-blocks plus the red.add epilogue of its fp32 tile, which is
+  // NOT hidden behind the next unit's main loop and is worth ~45 k-blocks for a 256 x 256 tile (17-20 us on B200):
+  //     time(s) ~ waves(s) * (ceil(k_blocks / s) + 45 * block_n / 256),   waves(s) = ceil(tiles * s / slots)
+  // (round 1 charged 0.4 % of a wave per split, which sent ViT-L's 64-tile fc weight gradients to 8 splits:
+  //  273 / 293 us against 225 / 220 us with one).
+  const int epi = 45 * block_n / 256;
   int best = 1;
-  double best_eff = 0.0;
+  long long best_cost = -1;
   for (int s = 1; s <= 32 && s <= num_k_blocks; ++s) {
-    const int units = tiles * s;
-    const int waves = (units + slots - 1) / slots;
-    double eff = (double)units / ((double)waves * slots);
-    eff -= 0.004 * s;  // each split adds one more pass of red.add traffic over the tile
-    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    const long long waves = ((long long)tiles * s + slots - 1) / slots;
+    const long long cost = waves * ((num_k_blocks + s - 1) / s + epi);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
   return best;
 }
@@ -1056,11 +1128,20 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   constexpr int TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   CUtensorMap tmA, tmB;
   int rc;
-  if (!A_MN) rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, BLOCK_K, BLOCK_M);
-  else       rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->M, a->K, a->lda, 64, BLOCK_K);
+  // the patch view of an NCHW image (patch 16): dims (px, gx, y, b*c) with strides (1, 16, W, H*W) elements, boxes of
+  // (16 px, 8 patches, 4 image rows, 1) in the 32-byte swizzle
+  auto image_map = [&](CUtensorMap* tm, const void* img) {
+    return vitk_make_tmap_4d(tm, img, 2, 16, (uint64_t)(a->img_w / 16), (uint64_t)a->img_h,
+                             (uint64_t)((long long)a->img_c * image_batch(a)), 16, (uint64_t)a->img_w,
+                             (uint64_t)a->img_h * a->img_w, 16u, 8u, 4u, 1u, 32);
+  };
+  if (a->a_image) rc = image_map(&tmA, a->A);
+  else if (!A_MN) rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, BLOCK_K, BLOCK_M);
+  else            rc = vitk_make_tmap_2d(&tmA, a->A, 2, a->M, a->K, a->lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!B_MN) rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->K, a->N, a->ldb, BLOCK_K, Cfg::B_ROWS);
-  else       rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, 64, BLOCK_K);
+  if (a->b_image) rc = image_map(&tmB, a->B);
+  else if (!B_MN) rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->K, a->N, a->ldb, BLOCK_K, Cfg::B_ROWS);
+  else            rc = vitk_make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, 64, BLOCK_K);
   if (rc) return rc;
 
   CUtensorMap tmOut, tmAux;
@@ -1108,7 +1189,7 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   p.num_k_blocks = (a->K + BLOCK_K - 1) / BLOCK_K;
   p.splits = 1;
   if (EPI == EPI_ATOMIC) {
-    p.splits = a->splits > 0 ? a->splits : pick_splits(p.num_m_tiles * p.num_n_tiles, p.num_k_blocks, slots);
+    p.splits = a->splits > 0 ? a->splits : pick_splits(p.num_m_tiles * p.num_n_tiles, p.num_k_blocks, slots, BLOCK_N);
     if (p.splits > p.num_k_blocks) p.splits = p.num_k_blocks;
   }
   p.out = a->out; p.ld_out = a->ld_out;
@@ -1121,6 +1202,11 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   p.prefix = a->prefix;
   p.ragged = (EPI == EPI_F32 && (a->N % 8 != 0 || a->ld_out % 4 != 0)) ? 1 : 0;
   p.colsum_out = (EPI == EPI_ATOMIC && A_MN) ? a->colsum_out : nullptr;
+  p.a_image = (a->a_image && !A_MN) ? 1 : 0;
+  p.b_image = (a->b_image && B_MN) ? 1 : 0;
+  p.img_c = a->img_c; p.img_ps = a->img_patch > 0 ? a->img_patch : 16; p.img_gwp = a->img_gwp > 0 ? a->img_gwp : 16;
+  p.img_gh = a->img_h / p.img_ps; p.img_gw = a->img_w / p.img_ps;
+  if (p.img_gh < 1) p.img_gh = 1;
 
   auto kern = gemm_kernel<BLOCK_N, A_MN, B_MN, EPI, EW, CTA2>;
   static bool attr_set = false;  // per-instantiation
@@ -1151,9 +1237,12 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
 template <int BLOCK_N, bool CTA2>
 int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
+  constexpr bool PAIR192 = CTA2 && BLOCK_N == 192;   // built for the forward (K-major B) epilogues only
   if (a->epilogue == EPI_ATOMIC) {
-    if (amn && bmn) return launch_gemm<BLOCK_N, true, true, EPI_ATOMIC, CTA2>(a, stream);
-    if (!amn && !bmn) return launch_gemm<BLOCK_N, false, false, EPI_ATOMIC, CTA2>(a, stream);
+    if constexpr (!PAIR192) {
+      if (amn && bmn) return launch_gemm<BLOCK_N, true, true, EPI_ATOMIC, CTA2>(a, stream);
+      if (!amn && !bmn) return launch_gemm<BLOCK_N, false, false, EPI_ATOMIC, CTA2>(a, stream);
+    }
     return vitk_set_error(VITK_ERR_UNSUPPORTED, "gemm: EPI_ATOMIC needs both operands in the same major");
   }
   if (!amn && !bmn) {
@@ -1179,6 +1268,7 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
       case EPI_PATCH: return launch_gemm<BLOCK_N, false, false, EPI_PATCH, CTA2>(a, stream);
     }
   } else if (!amn && bmn) {
+    if constexpr (!PAIR192) {
     switch (a->epilogue) {
       case EPI_BF16:
         if constexpr (BLOCK_N == 256) {
@@ -1194,16 +1284,26 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
         break;
       case EPI_F32:   return launch_gemm<BLOCK_N, false, true, EPI_F32, CTA2>(a, stream);
     }
+    }
   }
   return vitk_set_error(VITK_ERR_UNSUPPORTED, "gemm: unsupported layout/epilogue combination (a_mn=%d b_mn=%d epi=%d)",
                         (int)amn, (int)bmn, a->epilogue);
 }
 
+bool pair192_enabled() {
+  static const bool on = [] { const char* e = getenv("VITK_GEMM_192_2CTA"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <int BLOCK_N>
 int dispatch(const vitk_gemm_args* a, cudaStream_t stream) {
+  // CTA pairs pay off once there are enough 256-row tiles to go round; tiny problems keep 128-row tiles
   if constexpr (BLOCK_N != 192) {
-    // CTA pairs pay off once there are enough 256-row tiles to go round; tiny problems keep 128-row tiles
     if (use_cta_pairs() && a->M >= 256) return dispatch2<BLOCK_N, true>(a, stream);
+  } else {
+    // 256 x 192 pair tiles exist for the forward layouts (both operands K-major, not split-K)
+    if (use_cta_pairs() && pair192_enabled() && a->M >= 256 && !a->a_mn_major && !a->b_mn_major && a->epilogue != EPI_ATOMIC)
+      return dispatch2<BLOCK_N, true>(a, stream);
   }
   return dispatch2<BLOCK_N, false>(a, stream);
 }
@@ -1231,9 +1331,29 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream_) {
   if (a->epilogue == EPI_PATCH)
     VITK_REQUIRE(a->pos != nullptr && a->tokens_per_img > 0, VITK_ERR_SHAPE, "gemm: pos/tokens_per_img required");
 
+  if (a->a_image || a->b_image) {
+    const int ps = a->img_patch, gwp = a->img_gwp;
+    VITK_REQUIRE(ps == 16, VITK_ERR_UNSUPPORTED, "gemm: image operand: patch %d (built for 16)", ps);
+    VITK_REQUIRE(a->img_c > 0 && a->img_h > 0 && a->img_w > 0 && a->img_h % ps == 0 && a->img_w % ps == 0 && a->img_w % 8 == 0,
+                 VITK_ERR_SHAPE, "gemm: image operand: bad geometry C=%d H=%d W=%d patch=%d", a->img_c, a->img_h, a->img_w, ps);
+    VITK_REQUIRE(gwp > 0 && gwp % 8 == 0 && gwp >= a->img_w / ps && gwp < a->img_w / ps + 8, VITK_ERR_SHAPE,
+                 "gemm: image operand: img_gwp=%d must be the patch-grid width %d rounded up to a multiple of 8", gwp, a->img_w / ps);
+    VITK_REQUIRE(!(a->a_image && a->b_image), VITK_ERR_UNSUPPORTED, "gemm: only one operand can be an image");
+    if (a->a_image)
+      VITK_REQUIRE(!a->a_mn_major && a->K == a->img_c * ps * ps && a->M % gwp == 0, VITK_ERR_SHAPE,
+                   "gemm: a_image needs K-major A, K = C * patch^2 and M a multiple of img_gwp");
+    if (a->b_image)
+      VITK_REQUIRE(a->b_mn_major && a->N == a->img_c * ps * ps && a->K % gwp == 0, VITK_ERR_SHAPE,
+                   "gemm: b_image needs MN-major B, N = C * patch^2 and K a multiple of img_gwp");
+  }
+
   int bn = a->block_n;
   if (bn == 0) {
-    if (a->N % 256 == 0) bn = 256;
+    // 256-wide pair tiles are the most efficient ones, even with a partly empty last column of tiles, as long as that
+    // costs <= 15 % extra MMA work (ViT-S qkv, N = 1152 = 4.5 x 256: 48.6 us against 57.0 us with 6 x 192 pair tiles,
+    // profiles/r02_gemm_tile_width.txt); beyond that an exact 192 / 128 split wins (N = 384: 41-42 us against 48.3 us)
+    const int n256 = (a->N + 255) / 256 * 256;
+    if (a->N % 256 == 0 || (a->N > 512 && n256 * 100 <= a->N * 115)) bn = 256;
     else if (a->N % 192 == 0) bn = 192;
     else if (a->N % 128 == 0) bn = 128;
     else bn = (a->N > 192) ? 256 : (a->N > 128 ? 192 : 128);

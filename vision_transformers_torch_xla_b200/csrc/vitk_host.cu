@@ -118,11 +118,13 @@ int vitk_make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64
 extern "C" const char* vitk_build_id(void) { return VITK_BUILD_ID; }
 int vitk_make_tmap_4d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3,
                       uint64_t ld1_elems, uint64_t ld2_elems, uint64_t ld3_elems, uint32_t b0, uint32_t b1, uint32_t b2,
-                      uint32_t b3) {
+                      uint32_t b3, int swizzle_bytes) {
   cuuint64_t dims[4] = {d0, d1, d2, d3};
   cuuint64_t strides[3] = {ld1_elems * (uint64_t)elem_bytes, ld2_elems * (uint64_t)elem_bytes, ld3_elems * (uint64_t)elem_bytes};
   cuuint32_t box[4] = {b0, b1, b2, b3};
-  return encode(out, base, elem_bytes, 4, dims, strides, box);
+  return encode(out, base, elem_bytes, 4, dims, strides, box,
+                swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                        : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 extern "C" int vitk_abi_version(void) { return VITK_ABI_VERSION; }

@@ -397,8 +397,10 @@ class VisionTransformer(nn.Module):
     def _features(self, x: torch.Tensor, st) -> torch.Tensor:
         """patch embed + tokens + pos_embed + blocks; returns the un-normalised fp32 residual stream."""
         self.patch_embed._check(x)
-        if x.dtype != torch.float32 or not x.is_cuda:
-            raise ops.L.VitkError(f"VisionTransformer expects a float32 CUDA image batch, got {x.dtype} on {x.device}")
+        if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda:
+            raise ops.L.VitkError(f"VisionTransformer expects a float32 (or bfloat16) CUDA image batch, got {x.dtype} on {x.device}")
+        if x.dtype == torch.bfloat16 and ops.PATCH_EMBED != "tma":
+            x = x.float()
         x = x if x.is_contiguous() else x.contiguous()
         x = ops.EmbedFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
         st.__dict__["_in_root"] = self

@@ -67,6 +67,19 @@ def _bf16_grad(store: ParamStore, g: torch.Tensor, rowscale: Optional[torch.Tens
 # ================================================================================================
 # Patch embedding + prefix tokens + positional embedding
 # ================================================================================================
+#: "tma" (default): im2col-free — the image (cast to bf16 NCHW in one coalesced pass, or handed in as bf16 already) is the
+#: GEMM's A operand through a 4-D tensor map that reads it as its patch matrix; the [B*P, C*ps*ps] matrix is never
+#: materialised, neither for the forward nor for the weight gradient.  "patchify": the explicit im2col + cast kernel.
+PATCH_EMBED = os.environ.get("VITK_PATCH_EMBED", "tma")
+if PATCH_EMBED not in ("tma", "patchify"):
+    raise ValueError(f"VITK_PATCH_EMBED={PATCH_EMBED!r}: expected 'tma' or 'patchify'")
+
+
+def _patch_grid_pad(gw: int) -> int:
+    """Patch-grid width rounded up to a multiple of 8: the TMA boxes of the image operand cover 8 neighbouring patches."""
+    return (gw + 7) // 8 * 8
+
+
 class EmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, anchor, model, store: ParamStore, save: bool):
@@ -79,13 +92,27 @@ class EmbedFn(torch.autograd.Function):
         N = P + prefix
         K = C * ps * ps
         dev = img.device
-        patches = _empty((B * P, K), torch.bfloat16, dev)
-        L.patchify(img, patches, ps)
+        gh, gw = pe.grid_size
+        gwp = _patch_grid_pad(gw)
         x = _empty((B, N, D), torch.float32, dev)
         w = store.shadow_of(pe.proj.weight).view(D, K)
         pos = model.pos_embed.data.view(N, D)
-        L.gemm(patches, w, x, M=B * P, N=D, K=K, epilogue=L.EPI_PATCH,
-               bias=None if pe.proj.bias is None else pe.proj.bias.data, pos=pos, tokens_per_img=P, prefix=prefix)
+        bias = None if pe.proj.bias is None else pe.proj.bias.data
+        tma = PATCH_EMBED == "tma" and ps == 16 and pe.patch_size[1] == 16
+        if tma:
+            if img.dtype == torch.bfloat16:
+                src = img                         # a loader that already produces bf16 saves the cast (and half the H2D bytes)
+            else:
+                src = _empty(img.shape, torch.bfloat16, dev)
+                L.cast_bf16(img, src)
+            geom = (C, H, W, ps, gwp)
+            L.gemm(src, w, x, M=B * gh * gwp, N=D, K=K, epilogue=L.EPI_PATCH, bias=bias, pos=pos, tokens_per_img=P, prefix=prefix,
+                   image=("a",) + geom)
+        else:
+            src = _empty((B * P, K), torch.bfloat16, dev)
+            L.patchify(img, src, ps)
+            geom = None
+            L.gemm(src, w, x, M=B * P, N=D, K=K, epilogue=L.EPI_PATCH, bias=bias, pos=pos, tokens_per_img=P, prefix=prefix)
         xf = x.view(-1)
         posf = pos.view(-1)
         toks = [model.cls_token] + ([model.dist_token] if prefix == 2 else [])
@@ -93,7 +120,7 @@ class EmbedFn(torch.autograd.Function):
             L.prefix_rows(xf[j * D:], tok.data.view(1, D), posf[j * D:], B, N, D, 1)
         if save:
             ctx.model, ctx.store = model, store
-            ctx.patches = patches
+            ctx.src, ctx.geom = src, geom
             ctx.dims = (B, N, D, P, prefix, K)
         return x
 
@@ -105,16 +132,25 @@ class EmbedFn(torch.autograd.Function):
         g = _require_f32_cuda(g, "EmbedFn.backward grad")
         store.chain.pop(g.data_ptr(), None)
         dev = g.device
-        gp = _empty((B * P, D), torch.bfloat16, dev)
         toks = [model.cls_token] + ([model.dist_token] if prefix == 2 else [])
         # the token gradients are summed over the batch straight into their rows of the flat gradient buffer
         dpre = [store.grad_of(tok).view(D) if tok.requires_grad else None for tok in toks] + [None]
         dpos = store.grad_of(model.pos_embed).view(N, D) if model.pos_embed.requires_grad else None
-        L.embed_bwd(g, gp, dpos, dpre[0], dpre[1], B, N, D, prefix)
-        L.gemm(gp, ctx.patches, store.grad_of(pe.proj.weight).view(D, K), M=D, N=K, K=B * P,
-               epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
-               colsum=None if pe.proj.bias is None else store.grad_of(pe.proj.bias))
-        ctx.patches = None
+        colsum = None if pe.proj.bias is None else store.grad_of(pe.proj.bias)
+        dW = store.grad_of(pe.proj.weight).view(D, K)
+        if ctx.geom is not None:
+            C, H, W, ps, gwp = ctx.geom
+            gh, gw = H // ps, W // ps
+            rows = B * gh * gwp                    # gp in the image operand's padded row order, pad rows zeroed
+            gp = _empty((rows, D), torch.bfloat16, dev)
+            L.embed_bwd(g, gp, dpos, dpre[0], dpre[1], B, N, D, prefix, gw, gwp)
+            L.gemm(gp, ctx.src, dW, M=D, N=K, K=rows, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, colsum=colsum,
+                   image=("b",) + ctx.geom)
+        else:
+            gp = _empty((B * P, D), torch.bfloat16, dev)
+            L.embed_bwd(g, gp, dpos, dpre[0], dpre[1], B, N, D, prefix)
+            L.gemm(gp, ctx.src, dW, M=D, N=K, K=B * P, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True, colsum=colsum)
+        ctx.src = None
         store.fire_grad_ready("embed")
         return None, None, None, None, None
 
