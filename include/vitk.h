@@ -216,10 +216,13 @@ int vitk_adamw_flat(float* p, float* g, const void* g_bf16, const float* grad_sc
 void vitk_debug_set_trace(long long* device_buf);
 
 /* Gradient clipping (engine.py:175-177; torch.nn.utils.clip_grad_norm_) without a host sync or an extra pass:
- * vitk_sumsq / vitk_sumsq_bf16: out[0] += sum_i x[i]^2;  vitk_clip_coef: norm[0] = sqrt(sumsq[0]) * grad_scale (optional output),
+ * vitk_sumsq / vitk_sumsq_bf16: out[0] += sum_i x[i]^2, DETERMINISTIC (fixed grid and summation order, no floating-point
+ * atomics: data-parallel ranks must get bit-identical coefficients from bit-identical gradients); `scratch` is a
+ * caller-owned fp32 buffer of vitk_sumsq_scratch_floats() elements.  vitk_clip_coef: norm[0] = sqrt(sumsq[0]) * grad_scale (optional output),
  * coef[0] = min(1, max_norm / (norm + 1e-6)), which vitk_adamw_flat multiplies in through grad_scale_dev. */
-int vitk_sumsq(const float* x, int64_t n, float* out, void* stream);
-int vitk_sumsq_bf16(const void* x_bf16, int64_t n, float* out, void* stream);
+int32_t vitk_sumsq_scratch_floats(void);
+int vitk_sumsq(const float* x, int64_t n, float* out, float* scratch, void* stream);
+int vitk_sumsq_bf16(const void* x_bf16, int64_t n, float* out, float* scratch, void* stream);
 int vitk_clip_coef(const float* sumsq, float grad_scale, float max_norm, float* coef, float* norm, void* stream);
 
 /* Mixup / CutMix, batch mode, in place on fp32 NCHW images (image b mixes with image B-1-b); replaces

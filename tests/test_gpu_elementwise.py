@@ -240,6 +240,14 @@ def test_sumsq(cuda_device):
     out.zero_()
     L.sumsq(xb, out)
     assert abs(out.item() - xb.double().pow(2).sum().item()) < 1e-3 * xb.numel() ** 0.5 * 10
+    # deterministic: no floating-point atomics (data-parallel ranks derive their clip coefficient from this)
+    big = torch.randn(86_567_656, device=cuda_device)
+    results = []
+    for _ in range(5):
+        o = torch.zeros(1, device=cuda_device)
+        L.sumsq(big, o)
+        results.append(o.item())
+    assert len(set(results)) == 1, results
 
 
 def test_adamw_bf16_gradient_source_and_device_scale(cuda_device):

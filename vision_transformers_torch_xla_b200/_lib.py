@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = (
     "vitk_embed_bwd", "vitk_pool_fwd", "vitk_pool_bwd", "vitk_colsum_bf16", "vitk_ce_fwd_bwd",
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
     "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target", "vitk_colscale_bf16", "vitk_layerscale_grad",
-    "vitk_build_id", "vitk_droppath_masks", "vitk_scale_f32", "vitk_clip_coef", "vitk_sumsq_bf16",
+    "vitk_build_id", "vitk_droppath_masks", "vitk_scale_f32", "vitk_clip_coef", "vitk_sumsq_bf16", "vitk_sumsq_scratch_floats",
 )
 
 ABI_VERSION = 2
@@ -129,8 +129,9 @@ def load() -> ctypes.CDLL:
                                     c_void_p,
                                     c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_float, c_float, c_float,
                                     c_int64, c_float, c_float, c_int32, c_void_p]
-    lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
-    lib.vitk_sumsq_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.vitk_sumsq_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.vitk_sumsq_scratch_floats.restype = c_int32
     lib.vitk_mixup_batch.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_double, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_void_p]
     lib.vitk_colscale_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p]
@@ -141,7 +142,7 @@ def load() -> ctypes.CDLL:
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version", "vitk_attn_bwd_workspace_bytes",
-                        "vitk_debug_set_trace", "vitk_build_id"):
+                        "vitk_debug_set_trace", "vitk_build_id", "vitk_sumsq_scratch_floats"):
             fn.restype = c_int32
     _lib = lib
     return lib
@@ -516,14 +517,17 @@ def adamw_flat(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tenso
 
 
 def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:
-    """out[0] += sum(x^2); x fp32 or bf16."""
+    """out[0] += sum(x^2); x fp32 or bf16.  Deterministic (no floating-point atomics): ranks holding the same reduced
+    gradient get the same bits."""
     _req(out, torch.float32, "sumsq out")
     if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
         raise VitkError(f"sumsq x: expected a float32 / bfloat16 CUDA tensor, got {x.dtype} on {x.device}")
-    fn = load().vitk_sumsq if x.dtype == torch.float32 else load().vitk_sumsq_bf16
+    lib = load()
+    fn = lib.vitk_sumsq if x.dtype == torch.float32 else lib.vitk_sumsq_bf16
+    scratch = torch.empty(lib.vitk_sumsq_scratch_floats(), dtype=torch.float32, device=x.device)
     with _Timed("sumsq"):
-        _check(fn(x.data_ptr(), x.numel(), out.data_ptr(), _stream()), "vitk_sumsq")
-    _count()
+        _check(fn(x.data_ptr(), x.numel(), out.data_ptr(), scratch.data_ptr(), _stream()), "vitk_sumsq")
+    _count(2)
 
 
 # ------------------------------------------------------------------------------------------------

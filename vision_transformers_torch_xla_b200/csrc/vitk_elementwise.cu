@@ -435,37 +435,43 @@ adamw_kernel(float* __restrict__ p, float* __restrict__ g, const __nv_bfloat16* 
   }
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+// Sum of squares, DETERMINISTIC: every data-parallel rank must derive bit-identical clip coefficients from bit-identical
+// reduced gradients, so there are no floating-point atomics here.  Stage 1: a fixed grid, each block sums its grid-stride
+// share in a fixed order and writes one partial; stage 2: one block adds the partials in index order.
+constexpr int SUMSQ_BLOCKS = 1024;
+template <typename T>
+__global__ void __launch_bounds__(CE_THREADS) sumsq_partial_kernel(const T* __restrict__ x, long long n, float* __restrict__ partial) {
   __shared__ float sh[CE_THREADS / 32];
+  constexpr int V = 16 / sizeof(T);   // elements per 16-byte load
   float s = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x * 4;
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-    if (i + 3 < n) {
-      const float4 v = *reinterpret_cast<const float4*>(x + i);
-      s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-    } else {
-      for (long long j = i; j < n; ++j) s += x[j] * x[j];
-    }
-  }
-  s = block_reduce(s, false, sh);
-  if (threadIdx.x == 0) atomicAdd(out, s);
-}
-
-__global__ void sumsq_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long n, float* __restrict__ out) {
-  __shared__ float sh[CE_THREADS / 32];
-  float s = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x * 8;
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
-    if (i + 7 < n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * V;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+    if (i + V - 1 < n) {
       const uint4 u = *reinterpret_cast<const uint4*>(x + i);
-      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      s += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+      if constexpr (sizeof(T) == 4) {
+        const float a = __uint_as_float(u.x), b = __uint_as_float(u.y), c = __uint_as_float(u.z), d = __uint_as_float(u.w);
+        s += (a * a + b * b) + (c * c + d * d);
+      } else {
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+        s += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y) + (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+      }
     } else {
-      for (long long j = i; j < n; ++j) { const float v = __bfloat162float(x[j]); s += v * v; }
+      for (long long j = i; j < n; ++j) {
+        float v;
+        if constexpr (sizeof(T) == 4) v = x[j]; else v = __bfloat162float(x[j]);
+        s += v * v;
+      }
     }
   }
   s = block_reduce(s, false, sh);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(CE_THREADS) sumsq_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ out) {
+  __shared__ float sh[CE_THREADS / 32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += CE_THREADS) s += partial[i];
+  s = block_reduce(s, false, sh);
+  if (threadIdx.x == 0) out[0] += s;
 }
 
 inline unsigned blocks_for(long long n, int per) { return (unsigned)((n + per - 1) / per); }
@@ -792,27 +798,23 @@ extern "C" int vitk_droppath_masks(float* rs, const float* drop_probs, int32_t r
   return vitk_check_launch("droppath_masks");
 }
 
-extern "C" int vitk_sumsq(const float* x, int64_t n, float* out, void* stream) {
-  VITK_REQUIRE(n >= 0 && out, VITK_ERR_SHAPE, "sumsq: bad args");
+template <typename T>
+static int sumsq_launch(const T* x, int64_t n, float* out, float* scratch, void* stream) {
+  VITK_REQUIRE(n >= 0 && out && scratch, VITK_ERR_SHAPE, "sumsq: out and a scratch of vitk_sumsq_scratch_floats() fp32 required");
+  VITK_REQUIRE(((uintptr_t)x & 15) == 0, VITK_ERR_ALIGN, "sumsq: x must be 16-byte aligned");
   if (n == 0) return VITK_OK;
-  long long blocks = (n / 4 + 255) / 256;
-  const long long cap = (long long)vitk_num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  sumsq_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, n, out);
-  return vitk_check_launch("sumsq");
+  sumsq_partial_kernel<T><<<SUMSQ_BLOCKS, CE_THREADS, 0, (cudaStream_t)stream>>>(x, n, scratch);
+  int rc = vitk_check_launch("sumsq");
+  if (rc) return rc;
+  sumsq_final_kernel<<<1, CE_THREADS, 0, (cudaStream_t)stream>>>(scratch, SUMSQ_BLOCKS, out);
+  return vitk_check_launch("sumsq_final");
 }
-
-extern "C" int vitk_sumsq_bf16(const void* x_bf16, int64_t n, float* out, void* stream) {
-  VITK_REQUIRE(n >= 0 && out, VITK_ERR_SHAPE, "sumsq_bf16: bad args");
-  VITK_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, VITK_ERR_ALIGN, "sumsq_bf16: unaligned");
-  if (n == 0) return VITK_OK;
-  long long blocks = (n / 8 + 255) / 256;
-  const long long cap = (long long)vitk_num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  sumsq_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_bf16, n, out);
-  return vitk_check_launch("sumsq_bf16");
+extern "C" int32_t vitk_sumsq_scratch_floats(void) { return SUMSQ_BLOCKS; }
+extern "C" int vitk_sumsq(const float* x, int64_t n, float* out, float* scratch, void* stream) {
+  return sumsq_launch<float>(x, n, out, scratch, stream);
+}
+extern "C" int vitk_sumsq_bf16(const void* x_bf16, int64_t n, float* out, float* scratch, void* stream) {
+  return sumsq_launch<__nv_bfloat16>((const __nv_bfloat16*)x_bf16, n, out, scratch, stream);
 }
 
 extern "C" int vitk_mixup_batch(float* x, int32_t B, int32_t C, int32_t H, int32_t W, double lam, int32_t use_cutmix,

@@ -60,20 +60,33 @@ struct GemmParams {
 
 // One [8 patch rows][64 columns] piece of the patch matrix of an NCHW image (patch 16) = one TMA box (px, gx, y, bc) =
 // (16, 8, 4, 1): four image rows of eight neighbouring patches of one channel.  With the 32-byte swizzle (a swizzle
-// narrower than the box's inner dimension would pad every 32-byte row to the swizzle span: tools/tma_probe.cu) it lands
+// WIDER than the box's inner dimension would pad every 32-byte row to the swizzle span: tools/tma_probe.cu) it lands
 // as [py 4][gx' 8][32 B] = four 256-byte atoms, which tcgen05 reads either as a K-major SW32 tile (8 rows x one 16-wide
 // k-step per atom: the forward's A operand) or as an MN-major SW32 tile (8 k-rows x 16 columns per atom: the weight
 // gradient's B operand).  Columns gx' >= gw of a patch-grid row and groups past the last image are zero-filled by TMA.
-//   row_group8 = rows / 8 of the padded row order (b, gy, gx'), col0 = first of the 64 columns (c, py, px)
+// A run of `n` consecutive 8-row groups starting at group `first` (= row / 8 of the padded row order (b, gy, gx')), all
+// for the same 64 columns starting at col0 (c, py, px), box j going to dst + j * dst_stride.  Issued by ONE lane: the
+// (image, grid row, part) of the first group costs two divisions, the others follow by increments (a division per box
+// made the producer, not the tensor core, the limit: 25 us per 256 x 256 tile).
 template <bool CTA2>
-__device__ __forceinline__ void tma_load_patch_box(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t bar_addr,
-                                                   const GemmParams& p, int row_group8, int col0) {
+__device__ __forceinline__ void tma_load_patch_boxes(uint8_t* dst, uint32_t dst_stride, const CUtensorMap* tm, uint64_t* bar,
+                                                     uint32_t bar_addr, const GemmParams& p, int first, int n, int col0) {
   const int per_row = p.img_gwp >> 3;                    // 8-patch groups per patch-grid row
-  const int bgy = row_group8 / per_row, part = row_group8 - bgy * per_row;
-  const int b = bgy / p.img_gh, gy = bgy - b * p.img_gh;
+  const int bgy = first / per_row;
+  int part = first - bgy * per_row;
+  int b = bgy / p.img_gh;
+  int gy = bgy - b * p.img_gh;
   const int c = col0 >> 8, py0 = (col0 & 255) >> 4;      // patch 16: 256 columns per channel, 16 per image row
-  if constexpr (CTA2) tma_load_4d_2cta(dst, tm, bar_addr, 0, part * 8, gy * 16 + py0, b * p.img_c + c);
-  else tma_load_4d(dst, tm, bar, 0, part * 8, gy * 16 + py0, b * p.img_c + c);
+  for (int j = 0; j < n; ++j) {
+    // (a group past the last image has b >= B: the bc coordinate is out of range and the box is zero-filled)
+    if constexpr (CTA2) tma_load_4d_2cta(dst, tm, bar_addr, 0, part * 8, gy * 16 + py0, b * p.img_c + c);
+    else tma_load_4d(dst, tm, bar, 0, part * 8, gy * 16 + py0, b * p.img_c + c);
+    dst += dst_stride;
+    if (++part == per_row) {
+      part = 0;
+      if (++gy == p.img_gh) { gy = 0; ++b; }
+    }
+  }
 }
 
 // EPI_PATCH: matrix row -> (output token row, pos_embed row), or orow < 0 for a pad row of an image operand
@@ -575,8 +588,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
             if constexpr (!A_MN) {
               if (p.a_image) {
-                for (int j = 0; j < BLOCK_M / 8; ++j)
-                  tma_load_patch_box<true>(sA + j * 1024, &tmA, nullptr, bar, p, a_row / 8 + j, kb * BLOCK_K);
+                tma_load_patch_boxes<true>(sA, 1024, &tmA, nullptr, bar, p, a_row / 8, BLOCK_M / 8, kb * BLOCK_K);
               } else {
                 tma_load_2d_2cta(sA, &tmA, bar, kb * BLOCK_K, a_row);
               }
@@ -591,9 +603,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int c = 0; c < Cfg::B_ROWS / 64; ++c) {
                 if (p.b_image) {   // [8 k-row groups][B_ROWS / 64 column chunks][1 KB box]
-                  for (int j = 0; j < BLOCK_K / 8; ++j)
-                    tma_load_patch_box<true>(sB + j * (Cfg::B_ROWS / 64) * 1024 + c * 1024, &tmB, nullptr, bar, p,
-                                             kb * (BLOCK_K / 8) + j, b_row + c * 64);
+                  tma_load_patch_boxes<true>(sB + c * 1024, (Cfg::B_ROWS / 64) * 1024, &tmB, nullptr, bar, p,
+                                             kb * (BLOCK_K / 8), BLOCK_K / 8, b_row + c * 64);
                 } else {
                   tma_load_2d_2cta(sB + c * (BLOCK_K * 128), &tmB, bar, b_row + c * 64, kb * BLOCK_K);
                 }
@@ -603,8 +614,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
             if constexpr (!A_MN) {
               if (p.a_image) {
-                for (int j = 0; j < BLOCK_M / 8; ++j)
-                  tma_load_patch_box<false>(sA + j * 1024, &tmA, &full_bar[stage], 0u, p, a_row / 8 + j, kb * BLOCK_K);
+                tma_load_patch_boxes<false>(sA, 1024, &tmA, &full_bar[stage], 0u, p, a_row / 8, BLOCK_M / 8, kb * BLOCK_K);
               } else {
                 tma_load_2d(sA, &tmA, &full_bar[stage], kb * BLOCK_K, a_row);
               }
@@ -619,9 +629,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int c = 0; c < BLOCK_N / 64; ++c) {
                 if (p.b_image) {
-                  for (int j = 0; j < BLOCK_K / 8; ++j)
-                    tma_load_patch_box<false>(sB + j * (BLOCK_N / 64) * 1024 + c * 1024, &tmB, &full_bar[stage], 0u, p,
-                                              kb * (BLOCK_K / 8) + j, b_row + c * 64);
+                  tma_load_patch_boxes<false>(sB + c * 1024, (BLOCK_N / 64) * 1024, &tmB, &full_bar[stage], 0u, p,
+                                              kb * (BLOCK_K / 8), BLOCK_K / 8, b_row + c * 64);
                 } else {
                   tma_load_2d(sB + c * (BLOCK_K * 128), &tmB, &full_bar[stage], b_row + c * 64, kb * BLOCK_K);
                 }
@@ -645,7 +654,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // Descriptors are built once; per stage / per k-step only the 14-bit start-address field moves
       // (units of 16 B, never carries out of the field: smem < 256 KB).
       const uint32_t s0 = smem_u32(smem);
-      // an image operand (32-byte-swizzle boxes, see tma_load_patch_box): A K-major = [16 row groups][4 k-steps][256 B],
+      // an image operand (32-byte-swizzle boxes, see tma_load_patch_boxes): A K-major = [16 row groups][4 k-steps][256 B],
       // B MN-major = [8 k-row groups][column chunks of 64][4 x 256 B]
       constexpr uint32_t B_SBO_IMG = (Cfg::B_ROWS / 64) * 1024;
       const uint64_t adesc0 = A_MN ? umma_desc_mnmajor(s0, BLOCK_K * 128)
