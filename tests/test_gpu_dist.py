@@ -166,11 +166,11 @@ def _run(worker, *args):
     assert results == {0: "ok", 1: "ok"}, results
 
 
-@pytest.mark.parametrize("sync,wire", [("step", "bf16"), ("step", "fp32"), ("block", "fp32"), ("tail:1", "fp32")])
+@pytest.mark.parametrize("sync,wire", [("step", "bf16"), ("step", "fp32"), ("block", "fp32"), ("tail:1", "fp32"), ("tail:1", "bf16")])
 def test_data_parallel_two_gpus(sync, wire):
     _run(_worker_sum, sync, wire)
 
 
-@pytest.mark.parametrize("sync,wire", [("step", "bf16"), ("step", "fp32"), ("block", "fp32"), ("tail:1", "fp32")])
+@pytest.mark.parametrize("sync,wire", [("step", "bf16"), ("step", "fp32"), ("block", "fp32"), ("tail:1", "fp32"), ("tail:1", "bf16")])
 def test_engine_update_freq_and_clipping_two_gpus(sync, wire):
     _run(_worker_engine, sync, wire)

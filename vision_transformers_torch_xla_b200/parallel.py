@@ -13,8 +13,8 @@ on GPU — with a bucketed all-reduce driven by the fused backward stages:
 
 Wire format (``VITK_DP_GRAD``): ``bf16`` (default) casts the flat fp32 gradient into a persistent bf16 buffer (one
 vitk cast kernel, 0.09 ms for ViT-B), all-reduces THAT (173 MB instead of 346 MB for ViT-B) and lets the AdamW kernel
-read the summed gradient from it; ``fp32`` all-reduces the fp32 buffer in place.  bf16 applies to the ``step`` schedule
-(the overlapped ones reduce slices of the fp32 buffer while backward is still accumulating into other slices).
+read the summed gradient from it; ``fp32`` all-reduces the fp32 buffer in place.  bf16 applies to the ``step`` and
+``tail:K`` schedules (a slice is cast when its gradient is final; ``block`` reduces fp32 slices in place).
 
 Two schedules (``VITK_DP_SYNC``): ``block`` is the bucketed, overlapped one described above; ``step`` (default) reduces
 the whole flat gradient once, right after backward.  Measured at 8 B200, ViT-B/16, batch 256/GPU, same box, back to back:
@@ -123,7 +123,9 @@ class DataParallel(nn.Module):
         if self.sync_mode == "tail":
             self._pending = True
             if tag == self._tail_tag and not self._works:
-                self._works.append(dist.all_reduce(self.store.grad[self._tail_lo:], op=dist.ReduceOp.SUM, async_op=True))
+                # the gradient of blocks K .. head is final here (forward-order layout, backward runs in reverse)
+                self._works.append(dist.all_reduce(self._wire(self._tail_lo, self.store.total), op=dist.ReduceOp.SUM,
+                                                   async_op=True))
             return
         rng = self._ranges.get(tag)
         if rng is None or rng[1] <= rng[0]:
@@ -135,21 +137,30 @@ class DataParallel(nn.Module):
         """Complete the gradient SUM over the replicas (idempotent: a second call before the next backward is a no-op)."""
         if self._pending:
             self._pending = False
-            if self.sync_mode == "tail" and self._works:
-                dist.all_reduce(self.store.grad[:self._tail_lo], op=dist.ReduceOp.SUM)
-            elif self.grad_wire == "bf16" and self._optimizer is not None and self.store.grad.is_cuda:
-                from . import _lib as L
-
-                if self._grad16 is None or self._grad16.numel() != self.store.grad.numel():
-                    self._grad16 = torch.empty_like(self.store.grad, dtype=torch.bfloat16)
-                L.cast_bf16(self.store.grad, self._grad16)
-                dist.all_reduce(self._grad16, op=dist.ReduceOp.SUM)
+            hi = self._tail_lo if (self.sync_mode == "tail" and self._works) else self.store.total
+            dist.all_reduce(self._wire(0, hi), op=dist.ReduceOp.SUM)
+            if self._lowp():
                 self._optimizer.grad_lowp = self._grad16   # AdamW reads the summed gradient from here (this step only)
-            else:
-                dist.all_reduce(self.store.grad, op=dist.ReduceOp.SUM)
         for w in self._works:
             w.wait()
         self._works.clear()
+
+    def _lowp(self) -> bool:
+        """bf16 wire: needs the optimizer (it reads the summed bf16 gradient) and a schedule whose slices are final when
+        they are cast (``step``, ``tail``; ``block`` reduces fp32 slices in place)."""
+        return (self.grad_wire == "bf16" and self._optimizer is not None and self.store.grad.is_cuda
+                and self.sync_mode in ("step", "tail"))
+
+    def _wire(self, lo: int, hi: int) -> torch.Tensor:
+        """The buffer that goes on the wire for gradient elements [lo, hi): the fp32 gradient itself, or its bf16 cast."""
+        if not self._lowp():
+            return self.store.grad[lo:hi]
+        from . import _lib as L
+
+        if self._grad16 is None or self._grad16.numel() != self.store.grad.numel():
+            self._grad16 = torch.empty_like(self.store.grad, dtype=torch.bfloat16)
+        L.cast_bf16(self.store.grad[lo:hi], self._grad16[lo:hi])
+        return self._grad16[lo:hi]
 
     @contextlib.contextmanager
     def no_sync(self):
