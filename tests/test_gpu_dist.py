@@ -64,7 +64,7 @@ def _worker_sum(rank, world, port, q, sync, wire):
         dp.finish_gradient_sync()
         torch.cuda.synchronize()
         lowp = opt.grad_lowp is not None
-        assert lowp == (wire == "bf16" and sync == "step")
+        assert lowp == (wire == "bf16" and sync in ("step", "tail:1"))
         grad_sum = (opt.grad_lowp.float() if lowp else dp.store.grad).clone()
         other = [torch.zeros_like(grad_sum) for _ in range(world)]
         dist.all_gather(other, grad_sum)
