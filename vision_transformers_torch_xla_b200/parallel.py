@@ -25,7 +25,8 @@ another one has finished its whole tile loop.
 
 A third schedule, ``tail:K``, reduces blocks K .. head in one asynchronous all-reduce fired when ``blocks.K`` is ready
 (overlapping only the backward of blocks K-1 .. 0 and the embedding) and the rest after backward; at 2 GPUs it measures
-the same as ``step`` (33.13 / 33.42 ms vs 33.43 / 33.40).
+the same as ``step`` (33.13 / 33.42 ms vs 33.43 / 33.40), and at 8 GPUs on the bf16 wire too (tail:9 / tail:6 / tail:3:
+34.05 / 34.07 / 34.23 ms vs 33.94 - 34.24 for ``step``; 1 GPU of that box: 33.05 ms).
 
 With ``update_freq > 1`` buckets are only reduced on the micro-batch that precedes ``optimizer.step()``
 (``no_sync()`` context, like DDP).
