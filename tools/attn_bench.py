@@ -42,6 +42,9 @@ def run(B, N, H, hd):
     f = 4.0 * B * H * N * N * hd
     fwd = timed(lambda: L.attn_fwd(qkv, out, lse, B, N, H, hd, scale))
     bwd = timed(lambda: L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, hd, scale))
+    if os.environ.get("GB_NOSDPA", "0") == "1":
+        print(f"B={B:4d} N={N:4d} H={H:3d} hd={hd:3d} | vitk fwd {fwd:7.1f} us ({f / fwd / 1e6:6.1f} TF)  bwd {bwd:7.1f} us ({2.5 * f / bwd / 1e6:6.1f} TF)", flush=True)
+        return
     qkv_g = qkv.clone().requires_grad_(True)
     q, k, v = qkv_g.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
     lib_fwd = timed(lambda: F.scaled_dot_product_attention(q, k, v))

@@ -46,6 +46,15 @@ __device__ __forceinline__ void st_swz(uint8_t* tile, int r, int col8, uint4 val
   *reinterpret_cast<uint4*>(p) = val;
 }
 
+// Compiler-level scheduling fence over 32 registers: everything that produces r[] is emitted before, everything that
+// consumes it after (no instruction is generated).
+__device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+               "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+               "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
+
 // ================================================================================================
 // Forward
 // ================================================================================================
@@ -1198,6 +1207,462 @@ int launch_fwd5(const CUtensorMap& tm, const CUtensorMap& tm_out, float* lse, in
   return vitk_check_launch("attn_fwd5");
 }
 
+// ================================================================================================
+// attn_fwd6: the kv-loop forward with the score MMA taken OFF the softmax's critical path (128 < N <= 640).
+// In attn_fwd5 S and P share TMEM columns, so S_{j+1} = Q K_{j+1}^T can only be issued after P_j has been written and both
+// groups end up in phase (timeline, tools/attn_trace5.py): ~2 700 cycles of two groups fighting for the MUFU pipe, then
+// ~1 350 cycles in which both wait for the P V / S hop and nobody issues an exp.  Here P has its own columns:
+//   TMEM per group (256 columns): S [0,128) fp32 | P [128,192) packed bf16 | O [192,256) fp32
+// and the MMA warp issues S_{k+1} as soon as the softmax group has S_k in REGISTERS (s_read) — across kv tiles, q tiles
+// and work items (Q is double-buffered), so the next score tile is always waiting in TMEM when a group finishes a step
+// and the MUFU pipe never idles on an MMA round trip.  P V_k is issued when P_k is written; the group waits for it
+// (pv_done) only before it touches P or O again, one whole max phase later.
+// Work item = (b, h, round): group g owns q tile 2 round + g; when the number of q tiles is odd the last round's second
+// tile does not exist: its group keeps the barrier protocol (and the shared K/V ring) going but issues no MMA and no exp.
+// Every softmax warp executes every wait, also when none of its rows is real: a warp that ran ahead would deliver its
+// arrival for step k + 1 into phase k of a barrier.
+// smem: Q[g][2] (also the O staging tiles) | 4 x (K_j V_j) | barriers = 192 KB
+// ================================================================================================
+constexpr int FWD6_THREADS = 12 * 32;   // softmax g0 | softmax g1 | MMA g0, MMA g1, TMA, idle
+
+struct Fwd6Smem {
+  static constexpr uint32_t Q_OFF = 0;                       // [g][buf]
+  static constexpr uint32_t KV_OFF = 4 * TILE_BYTES;
+  static constexpr int STAGES = 4;
+  static constexpr uint32_t BAR_OFF = KV_OFF + STAGES * 2 * TILE_BYTES;
+  static constexpr uint32_t BYTES = BAR_OFF + 256;
+};
+
+__global__ void __launch_bounds__(FWD6_THREADS, 1)
+attn_fwd6_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
+                 int B, int N, int H, float scale, int stagger, float lazy_thr, long long* trace) {
+  using L = Fwd6Smem;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [2 g + buf] TMA -> MMA g: Q tile landed
+  uint64_t* q_empty = q_full + 4;                                      // [2 g + buf] MMA g -> TMA: O tile stored, buffer reusable
+  uint64_t* kv_full = q_empty + 4;                                     // [4] TMA -> MMA warps
+  uint64_t* kv_empty = kv_full + L::STAGES;                            // [4] both MMA warps -> TMA
+  uint64_t* s_full = kv_empty + L::STAGES;                             // [g] MMA -> group: S_k in TMEM
+  uint64_t* s_read = s_full + 2;                                       // [g] group -> MMA: S_k in registers
+  uint64_t* p_full = s_read + 2;                                       // [g] group -> MMA: P_k written, O rescaled
+  uint64_t* pv_done = p_full + 2;                                      // [g] MMA -> group: P V_k retired
+  uint64_t* o_free = pv_done + 2;                                      // [g] group -> MMA: O read out
+  uint64_t* o_staged = o_free + 2;                                     // [g] group -> MMA: bf16 O tile in smem
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_staged + 2);
+  volatile uint32_t* half_step = tmem_slot + 1;   // set once: group 0 is half way through its first step
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int QT = (N + TILE - 1) / TILE;     // q tiles == kv tiles
+  const int R = (QT + 1) / 2;               // rounds per (b, h)
+  const int items = B * H * R;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_read[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_free[i], 4);
+      mbar_init(&o_staged[i], 4);
+    }
+    for (int i = 0; i < L::STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);
+    }
+    *half_step = 0;
+    fence_mbar_init();
+  }
+  if (warp == 10) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    // 168 registers per thread at launch (384 threads): the control warpgroup gives back (168 - 56) x 128, exactly what the
+    // two softmax warpgroups take ((224 - 168) x 256); an increase that the pool cannot cover never returns
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
+  if (warp == 11) {
+    // idle: completes the control warpgroup (setmaxnreg is a warpgroup-wide instruction)
+  } else if (warp == 10) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_qkv);
+      int k = 0;
+      for (int it = blockIdx.x, n = 0; it < items; it += gridDim.x, ++n) {
+        const int r = it % R, bh = it / R, h = bh % H, b = bh / H;
+        for (int g = 0; g < 2; ++g) {
+          const int qt = 2 * r + g, qb = 2 * g + (n & 1);
+          mbar_wait(&q_empty[qb], ((n >> 1) & 1) ^ 1);
+          if (qt < QT) {
+            mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
+            tma_load_head(smem + L::Q_OFF + qb * TILE_BYTES, &tm_qkv, &q_full[qb], h, qt * TILE, b);
+          } else {
+            mbar_arrive(&q_full[qb]);   // no such q tile: the group only keeps the protocol going
+          }
+        }
+        for (int j = 0; j < QT; ++j, ++k) {
+          const int st = k % L::STAGES;
+          mbar_wait(&kv_empty[st], ((k / L::STAGES) & 1) ^ 1);
+          uint8_t* base = smem + L::KV_OFF + st * 2 * TILE_BYTES;
+          mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
+          tma_load_head(base, &tm_qkv, &kv_full[st], H + h, j * TILE, b);
+          tma_load_head(base + TILE_BYTES, &tm_qkv, &kv_full[st], 2 * H + h, j * TILE, b);
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------ MMA issuer of group g (uniform control flow, one elected lane issues) ------------------------------
+    const int g = warp - 8;   // warps 8, 9
+    const uint32_t slot = tmem_base + g * 256;
+    const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P (TMEM, K-major), B = V MN-major
+    const uint32_t n_last = roundup16(N - (QT - 1) * TILE);
+    const uint32_t idesc_full = umma_idesc(TILE, TILE, 1, false, false), idesc_last = umma_idesc(TILE, n_last, 1, false, false);
+    const uint64_t qdesc0 = umma_desc_kmajor(smem_u32(smem + L::Q_OFF + 2 * g * TILE_BYTES));
+    const uint64_t kdesc0 = umma_desc_kmajor(smem_u32(smem + L::KV_OFF));
+    const uint64_t vdesc0 = umma_desc_mnmajor(smem_u32(smem + L::KV_OFF + TILE_BYTES), TILE_BYTES);
+    constexpr uint64_t STAGE_STEP = (2 * TILE_BYTES) >> 4, QBUF_STEP = TILE_BYTES >> 4;
+    const int n_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = n_items * QT;   // steps of this group; step k = (item n, kv tile j) uses ring tile k
+    auto real_tile = [&](int n) { return 2 * ((int)(blockIdx.x + n * gridDim.x) % R) + g < QT; };
+    auto issue_s = [&](int k, int n, int j, bool real) {   // S_k = Q_n K_j^T (operands already waited for)
+      const uint64_t qd = qdesc0 + (uint64_t)(n & 1) * QBUF_STEP, kd = kdesc0 + (uint64_t)(k % L::STAGES) * STAGE_STEP;
+      const uint32_t ids = (j == QT - 1) ? idesc_last : idesc_full;
+      if (elect_one()) {
+        if (real) {
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) umma_bf16_ss(slot, qd + (uint64_t)(c * 2), kd + (uint64_t)(c * 2), ids, c > 0);
+        }
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    int n = 0, j = 0;
+    bool real = real_tile(0);
+    mbar_wait(&q_full[2 * g], 0);
+    mbar_wait(&kv_full[0], 0);
+    // Two groups that start together stay together (they share the schedulers evenly) and then also END their steps
+    // together: the hand-over between steps (P stores landing, the last S chunk arriving, the row maximum) issues no exp,
+    // and in step the MUFU pipe idles through it twice per step.  Group 1 therefore starts half a step late; after that
+    // neither group ever waits for the other, so the offset stays.
+    if (g == 1 && stagger)
+      while (*half_step == 0) __nanosleep(64);
+    tc_fence_after();
+    issue_s(0, 0, 0, real);
+    for (int k = 0; k < total; ++k) {
+      const bool last = j == QT - 1;
+      const int n1 = last ? n + 1 : n, j1 = last ? 0 : j + 1;
+      bool real1 = real;
+      if (k + 1 < total) {
+        // S_{k+1} goes out as soon as the group holds S_k in registers: it is ready long before the group asks for it
+        if (last) {
+          real1 = real_tile(n1);
+          mbar_wait(&q_full[2 * g + (n1 & 1)], (n1 >> 1) & 1);
+        }
+        mbar_wait(&kv_full[(k + 1) % L::STAGES], ((k + 1) / L::STAGES) & 1);
+        mbar_wait(&s_read[g], k & 1);
+        tc_fence_after();
+        issue_s(k + 1, n1, j1, real1);
+      }
+      mbar_wait(&p_full[g], k & 1);
+      if (j == 0 && n > 0) mbar_wait(&o_free[g], (n - 1) & 1);   // the previous q tile's O has been read out
+      tc_fence_after();
+      {
+        const int st = k % L::STAGES;
+        const int ksteps = (int)(last ? n_last : (uint32_t)TILE) / 16;
+        const uint64_t vd = vdesc0 + (uint64_t)st * STAGE_STEP;
+        if (elect_one()) {
+          if (real)
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_bf16_ts(slot + 192, slot + 128 + 8 * ks, vd + (uint64_t)(ks * 128), idesc_o, (j > 0 || ks > 0));
+          umma_commit(&kv_empty[st]);
+          umma_commit(&pv_done[g]);
+        }
+        __syncwarp();
+      }
+      if (last) {
+        // bf16 O tile (staged by the group in its dead Q buffer) -> global; then the buffer may be reloaded
+        mbar_wait(&o_staged[g], n & 1);
+        if (elect_one()) {
+          if (real) {
+            const int it = (int)(blockIdx.x + n * gridDim.x);
+            const int r = it % R, bh = it / R;
+            tma_store_head(&tm_out, smem + L::Q_OFF + (2 * g + (n & 1)) * TILE_BYTES, bh % H, (2 * r + g) * TILE, bh / H);  // rows >= N clipped
+            tma_store_commit_and_wait_read();
+          }
+          mbar_arrive(&q_empty[2 * g + (n & 1)]);
+        }
+        __syncwarp();
+      }
+      n = n1;
+      j = j1;
+      real = real1;
+    }
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the store
+    __syncwarp();
+  } else {
+    // ------------------------------ softmax group g: 128 threads, thread = score row ------------------------------
+    // Software pipeline over the steps of the group (across kv tiles, q tiles and work items): while the exps of step k
+    // are issued chunk by chunk out of registers, the freed registers are refilled with S_{k+1} (tcgen05.ld is slow when
+    // the MUFU queue is busy — ~700 cycles against ~40 — so a load phase of its own would leave the warp with nothing to
+    // issue); at the end of the step the loads have landed, S_{k+1} is handed back to the MMA warp and its row maximum is
+    // taken, so the next step starts with its exps.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = warp >> 2, quarter = warp & 3;
+    const int rr = quarter * 32 + lane;
+    const uint32_t slot = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float c2 = scale * LOG2E;
+    const int n_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = n_items * QT;
+    auto tile_rows = [&](int n) { return min(TILE, N - (2 * ((int)(blockIdx.x + n * gridDim.x) % R) + g) * TILE); };   // <= 0: no such q tile
+    uint32_t sv[4][32];
+    auto load_chunk = [&](int c) { tmem_ld_32x32(slot + c * 32, sv[c]); };
+    auto row_max = [&](int kvn, int nch, float run) {
+      float m0 = run, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nch) {
+          if (c * 32 + 32 <= kvn) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(sv[c][i]));
+              m1 = fmaxf(m1, __uint_as_float(sv[c][i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(sv[c][i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(sv[c][i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < kvn) m0 = fmaxf(m0, __uint_as_float(sv[c][i]));
+          }
+        }
+      }
+      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    };
+    float m = -INFINITY, l = 0.f, m_new = -INFINITY, alpha = 0.f;
+    bool active = quarter * 32 < tile_rows(0);   // warp-uniform
+    {   // prologue: S_0 into registers, its maximum
+      const int kvn = min(TILE, N), nch = ((int)roundup16(kvn) + 31) / 32;
+      mbar_wait(&s_full[g], 0);
+      tc_fence_after();
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < nch) load_chunk(c);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_read[g]);
+      if (active) {
+        m_new = row_max(kvn, nch, m);
+        alpha = 0.f;
+      }
+    }
+    int k = 0;
+    for (int n = 0; n < n_items; ++n) {
+      const int it = (int)(blockIdx.x + n * gridDim.x);
+      const int r = it % R, bh = it / R, h = bh % H, b = bh / H;
+      const int qt = 2 * r + g;
+      const bool stamp = trace != nullptr && blockIdx.x == 0 && quarter == 0 && lane == 0 && n == 1;
+      uint8_t* stg = smem + L::Q_OFF + (2 * g + (n & 1)) * TILE_BYTES;
+      bool active1 = active;
+      for (int j = 0; j < QT; ++j, ++k) {
+        const int kvn = min(TILE, N - j * TILE);
+        const int nch = ((int)roundup16(kvn) + 31) / 32;
+        const bool has_next = k + 1 < total;
+        const int j1 = (j == QT - 1) ? 0 : j + 1;
+        const int kvn1 = min(TILE, N - j1 * TILE);
+        const int nch1 = ((int)roundup16(kvn1) + 31) / 32;
+        if (j == QT - 1 && has_next) active1 = quarter * 32 < tile_rows(n + 1);
+        if (stamp && j < 5) trace[16 * g + 3 * j] = clock64();
+        const float mc = m_new * c2;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (active && c < nch) {
+            uint32_t pk[16];
+            if (c * 32 + 32 <= kvn) {
+              // all 32 exps first, their consumers afterwards: a warp issues in order, and a sum scheduled two
+              // instructions behind its MUFU.EX2 stalls the warp (and every exp behind it) for the MUFU latency
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sv[c][i] = __float_as_uint(ex2_approx(fmaf(__uint_as_float(sv[c][i]), c2, -mc)));
+              pin32(sv[c]);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float e0 = __uint_as_float(sv[c][2 * i]), e1 = __uint_as_float(sv[c][2 * i + 1]);
+                s0 += e0;
+                s1 += e1;
+                pk[i] = pack_bf16x2(e0, e1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float e0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i]), c2, -mc));
+                float e1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i + 1]), c2, -mc));
+                e0 = (c * 32 + 2 * i < kvn) ? e0 : 0.f;
+                e1 = (c * 32 + 2 * i + 1 < kvn) ? e1 : 0.f;
+                s0 += e0;
+                s1 += e1;
+                pk[i] = pack_bf16x2(e0, e1);
+              }
+            }
+            // P V_{k-1} reads P and accumulates into O: it has retired before either is touched (it was issued a whole
+            // hand-over and 32 exps ago); every warp takes this wait (below for the warps without rows)
+            if (c == 0 && j > 0) {
+              mbar_wait(&pv_done[g], (k - 1) & 1);
+              tc_fence_after();
+            }
+            tmem_st_32x16(slot + 128 + c * 16, pk);
+          }
+          if (c == 0 && j > 0 && !active) mbar_wait(&pv_done[g], (k - 1) & 1);
+          if (c == 1 && k == 0 && g == 0 && quarter == 0 && lane == 0) *half_step = 1;
+          // refill the registers this step is done with from S_{k+1} (issued by the MMA warp when S_k was handed back)
+          // (S_{k+1} takes ~800 cycles from the hand-over to its commit: waiting for it after two chunks, not one)
+          if (has_next && c >= 2) {
+            if (c == 2) {
+              mbar_wait(&s_full[g], (k + 1) & 1);
+              tc_fence_after();
+              if (active1 && 0 < nch1) load_chunk(0);
+              if (active1 && 1 < nch1) load_chunk(1);
+            }
+            if (active1 && c < nch1) load_chunk(c);
+          }
+        }
+        if (active) {
+          l = fmaf(l, alpha, s0 + s1);
+          // O <- alpha * O before P V_k accumulates into it (only if some row of the warp raised its maximum)
+          if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {   // warp-uniform: set together in the hand-over
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint32_t o0[32];
+              tmem_ld_32x32(slot + 192 + hh * 32, o0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                uint32_t t16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) t16[i] = __float_as_uint(__uint_as_float(o0[u * 16 + i]) * alpha);
+                tmem_st_32x16(slot + 192 + hh * 32 + u * 16, t16);
+              }
+            }
+          }
+          m = m_new;
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+        if (stamp && j < 5) trace[16 * g + 3 * j + 1] = clock64();
+
+        if (j == QT - 1) {
+          // ---- O read-out, normalisation, staging (the loads of the next q tile's S_0 are in flight meanwhile) ----
+          mbar_wait(&pv_done[g], k & 1);
+          tc_fence_after();
+          uint32_t ra[32];
+          const float inv = 1.0f / l;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (active) {
+              tmem_ld_32x32(slot + 192 + hh * 32, ra);
+              tmem_ld_wait();
+            }
+            if (hh == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&o_free[g]);
+            }
+            if (active) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int e = u * 8;
+                uint4 v4;
+                v4.x = pack_bf16x2(__uint_as_float(ra[e + 0]) * inv, __uint_as_float(ra[e + 1]) * inv);
+                v4.y = pack_bf16x2(__uint_as_float(ra[e + 2]) * inv, __uint_as_float(ra[e + 3]) * inv);
+                v4.z = pack_bf16x2(__uint_as_float(ra[e + 4]) * inv, __uint_as_float(ra[e + 5]) * inv);
+                v4.w = pack_bf16x2(__uint_as_float(ra[e + 6]) * inv, __uint_as_float(ra[e + 7]) * inv);
+                st_swz(stg, rr, hh * 4 + u, v4);
+              }
+            }
+          }
+          if (active) {
+            const int q = qt * TILE + rr;
+            if (q < N && lse) lse[((long long)b * H + h) * N + q] = m * scale + __logf(l);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_staged[g]);
+          m = -INFINITY;
+          l = 0.f;
+        }
+
+        if (has_next) {
+          if (active1) tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_read[g]);   // the MMA warp may overwrite S with S_{k+2}
+          if (active1) {
+            // lazy_thr = 0: the reference of a row is its running maximum (rescale whenever some row of the warp raised it).
+            // lazy_thr > 0 (VITK_ATTN_FWD6_LAZY, log2 units): the row keeps its old reference unless some row of the warp
+            // outgrew it by more than 2^lazy_thr.  P and l stay relative to the SAME reference, so O = sum(P V) / l and
+            // lse = ref * scale + log(l) are the same numbers in exact arithmetic and the O rescale all but disappears
+            // after the first kv tile — but the dominant key of a peaked row no longer has P = 1 exactly, so its bf16
+            // rounding (2^-9 of the largest term) shows in the output: measured max error 2x, rms error +4 % against the
+            // exact reference, bit-identical to torch's bf16 SDPA on this GPU (tools/attn_check.py).  Default: 0.
+            m_new = row_max(kvn1, nch1, m);
+            if (__any_sync(0xffffffffu, (m_new - m) * c2 > lazy_thr)) {
+              alpha = ex2_approx((m - m_new) * c2);   // 0 on the first kv tile of a q tile (m = -inf)
+            } else {
+              m_new = m;
+              alpha = 1.f;
+            }
+          }
+        }
+        if (stamp && j < 5) trace[16 * g + 3 * j + 2] = clock64();
+      }
+      active = active1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_fwd6(const CUtensorMap& tm, const CUtensorMap& tm_out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd6Smem::BYTES);
+    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd6: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int QT = (N + TILE - 1) / TILE;
+  const int items = B * H * ((QT + 1) / 2);
+  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
+  static const int stagger = [] {   // VITK_ATTN_FWD6_STAGGER=0: both groups start together (comparison)
+    const char* e = getenv("VITK_ATTN_FWD6_STAGGER");
+    return e ? atoi(e) : 1;
+  }();
+  static const float lazy_thr = [] {   // see the hand-over in the kernel
+    const char* e = getenv("VITK_ATTN_FWD6_LAZY");
+    return e ? (float)atof(e) : 0.f;
+  }();
+  attn_fwd6_kernel<<<grid, FWD6_THREADS, Fwd6Smem::BYTES, s>>>(tm, tm_out, lse, B, N, H, scale, stagger, lazy_thr, g_trace_buf);
+  return vitk_check_launch("attn_fwd6");
+}
+
 // D[b, h, n] = sum_d O[b, n, h, d] * dO[b, n, h, d]: one warp per token row, fully coalesced 16-byte loads.
 // (Computing it inside the backward kernel costs ~10k cycles of exposed, row-strided global loads per CTA.)
 __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
@@ -1962,18 +2427,19 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   if (rc) return rc;
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
-  // VITK_ATTN_FWD: unset = warp-specialised persistent kernel (one thread per row) for 128 < N <= 256, the flash-style
-  // kv-loop kernel above that, the tiled one-CTA-per-q-tile kernel for N <= 128; "1" = tiled kernel everywhere;
-  // "5" = the kv-loop kernel also at 128 < N <= 256 (comparison)
+  // VITK_ATTN_FWD: unset = attn_fwd4 (whole score row in TMEM, one thread per row) for 128 < N <= 256, attn_fwd6 (kv loop,
+  // score MMA off the softmax's critical path) above that, the tiled one-CTA-per-q-tile kernel for N <= 128;
+  // "1" = tiled kernel everywhere; "5" / "6" = attn_fwd5 (the previous kv-loop kernel) / attn_fwd6 for every N > 128
   static const int variant = [] {
     const char* e = getenv("VITK_ATTN_FWD");
     return e ? atoi(e) : 0;
   }();
-  if ((variant == 0 || variant == 5) && T >= 2) {
+  if ((variant == 0 || variant == 5 || variant == 6) && T >= 2) {
     rc = make_head_tmap(&tm_out, out, H, hd, N, B, TILE);
     if (rc) return rc;
     if (variant == 0 && T == 2) return launch_fwd4(tm, tm_out, lse, B, N, H, scale, s);
-    return launch_fwd5(tm, tm_out, lse, B, N, H, scale, s);
+    if (variant == 5) return launch_fwd5(tm, tm_out, lse, B, N, H, scale, s);
+    return launch_fwd6(tm, tm_out, lse, B, N, H, scale, s);
   }
   switch (T) {
     case 1: return launch_fwd<1>(tm, out, lse, B, N, H, hd, scale, s);
