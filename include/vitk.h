@@ -123,12 +123,13 @@ int vitk_layernorm_bwd(const void* dy_bf16, int64_t ld_dy, const float* x, int64
 /* ------------------------------------------------------------------------------------------------
  * Attention (timm Attention fused path = F.scaled_dot_product_attention, dropout 0, no mask)
  * qkv: bf16 [B, N, 3, H, hd] (exactly the qkv Linear output), out: bf16 [B, N, H*hd],
- * lse: fp32 [B, H, N] (natural-log sum-exp of scaled scores).  hd must be 64, N <= 640.
+ * lse: fp32 [B, H, N] (natural-log sum-exp of scaled scores).  hd: a multiple of 8 in [16, 80]; N <= 640
+ * (N <= 256 when hd > 64).
  * ---------------------------------------------------------------------------------------------- */
 int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H,
                   int32_t head_dim, float scale, void* stream);
-/* bwd needs a caller-owned fp32 workspace when N > 256 (dQ partials of the kv tiles are red.add'ed into it):
- * vitk_attn_bwd_workspace_bytes() says how much (0 for N <= 256, then `workspace` may be NULL). */
+/* bwd needs a caller-owned fp32 workspace of vitk_attn_bwd_workspace_bytes(): D = rowsum(O * dO) [B, H, N], plus - when
+ * N > 256 or hd > 64 - the dQ accumulator the kv tiles red.add their partials into. */
 int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim);
 int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim,

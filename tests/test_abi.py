@@ -100,8 +100,10 @@ def test_argument_validation_reports_through_error_slot(lib):
     rc = lib.vitk_gemm_bf16(ctypes.byref(args), None)
     assert rc < 0 and b"empty problem" in lib.vitk_last_error()
     assert lib.vitk_gemm_bf16(None, None) < 0
-    rc = lib.vitk_attn_fwd(None, None, None, 1, 16, 1, 72, ctypes.c_float(1.0), None)
-    assert rc == -6 and b"head_dim" in lib.vitk_last_error()  # VITK_STATUS_UNSUPPORTED (wider than the 64-wide head tile)
+    rc = lib.vitk_attn_fwd(None, None, None, 1, 16, 1, 96, ctypes.c_float(1.0), None)
+    assert rc == -6 and b"head_dim" in lib.vitk_last_error()  # VITK_STATUS_UNSUPPORTED (wider than a head tile + its tail)
+    rc = lib.vitk_attn_fwd(None, None, None, 1, 300, 1, 72, ctypes.c_float(1.0), None)
+    assert rc == -6 and b"N <= 256" in lib.vitk_last_error()   # heads of 72 / 80: sequences of at most 256 tokens
     rc = lib.vitk_layernorm_fwd(None, 770, None, None, None, 770, None, None, 4, 770, ctypes.c_float(1e-6), None)
     assert rc < 0 and b"multiple of 4" in lib.vitk_last_error()
     rc = lib.vitk_adamw_flat(None, None, None, None, None, None, None, None, 6, None, 64, 1, None, None, ctypes.c_float(0.9),

@@ -42,9 +42,11 @@ def test_attn_fwd(cuda_device, B, N, H, hd=64):
     # P is rounded to bf16 before P*V (as in every flash-attention bf16 kernel) and the output is bf16
     assert elem_err(out.float(), ref) < 1e-2 * narrow
     # max|err| / rms: one bf16 rounding of the largest output element alone is 2^-9 * max|ref| (a 10-sigma outlier in a
-    # 5M-element tensor), so the bound scales with max|ref| / rms
-    half_ulp_of_max = 2.0 ** -9 * float(ref.abs().max() / ref.pow(2).mean().sqrt())
-    assert rel_err(out.float(), ref) < max(3e-2, 1.5 * half_ulp_of_max) * narrow
+    # 5M-element tensor), so the bound scales with max|ref| / rms.  Two half ulps: an fp32 result next to a rounding tie
+    # lands on the other bf16 neighbour after any change of summation order (torch's own bf16 SDPA shows 2.04 half ulps on
+    # the (1, 577, 4) case, tools/attn_check.py); the P rounding underneath is the rest.
+    half_ulp_of_max = 2.0 ** -9 * float(ref.detach().abs().max() / ref.detach().pow(2).mean().sqrt())
+    assert rel_err(out.float(), ref) < max(3e-2, 2.2 * half_ulp_of_max) * narrow
     # and never worse than 2x the error torch's own bf16 SDPA makes against the same fp32 reference
     q, k, v = qkv.view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0)
     lib = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, H * hd)
@@ -68,7 +70,7 @@ def test_attn_bwd(cuda_device, B, N, H, hd=64):
     _, _, ref = _ref(qkv, B, N, H, hd, dout)
     d = dqkv.float().view(B, N, 3, H * hd)
     r = ref.view(B, N, 3, H * hd)
-    narrow = (64 / hd) ** 0.5   # see test_attn_fwd
+    narrow = max(1.0, (64 / hd) ** 0.5)   # see test_attn_fwd
     for i, name in enumerate("qkv"):
         # P and dS are rounded to bf16 before the dV/dK/dQ GEMMs; outputs are bf16
         assert elem_err(d[:, :, i], r[:, :, i]) < 2.5e-2 * narrow, f"d{name}"
@@ -87,13 +89,28 @@ def test_attn_narrow_heads(cuda_device, B, N, H, hd):
     test_attn_bwd(cuda_device, B, N, H, hd)
 
 
+@pytest.mark.parametrize("hd", [72, 80])
+@pytest.mark.parametrize("B,N,H", [(3, 197, 4), (2, 100, 2), (2, 256, 3), (40, 196, 4), (1, 129, 1)])
+def test_attn_wide_heads(cuda_device, B, N, H, hd):
+    """64 < head_dim <= 80 (my_vit_xs: 72, /root/reference/models/my_vit.py:97-106): every operand takes a second tile
+    with the head's columns 64 .. (zero from head_dim on): one more k-step for Q K^T / dO V^T, 80 accumulator columns for
+    O / dV / dK / dQ.  N <= 256."""
+    test_attn_fwd(cuda_device, B, N, H, hd)
+    test_attn_bwd(cuda_device, B, N, H, hd)
+
+
 def test_attn_unsupported_raises(cuda_device):
     from vision_transformers_torch_xla_b200 import _lib as L
-    qkv = torch.zeros(1, 16, 3 * 72, device=cuda_device, dtype=torch.bfloat16)
-    out = torch.zeros(1, 16, 72, device=cuda_device, dtype=torch.bfloat16)
+    qkv = torch.zeros(1, 16, 3 * 96, device=cuda_device, dtype=torch.bfloat16)
+    out = torch.zeros(1, 16, 96, device=cuda_device, dtype=torch.bfloat16)
     lse = torch.zeros(1, 1, 16, device=cuda_device)
     with pytest.raises(L.VitkError):
-        L.attn_fwd(qkv, out, lse, 1, 16, 1, 72, 72 ** -0.5)   # wider than the 64-wide head tile
+        L.attn_fwd(qkv, out, lse, 1, 16, 1, 96, 96 ** -0.5)   # wider than a head tile plus its tail
+    qkv = torch.zeros(1, 300, 3 * 72, device=cuda_device, dtype=torch.bfloat16)
+    out = torch.zeros(1, 300, 72, device=cuda_device, dtype=torch.bfloat16)
+    lse = torch.zeros(1, 1, 300, device=cuda_device)
+    with pytest.raises(L.VitkError):
+        L.attn_fwd(qkv, out, lse, 1, 300, 1, 72, 72 ** -0.5)   # wide heads: N <= 256
 
 
 @pytest.mark.parametrize("fwd,bwd,N,extra", [("1", "1", 197, {}), ("5", "0", 577, {}), ("5", "0", 197, {}), ("6", "0", 197, {}),

@@ -73,6 +73,7 @@ CASES = [
     ("deit_base_distilled_patch16_224", dict(num_classes=1000, drop_path_rate=0.1), 8, 1.5e-2),
     ("vit_large_patch16_384", dict(num_classes=1000, global_pool="avg", drop_path_rate=0.1), 2, 2e-2),
     ("my_vit_mini", dict(num_classes=1000, global_pool="avg", drop_path_rate=0.1), 8, 1.5e-2),
+    ("my_vit_xs", dict(num_classes=1000, global_pool="avg", drop_path_rate=0.1), 8, 1.5e-2),   # head_dim 72
 ]
 
 

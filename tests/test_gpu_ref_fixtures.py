@@ -148,10 +148,10 @@ def test_cuda_path_matches_reference_distilled_micro(cuda_device, fx):
         assert rel_err(model(x), case["logits_eval"].to(cuda_device)) < 2e-2
 
 
-@pytest.mark.parametrize("name", ["vit_tiny_patch16_224", "deit_tiny_distilled_patch16_224", "my_vit_mini"])
+@pytest.mark.parametrize("name", ["vit_tiny_patch16_224", "deit_tiny_distilled_patch16_224", "my_vit_mini", "my_vit_xs"])
 def test_named_configs_with_drop_path_match_reference(cuda_device, fx, name):
     """The reference's own entrypoints with drop_path_rate 0.1 (the launch value, run_train.sh:58): config 1 (ViT-Ti),
-    distilled DeiT-Ti and my_vit_mini (head_dim 48, my_vit.py:85-95) on a seeded 2-image batch with the reference's
+    distilled DeiT-Ti, my_vit_mini (head_dim 48, my_vit.py:85-95) and my_vit_xs (head_dim 72, my_vit.py:97-106) on a seeded 2-image batch with the reference's
     masks replayed: logits, loss, the last block's activations, every small gradient elementwise, all gradients by
     their energy."""
     from oracle import vit_oracle as O

@@ -66,8 +66,9 @@ def test_options_outside_the_fast_path_raise_instead_of_falling_back():
         with pytest.raises(NotImplementedError):
             VisionTransformer(embed_dim=64, depth=1, num_heads=1, **kw)
     with pytest.raises(NotImplementedError):
-        Attention(288, num_heads=4)  # head_dim 72 is wider than the attention kernels' 64-wide head tile
+        Attention(384, num_heads=4)  # head_dim 96 is wider than a 64-wide head tile plus its 16-column tail
     assert Attention(144, num_heads=3).head_dim == 48   # narrower heads run zero-padded (my_vit_mini)
+    assert Attention(288, num_heads=4).head_dim == 72   # my_vit_xs: a second, zero-padded tile per operand
     with pytest.raises(NotImplementedError):
         Mlp(64, act_layer=torch.nn.ReLU)
     with pytest.raises(NotImplementedError):

@@ -58,22 +58,37 @@ __device__ __forceinline__ void pin32(uint32_t (&r)[32]) {
 // ================================================================================================
 // Forward
 // ================================================================================================
-// smem: Q [16K] | K_j, V_j for all kv tiles [T * 32K] | P [32K] | barriers
-template <int T>
+// smem: Q | K_j, V_j for all kv tiles | P [32K] | barriers
+// WIDE (64 < head_dim <= 80, my_vit_xs: 72): every operand is [64-column tile][tail tile] (2 x 16 KB, the tail holding
+// columns 64 .. 127 of the head with everything >= head_dim zero-filled by TMA).  As a K-major operand the tail adds one
+// k-step (columns 64 .. 79) to Q K^T; as an MN-major operand it is the second 64-wide chunk of V, of which P V with
+// N = 80 reads the first 16 columns.  O has 80 accumulator columns.
+constexpr int HDW_MAX = 80;
+
+template <int T, bool WIDE>
 struct FwdSmem {
+  static constexpr uint32_t OPB = WIDE ? 2 * TILE_BYTES : TILE_BYTES;   // bytes of one operand tile (+ tail)
   static constexpr uint32_t Q_OFF = 0;
-  static constexpr uint32_t KV_OFF = TILE_BYTES;
-  static constexpr uint32_t P_OFF = KV_OFF + T * 2 * TILE_BYTES;
+  static constexpr uint32_t KV_OFF = OPB;
+  static constexpr uint32_t P_OFF = KV_OFF + T * 2 * OPB;
   static constexpr uint32_t BAR_OFF = P_OFF + 2 * TILE_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 128;
 };
 
-template <int T>
+// one operand box (+ its tail for wide heads) of head slot `slot`, rows row0 .., image b
+template <bool WIDE>
+__device__ __forceinline__ void load_head_tiles(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int slot, int row0, int b) {
+  tma_load_head(dst, tm, bar, slot, row0, b);
+  if (WIDE) tma_load_head_col(dst + TILE_BYTES, tm, bar, HD, slot, row0, b);
+}
+
+template <int T, bool WIDE>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
                 float* __restrict__ lse, int N, int H, int hd, float scale, long long* trace) {
   VITK_STAMP(0);
-  using L = FwdSmem<T>;
+  using L = FwdSmem<T, WIDE>;
+  constexpr int HDW = WIDE ? HDW_MAX : HD;   // accumulator columns of O
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* bar_kv = bar_q + 1;       // [T]
@@ -102,17 +117,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;         // S: 128 columns
-  const uint32_t tmem_o = tmem_base + 128;   // O_j: 64 columns
+  const uint32_t tmem_o = tmem_base + 128;   // O_j: 64 (80) columns
   VITK_STAMP(1);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
-    mbar_arrive_expect_tx(bar_q, TILE_BYTES);
-    tma_load_head(smem + L::Q_OFF, &tm_qkv, bar_q, h, q0, b);
+    mbar_arrive_expect_tx(bar_q, L::OPB);
+    load_head_tiles<WIDE>(smem + L::Q_OFF, &tm_qkv, bar_q, h, q0, b);
     for (int j = 0; j < nkv; ++j) {
-      mbar_arrive_expect_tx(&bar_kv[j], 2 * TILE_BYTES);
-      tma_load_head(smem + L::KV_OFF + j * 2 * TILE_BYTES, &tm_qkv, &bar_kv[j], H + h, j * TILE, b);
-      tma_load_head(smem + L::KV_OFF + j * 2 * TILE_BYTES + TILE_BYTES, &tm_qkv, &bar_kv[j], 2 * H + h, j * TILE, b);
+      mbar_arrive_expect_tx(&bar_kv[j], 2 * L::OPB);
+      load_head_tiles<WIDE>(smem + L::KV_OFF + j * 2 * L::OPB, &tm_qkv, &bar_kv[j], H + h, j * TILE, b);
+      load_head_tiles<WIDE>(smem + L::KV_OFF + j * 2 * L::OPB + L::OPB, &tm_qkv, &bar_kv[j], 2 * H + h, j * TILE, b);
     }
   }
 
@@ -120,9 +135,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   const int r = threadIdx.x;  // row inside the q tile
   const float c2 = scale * LOG2E;
   float m_run = -INFINITY, l_run = 0.f;
-  float o_acc[HD];
+  float o_acc[HDW];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+  for (int d = 0; d < HDW; ++d) o_acc[d] = 0.f;
 
   uint8_t* sP = smem + L::P_OFF;
   const uint32_t sQ_u = smem_u32(smem + L::Q_OFF);
@@ -131,17 +146,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
   for (int j = 0; j < nkv; ++j) {
     const int kvn = min(TILE, N - j * TILE);
     const uint32_t n_eff = roundup16(kvn);
-    const uint32_t sK_u = smem_u32(smem + L::KV_OFF + j * 2 * TILE_BYTES);
-    const uint32_t sV_u = sK_u + TILE_BYTES;
+    const uint32_t sK_u = smem_u32(smem + L::KV_OFF + j * 2 * L::OPB);
+    const uint32_t sV_u = sK_u + L::OPB;
     if (warp == 0) {   // uniform control flow + one elected lane: the descriptors stay in uniform registers
       if (j == 0) mbar_wait(bar_q, 0);
       mbar_wait(&bar_kv[j], 0);
       tc_fence_after();
       const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
       const uint64_t qd = umma_desc_kmajor(sQ_u), kd = umma_desc_kmajor(sK_u);
+      const uint64_t qd_t = umma_desc_kmajor(sQ_u + TILE_BYTES), kd_t = umma_desc_kmajor(sK_u + TILE_BYTES);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tmem_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0);
+        if (WIDE) umma_bf16_ss(tmem_s, qd_t, kd_t, idesc, true);   // head columns 64 .. 79
         umma_commit(bar_s);
       }
       __syncwarp();
@@ -209,7 +226,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     VITK_STAMP(4 + j * 4);
     if (warp == 0) {
       tc_fence_after();
-      const uint32_t idesc = umma_idesc(TILE, HD, 1, false, true);  // A = P K-major, B = V MN-major
+      const uint32_t idesc = umma_idesc(TILE, HDW, 1, false, true);  // A = P K-major, B = V MN-major (tail = second 64-wide chunk)
       const int ksteps = (int)n_eff / 16;
       const uint64_t pdesc = umma_desc_kmajor(sP_u), vdesc = umma_desc_mnmajor(sV_u, TILE_BYTES);
       if (elect_one()) {
@@ -231,6 +248,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha, __uint_as_float(ov[i]));
     }
+    if (WIDE) {
+      uint32_t ov[16];
+      tmem_ld_32x16(tmem_o + lane_addr + 64, ov);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o_acc[(HDW - 16) + i] = fmaf(o_acc[(HDW - 16) + i], alpha, __uint_as_float(ov[i]));
+    }
     tc_fence_before();
   }
 
@@ -239,8 +263,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
     const float inv = 1.0f / l_run;
     __nv_bfloat16* orow = out + ((long long)b * N + q) * (H * hd) + h * hd;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 8 >= hd) break;   // columns >= head_dim are the zero padding of the 64-wide tiles
+    for (int g = 0; g < HDW / 8; ++g) {
+      if (g * 8 >= hd) break;   // columns >= head_dim are the zero padding of the tiles
       uint4 u;
       u.x = pack_bf16x2(o_acc[g * 8 + 0] * inv, o_acc[g * 8 + 1] * inv);
       u.y = pack_bf16x2(o_acc[g * 8 + 2] * inv, o_acc[g * 8 + 3] * inv);
@@ -1685,6 +1709,12 @@ __global__ void attn_dsum_kernel(const __nv_bfloat16* __restrict__ out, const __
       const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
       s = a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
     }
+    if (h < H && (u + 8) * 8 < hd) {   // head columns 64 .. (wide heads)
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(op + h * hd) + u + 8), d = __ldg(reinterpret_cast<const uint4*>(dp + h * hd) + u + 8);
+      const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+      const float2 d0 = unpack_bf16x2(d.x), d1 = unpack_bf16x2(d.y), d2 = unpack_bf16x2(d.z), d3 = unpack_bf16x2(d.w);
+      s += a0.x * d0.x + a0.y * d0.y + a1.x * d1.x + a1.y * d1.y + a2.x * d2.x + a2.y * d2.y + a3.x * d3.x + a3.y * d3.y;
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -2143,26 +2173,49 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
 // q tiles, and each dQ_ij partial is read out of a TMEM scratch tile and red.add'ed into an fp32 workspace
 // [B, N, H*64] (the q rows are shared by the T CTAs of a head); a small kernel then casts it into dqkv.
 // TMEM: S [0,128) | dP [128,256) | dV_j [256,320) | dK_j [320,384) | dQ_ij [384,448)
+// WIDE (64 < head_dim <= 80, used for every N then): operands are [64-column tile][tail tile] pairs (see FwdSmem), S and dP
+// take one more k-step, dV / dK / dQ have 80 accumulator columns (TMEM: 256 | 336 | 416 .. 496), Q_i / dO_i are single-
+// buffered (192 KB of smem otherwise) and the fp32 dQ workspace keeps 80-wide heads.
 // ================================================================================================
+template <bool WIDE>
 struct BwdStreamSmem {
+  static constexpr uint32_t OPB = WIDE ? 2 * TILE_BYTES : TILE_BYTES;
+  static constexpr int NBUF = WIDE ? 1 : 2;
   static constexpr uint32_t KV_OFF = 0;
-  static constexpr uint32_t QDO_OFF = 2 * TILE_BYTES;   // [2 buffers][Q_i, dO_i]
-  static constexpr uint32_t P_OFF = 6 * TILE_BYTES;
-  static constexpr uint32_t DS_OFF = 8 * TILE_BYTES;
-  static constexpr uint32_t BAR_OFF = 10 * TILE_BYTES;
+  static constexpr uint32_t QDO_OFF = 2 * OPB;                     // [NBUF buffers][Q_i, dO_i]
+  static constexpr uint32_t P_OFF = QDO_OFF + NBUF * 2 * OPB;
+  static constexpr uint32_t DS_OFF = P_OFF + 2 * TILE_BYTES;
+  static constexpr uint32_t BAR_OFF = DS_OFF + 2 * TILE_BYTES;
   static constexpr uint32_t BYTES = BAR_OFF + 128;
 };
+
+// accumulator columns 64 .. 79 of a wide head -> bf16 (the first hd - 64 of them exist)
+__device__ __forceinline__ void store_row_bf16_tail(__nv_bfloat16* dst, const uint32_t (&a)[16], int n) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (g * 8 >= n) break;
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(a[g * 8 + 0]), __uint_as_float(a[g * 8 + 1]));
+    u.y = pack_bf16x2(__uint_as_float(a[g * 8 + 2]), __uint_as_float(a[g * 8 + 3]));
+    u.z = pack_bf16x2(__uint_as_float(a[g * 8 + 4]), __uint_as_float(a[g * 8 + 5]));
+    u.w = pack_bf16x2(__uint_as_float(a[g * 8 + 6]), __uint_as_float(a[g * 8 + 7]));
+    *reinterpret_cast<uint4*>(dst + g * 8) = u;
+  }
+}
 
 // Q_i / dO_i are double-buffered (tile i+1 is loading while tile i is processed), S / dP of tile i+1 are issued right
 // behind the dV / dK / dQ MMAs of tile i (their TMEM buffers are free once the threads have read them), so they execute
 // while the threads read dQ_ij out and red.add it.  D = rowsum(O * dO) comes from the workspace (attn_dsum_kernel).
 // No masks: kv rows >= N are TMA zero fill (they reach only discarded dK / dV rows and add 0 to dQ); q rows >= N have
 // Q = dO = 0 and use lse = D = 0.
+template <bool WIDE>
 __global__ void __launch_bounds__(128)
 attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                        const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                        float* __restrict__ dq32, int N, int H, int hd, float scale) {
-  using L = BwdStreamSmem;
+  using L = BwdStreamSmem<WIDE>;
+  constexpr int HDW = WIDE ? HDW_MAX : HD;   // accumulator columns of dV / dK / dQ, head pitch of the dQ workspace
+  constexpr int NBUF = L::NBUF;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* bar_q = bar_kv + 1;     // [2]
@@ -2194,36 +2247,42 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320;
-  const uint32_t tm_dq = tmem_base + 384;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tm_dv + HDW;
+  const uint32_t tm_dq = tm_dk + HDW;
   const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
   const int r = threadIdx.x;
   const float c2 = scale * LOG2E;
   uint8_t* sP = smem + L::P_OFF;
   uint8_t* sDS = smem + L::DS_OFF;
-  const uint32_t sK = smem_u32(smem + L::KV_OFF), sV = sK + TILE_BYTES;
+  const uint32_t sK = smem_u32(smem + L::KV_OFF), sV = sK + L::OPB;
   const uint32_t sQDO = smem_u32(smem + L::QDO_OFF);
   const uint32_t sP_u = smem_u32(sP), sDS_u = smem_u32(sDS);
   const uint32_t idesc = umma_idesc(TILE, n_eff, 1, false, false);
   const uint64_t kd = umma_desc_kmajor(sK), vd = umma_desc_kmajor(sV), k_mn = umma_desc_mnmajor(sK, TILE_BYTES);
+  const uint64_t kd_t = umma_desc_kmajor(sK + TILE_BYTES), vd_t = umma_desc_kmajor(sV + TILE_BYTES);   // WIDE: head columns 64 .. 79
+  auto buf_of = [&](int i) { return NBUF == 2 ? (i & 1) : 0; };
+  auto phase_of = [&](int i) { return NBUF == 2 ? ((i >> 1) & 1) : (i & 1); };
 
   auto load_q = [&](int i) {   // thread 0 only
-    const int buf = i & 1;
-    mbar_arrive_expect_tx(&bar_q[buf], 2 * TILE_BYTES);
-    tma_load_head(smem + L::QDO_OFF + buf * 2 * TILE_BYTES, &tm_qkv, &bar_q[buf], h, i * TILE, b);
-    tma_load_head(smem + L::QDO_OFF + buf * 2 * TILE_BYTES + TILE_BYTES, &tm_do, &bar_q[buf], h, i * TILE, b);
+    const int buf = buf_of(i);
+    mbar_arrive_expect_tx(&bar_q[buf], 2 * L::OPB);
+    load_head_tiles<WIDE>(smem + L::QDO_OFF + buf * 2 * L::OPB, &tm_qkv, &bar_q[buf], h, i * TILE, b);
+    load_head_tiles<WIDE>(smem + L::QDO_OFF + buf * 2 * L::OPB + L::OPB, &tm_do, &bar_q[buf], h, i * TILE, b);
   };
   // S = Q_i K_j^T and dP = dO_i V_j^T (warp 0, uniform control flow, one elected lane)
   auto issue_s_dp = [&](int i) {
-    const uint32_t sQ = sQDO + (i & 1) * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
+    const uint32_t sQ = sQDO + buf_of(i) * 2 * L::OPB, sDO = sQ + L::OPB;
     const uint64_t qd = umma_desc_kmajor(sQ), dod = umma_desc_kmajor(sDO);
-    mbar_wait(&bar_q[i & 1], (i >> 1) & 1);
+    const uint64_t qd_t = umma_desc_kmajor(sQ + TILE_BYTES), dod_t = umma_desc_kmajor(sDO + TILE_BYTES);
+    mbar_wait(&bar_q[buf_of(i)], phase_of(i));
     tc_fence_after();
     if (elect_one()) {
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_s, qd + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), idesc, k > 0);
+      if (WIDE) umma_bf16_ss(tm_s, qd_t, kd_t, idesc, true);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(tm_dp, dod + (uint64_t)(k * 2), vd + (uint64_t)(k * 2), idesc, k > 0);
+      if (WIDE) umma_bf16_ss(tm_dp, dod_t, vd_t, idesc, true);
       umma_commit(bar_sp);
     }
     __syncwarp();
@@ -2232,11 +2291,11 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
-    mbar_arrive_expect_tx(bar_kv, 2 * TILE_BYTES);
-    tma_load_head(smem + L::KV_OFF, &tm_qkv, bar_kv, H + h, j * TILE, b);
-    tma_load_head(smem + L::KV_OFF + TILE_BYTES, &tm_qkv, bar_kv, 2 * H + h, j * TILE, b);
+    mbar_arrive_expect_tx(bar_kv, 2 * L::OPB);
+    load_head_tiles<WIDE>(smem + L::KV_OFF, &tm_qkv, bar_kv, H + h, j * TILE, b);
+    load_head_tiles<WIDE>(smem + L::KV_OFF + L::OPB, &tm_qkv, bar_kv, 2 * H + h, j * TILE, b);
     load_q(0);
-    if (nt > 1) load_q(1);
+    if (NBUF == 2 && nt > 1) load_q(1);
   }
   if (warp == 0) {
     mbar_wait(bar_kv, 0);
@@ -2301,10 +2360,11 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      const uint32_t sQ = sQDO + (i & 1) * 2 * TILE_BYTES, sDO = sQ + TILE_BYTES;
-      const uint32_t idesc_t = umma_idesc(TILE, HD, 1, true, true);
-      const uint32_t idesc_q = umma_idesc(TILE, HD, 1, false, true);
+      const uint32_t sQ = sQDO + buf_of(i) * 2 * L::OPB, sDO = sQ + L::OPB;
+      const uint32_t idesc_t = umma_idesc(TILE, HDW, 1, true, true);
+      const uint32_t idesc_q = umma_idesc(TILE, HDW, 1, false, true);
       const int qsteps = (int)q_eff / 16;
+      // MN-major B operands over the head dimension: the tail tile is their second 64-wide chunk (pitch TILE_BYTES)
       const uint64_t p_mn = umma_desc_mnmajor(sP_u, TILE_BYTES), do_mn = umma_desc_mnmajor(sDO, TILE_BYTES);
       const uint64_t ds_mn = umma_desc_mnmajor(sDS_u, TILE_BYTES), q_mn = umma_desc_mnmajor(sQ, TILE_BYTES);
       const uint64_t ds_k = umma_desc_kmajor(sDS_u);
@@ -2317,19 +2377,19 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
       __syncwarp();
       // S / dP of the next q tile run while the threads read dQ_ij out (every thread has read S / dP of this tile)
-      if (i + 1 < nt) issue_s_dp(i + 1);
+      if (NBUF == 2 && i + 1 < nt) issue_s_dp(i + 1);
     }
     mbar_wait(bar_mma, i & 1);
     tc_fence_after();
-    // Q_i / dO_i are no longer read: their buffer takes tile i + 2
-    if (threadIdx.x == 0 && i + 2 < nt) load_q(i + 2);
+    // Q_i / dO_i are no longer read: their buffer takes tile i + 2 (i + 1 when there is one buffer)
+    if (threadIdx.x == 0 && i + NBUF < nt) load_q(i + NBUF);
     {
       uint32_t a0[32], a1[32];
       tmem_ld_32x32(tm_dq + lane_addr, a0);
       tmem_ld_32x32(tm_dq + lane_addr + 32, a1);
       tmem_ld_wait();
+      float* dst = dq32 + ((long long)b * N + q) * (H * HDW) + h * HDW;
       if (row_ok) {
-        float* dst = dq32 + ((long long)b * N + q) * (H * HD) + h * HD;
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(a0[g * 4])),
@@ -2342,23 +2402,49 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
                        : "memory");
         }
       }
+      if (WIDE) {
+        uint32_t a2[16];
+        tmem_ld_32x16(tm_dq + lane_addr + 64, a2);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 64 + g * 4), "f"(__uint_as_float(a2[g * 4])),
+                         "f"(__uint_as_float(a2[g * 4 + 1])), "f"(__uint_as_float(a2[g * 4 + 2])),
+                         "f"(__uint_as_float(a2[g * 4 + 3]))
+                         : "memory");
+        }
+      }
     }
     tc_fence_before();
     __syncthreads();  // P / dS / the dQ scratch may be overwritten by the next q tile
     tc_fence_after();
+    if (NBUF == 1 && warp == 0 && i + 1 < nt) issue_s_dp(i + 1);   // the single Q / dO buffer has just been reloaded
   }
 
   {
     uint32_t a0[32], a1[32];
     const int kv = j * TILE + r;
+    __nv_bfloat16* dv_row = dqkv + ((long long)b * N + kv) * (3 * H * hd) + (2 * H + h) * hd;
+    __nv_bfloat16* dk_row = dqkv + ((long long)b * N + kv) * (3 * H * hd) + (H + h) * hd;
     tmem_ld_32x32(tm_dv + lane_addr, a0);
     tmem_ld_32x32(tm_dv + lane_addr + 32, a1);
     tmem_ld_wait();
-    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * hd) + (2 * H + h) * hd, a0, a1, hd);
+    if (kv < N) store_row_bf16_64(dv_row, a0, a1, hd);
     tmem_ld_32x32(tm_dk + lane_addr, a0);
     tmem_ld_32x32(tm_dk + lane_addr + 32, a1);
     tmem_ld_wait();
-    if (kv < N) store_row_bf16_64(dqkv + ((long long)b * N + kv) * (3 * H * hd) + (H + h) * hd, a0, a1, hd);
+    if (kv < N) store_row_bf16_64(dk_row, a0, a1, hd);
+    if (WIDE) {
+      uint32_t t0[16], t1[16];
+      tmem_ld_32x16(tm_dv + lane_addr + 64, t0);
+      tmem_ld_32x16(tm_dk + lane_addr + 64, t1);
+      tmem_ld_wait();
+      if (kv < N) {
+        store_row_bf16_tail(dv_row + 64, t0, hd - 64);
+        store_row_bf16_tail(dk_row + 64, t1, hd - 64);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -2368,16 +2454,16 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   }
 }
 
-// dqkv[row, h * hd + c] = bf16(dq32[row, h * 64 + c]) for c < hd: the fp32 dQ workspace keeps the padded 64-wide heads of
-// the tiles, dqkv is the gradient of the qkv Linear output (row pitch 3 * H * hd)
-__global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int H, int hd) {
+// dqkv[row, h * hd + c] = bf16(dq32[row, h * pitch + c]) for c < hd: the fp32 dQ workspace keeps the padded heads of the
+// tiles (pitch 64, or 80 for wide heads), dqkv is the gradient of the qkv Linear output (row pitch 3 * H * hd)
+__global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dqkv, long long rows, int H, int hd, int pitch) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per_row = H * (hd / 8);
   if (idx >= rows * per_row) return;
   const long long row = idx / per_row;
   const int rem = (int)(idx - row * per_row);
   const int h = rem / (hd / 8), c = (rem - h * (hd / 8)) * 8;
-  const float* src = dq32 + (row * H + h) * HD + c;
+  const float* src = dq32 + (row * H + h) * pitch + c;
   const float4 a = *reinterpret_cast<const float4*>(src);
   const float4 b2 = *reinterpret_cast<const float4*>(src + 4);
   uint4 u;
@@ -2388,38 +2474,43 @@ __global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __
   *reinterpret_cast<uint4*>(dqkv + row * 3 * H * hd + h * hd + c) = u;
 }
 
-template <int T>
+template <int T, bool WIDE = false>
 int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
-  auto kern = attn_fwd_kernel<T>;
+  auto kern = attn_fwd_kernel<T, WIDE>;
+  using L = FwdSmem<T, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FwdSmem<T>::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  kern<<<grid, 128, FwdSmem<T>::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, hd, scale, g_trace_buf);
+  kern<<<grid, 128, L::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, hd, scale, g_trace_buf);
   return vitk_check_launch("attn_fwd");
 }
 
 // The attention tensors are mapped for TMA as (head_dim, head slot, token, image): a [rows][64] box of one head slot
 // arrives as a 128-byte-swizzled tile whose columns >= head_dim are zero-filled (and are clipped again on the way out),
 // so head_dim < 64 (my_vit_mini: 48) runs on the same 64-wide tiles; the zero columns add nothing to Q K^T or dO V^T
-// and produce zero columns of O / dQ / dK / dV.  slots = 3 H for qkv / dqkv, H for out / dout.
+// and produce zero columns of O / dQ / dK / dV.  A head wider than 64 (my_vit_xs: 72) takes a second box at column 64 (its
+// tail tile: columns 64 .. 127, zero from head_dim on).  slots = 3 H for qkv / dqkv, H for out / dout.
 int make_head_tmap(CUtensorMap* tm, const void* base, int slots, int hd, int N, int B, int box_rows) {
   return vitk_make_tmap_4d(tm, base, 2, (uint64_t)hd, (uint64_t)slots, (uint64_t)N, (uint64_t)B, (uint64_t)hd,
                            (uint64_t)slots * hd, (uint64_t)N * slots * hd, HD, 1, (uint32_t)box_rows, 1);
 }
 
-bool head_dim_ok(int hd) { return hd >= 16 && hd <= HD && hd % 8 == 0; }
+bool head_dim_ok(int hd) { return hd >= 16 && hd <= HDW_MAX && hd % 8 == 0; }
+constexpr int WIDE_MAX_N = 2 * TILE;   // heads wider than 64: the forward keeps every K / V tile (+ tail) of a head in smem
 
 }  // namespace
 
 extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t head_dim,
                              float scale, void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_fwd: bad shape B=%d N=%d H=%d", B, N, H);
-  VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d (built for multiples of 8 in [16, 64])", head_dim);
+  VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d (built for multiples of 8 in [16, 80])", head_dim);
   VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_fwd: N=%d > %d", N, FWD_MAX_T * TILE);
+  VITK_REQUIRE(head_dim <= HD || N <= WIDE_MAX_N, VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d > 64 is built for N <= %d (N=%d)",
+               head_dim, WIDE_MAX_N, N);
   VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, VITK_ERR_ALIGN, "attn_fwd: unaligned");
   const int hd = head_dim;
   CUtensorMap tm, tm_out;
@@ -2427,6 +2518,8 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   if (rc) return rc;
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
+  if (hd > HD)   // my_vit_xs (head_dim 72): the tiled kernel with [tile][tail] operands
+    return T == 1 ? launch_fwd<1, true>(tm, out, lse, B, N, H, hd, scale, s) : launch_fwd<2, true>(tm, out, lse, B, N, H, hd, scale, s);
   // VITK_ATTN_FWD: unset = attn_fwd4 (whole score row in TMEM, one thread per row) for 128 < N <= 256, attn_fwd6 (kv loop,
   // score MMA off the softmax's critical path) above that, the tiled one-CTA-per-q-tile kernel for N <= 128;
   // "1" = tiled kernel everywhere; "5" / "6" = attn_fwd5 (the previous kv-loop kernel) / attn_fwd6 for every N > 128
@@ -2457,10 +2550,11 @@ static int64_t dsum_bytes(int32_t B, int32_t N, int32_t H) {
 }
 
 extern "C" int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim) {
-  // D = rowsum(O * dO) [B, H, N] fp32, plus (N > 256) the fp32 dQ accumulator [B, N, H, 64] (heads padded to the tile width)
-  (void)head_dim;
+  // D = rowsum(O * dO) [B, H, N] fp32, plus (N > 256, or head_dim > 64) the fp32 dQ accumulator [B, N, H, 64 | 80] (heads padded
+  // to the tile width)
   int64_t bytes = dsum_bytes(B, N, H);
-  if (N > BWD_MAX_T * TILE) bytes += (int64_t)B * N * H * HD * (int64_t)sizeof(float);
+  if (head_dim > HD) bytes += (int64_t)B * N * H * HDW_MAX * (int64_t)sizeof(float);   // wide heads: streaming kernel for every N
+  else if (N > BWD_MAX_T * TILE) bytes += (int64_t)B * N * H * HD * (int64_t)sizeof(float);
   return bytes;
 }
 
@@ -2468,8 +2562,10 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
                              void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
                              void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
-  VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (built for multiples of 8 in [16, 64])", head_dim);
+  VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (built for multiples of 8 in [16, 80])", head_dim);
   VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_bwd: N=%d > %d", N, FWD_MAX_T * TILE);
+  VITK_REQUIRE(head_dim <= HD || N <= WIDE_MAX_N, VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d > 64 is built for N <= %d (N=%d)",
+               head_dim, WIDE_MAX_N, N);
   VITK_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)dout & 15) == 0 && ((uintptr_t)dqkv & 15) == 0,
                VITK_ERR_ALIGN, "attn_bwd: unaligned");
   const int hd = head_dim;
@@ -2484,7 +2580,9 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Bwd3Smem::BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem::BYTES);
+      e = cudaFuncSetAttribute(attn_bwd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem<false>::BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BwdStreamSmem<true>::BYTES);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -2500,19 +2598,24 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     rc = vitk_check_launch("attn_dsum");
     if (rc) return rc;
   }
-  if (N > BWD_MAX_T * TILE) {
+  if (N > BWD_MAX_T * TILE || hd > HD) {
     // one CTA per (b, h, kv tile): dQ partials are red.add'ed into the fp32 workspace (156 of the ~820 us per layer at
     // ViT-L/384, B = 64, H = 16, N = 577; ~90 us are the memset / cast / D kernels around it)
     const long long rows = (long long)B * N;
-    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * H * HD * sizeof(float), st);
+    const int pitch = hd > HD ? HDW_MAX : HD;
+    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows * H * pitch * sizeof(float), st);
     if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_bwd: memset: %s", cudaGetErrorString(e));
     dim3 grid((N + TILE - 1) / TILE, H, B);
-    attn_bwd_stream_kernel<<<grid, 128, BwdStreamSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32, N, H, hd,
-                                                                    scale);
+    if (hd > HD)
+      attn_bwd_stream_kernel<true><<<grid, 128, BwdStreamSmem<true>::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32,
+                                                                                  N, H, hd, scale);
+    else
+      attn_bwd_stream_kernel<false><<<grid, 128, BwdStreamSmem<false>::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv,
+                                                                                    dq32, N, H, hd, scale);
     rc = vitk_check_launch("attn_bwd_stream");
     if (rc) return rc;
     const long long n8 = rows * H * (hd / 8);
-    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, H, hd);
+    dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dqkv, rows, H, hd, pitch);
     return vitk_check_launch("attn_bwd_dq_cast");
   }
   // VITK_ATTN_BWD: unset = warp-specialised persistent kernel for 128 < N <= 256, single-warpgroup kernel for N <= 128;

@@ -152,6 +152,15 @@ __device__ __forceinline__ void tma_load_head(void* smem_dst, const CUtensorMap*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// the same box at inner (head_dim) coordinate c0: the columns 64 .. of a head wider than one 64-column tile
+__device__ __forceinline__ void tma_load_head_col(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                  int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
                                             int32_t c0, int32_t c1, int32_t c2, int32_t c3,
                                             int32_t c4) {

@@ -22,7 +22,7 @@ def my_vit_ti(pretrained: bool = False, **kwargs) -> VisionTransformer:
 
 @register_model
 def my_vit_xs(pretrained: bool = False, **kwargs) -> VisionTransformer:
-    """ViT-XS/16 — ~11 M params (head_dim 72 > 64: wider than the attention kernels' head tile -> raises)."""
+    """ViT-XS/16 — ~11 M params (head_dim 72: every attention operand takes a second, zero-padded tile; N <= 256)."""
     model_args = dict(patch_size=16, embed_dim=288, depth=12, num_heads=4)
     return _create_vision_transformer("my_vit_xs", pretrained=pretrained, **dict(model_args, **kwargs))
 

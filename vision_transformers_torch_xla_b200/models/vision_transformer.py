@@ -133,9 +133,10 @@ class Attention(nn.Module):
             raise NotImplementedError("Attention: attn_drop / proj_drop > 0 are not built (all reference configs use 0)")
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
-        if self.head_dim % 8 != 0 or not 16 <= self.head_dim <= 64:
+        if self.head_dim % 8 != 0 or not 16 <= self.head_dim <= 80:
             raise NotImplementedError(f"Attention: head_dim={self.head_dim}; the sm_100a attention kernels run on 64-wide head "
-                                      "tiles (head_dim a multiple of 8 in [16, 64]; narrower heads are zero-padded by TMA)")
+                                      "tiles (head_dim a multiple of 8 in [16, 80]: narrower heads are zero-padded by TMA, heads "
+                                      "of 72 / 80 take a second tile and sequences of at most 256 tokens)")
         self.scale = self.head_dim ** -0.5
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.q_norm = nn.Identity()
