@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 2
+#define VITK_ABI_VERSION 3
 
 enum vitk_status {
   VITK_STATUS_OK = 0,
@@ -100,6 +100,14 @@ typedef struct vitk_gemm_args {
    * b_image: B is such an image in MN-major use (the weight gradient dW[D, K'] += gp^T patches), K = rows as above. */
   int32_t a_image, b_image;
   int32_t img_c, img_h, img_w, img_patch, img_gwp;
+  /* Dropout in the epilogue (timm Attention.proj_drop, Mlp.drop1 / drop2; vision_transformer.py:149-171): keep-mask bytes
+   * [M, N] (1 = keep, 0 = drop; written by vitk_dropout_mask or by the caller), row pitch ld_mask (multiple of 4), or NULL.
+   *   VITK_EPI_GELU : out = gelu(h) * m * mask_scale, aux = gelu'(h) * m * mask_scale (the backward multiply is unchanged)
+   *   VITK_EPI_RESID: out = resid + rowscale * colscale * m * mask_scale * (acc + bias)
+   * mask_scale = 1 / (1 - p). */
+  const uint8_t* mask;
+  int64_t ld_mask;
+  float mask_scale;
 } vitk_gemm_args;
 
 int vitk_gemm_bf16(const vitk_gemm_args* args, void* stream);
@@ -187,6 +195,18 @@ int vitk_ce_fwd_bwd(const float* logits, const float* soft_targets, const int64_
                     void* stream);
 /* x[i] *= scale_dev[0] in place (the upstream gradient of the loss applied to dlogits, no host sync) */
 int vitk_scale_f32(float* x, const float* scale_dev, int64_t n, void* stream);
+
+/* Dropout (nn.Dropout sites of the reference model: pos_drop, proj_drop, Mlp.drop1/2, head_drop).
+ * vitk_dropout_mask: mask[i] = 1 with probability 1 - p, else 0 (Philox4x32-10 keyed by seed, counter = (i / 8, offset), 16 bits per element;
+ *   n bytes, any n).  The masks feed the GEMM epilogues above and the two multiplies below (the backward of a site, and the
+ *   sites that have no GEMM in front of them).
+ * vitk_mask_mul_bf16 / _f32: x[r, c] *= mask[r, c] ? scale : 0 in place; x: [rows, cols] with row pitch ld_x, mask: [rows, cols]
+ *   with row pitch ld_mask; cols a multiple of 4 (f32) / 8 (bf16). */
+int vitk_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int vitk_mask_mul_bf16(void* x, int64_t ld_x, const uint8_t* mask, int64_t ld_mask, int64_t rows, int32_t cols, float scale,
+                       void* stream);
+int vitk_mask_mul_f32(float* x, int64_t ld_x, const uint8_t* mask, int64_t ld_mask, int64_t rows, int32_t cols, float scale,
+                      void* stream);
 /* out_bf16[i] = in_f32[i] * scale_dev[0] */
 int vitk_scale_cast_bf16(const float* in, const float* scale_dev, void* out_bf16, int64_t n,
                          void* stream);

@@ -28,9 +28,10 @@ EXPORTED_SYMBOLS = (
     "vitk_scale_cast_bf16", "vitk_rowscale_cast_bf16", "vitk_cast_bf16", "vitk_adamw_flat", "vitk_sumsq",
     "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target", "vitk_colscale_bf16", "vitk_layerscale_grad",
     "vitk_build_id", "vitk_droppath_masks", "vitk_scale_f32", "vitk_clip_coef", "vitk_sumsq_bf16", "vitk_sumsq_scratch_floats",
+    "vitk_dropout_mask", "vitk_mask_mul_bf16", "vitk_mask_mul_f32",
 )
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 #: the files whose sha256 csrc/Makefile bakes into the library (same list, same order)
 _BUILD_SOURCES = ("csrc/vitk_host.cu", "csrc/vitk_gemm.cu", "csrc/vitk_attn.cu", "csrc/vitk_norm.cu",
                   "csrc/vitk_elementwise.cu", "csrc/vitk_common.cuh", "csrc/vitk_internal.h", "../include/vitk.h")
@@ -62,6 +63,7 @@ class GemmArgs(Structure):
         ("splits", c_int32), ("block_n", c_int32), ("colsum_out", c_void_p),
         ("a_image", c_int32), ("b_image", c_int32),
         ("img_c", c_int32), ("img_h", c_int32), ("img_w", c_int32), ("img_patch", c_int32), ("img_gwp", c_int32),
+        ("mask", c_void_p), ("ld_mask", c_int64), ("mask_scale", c_float),
     ]
 
 
@@ -132,6 +134,9 @@ def load() -> ctypes.CDLL:
     lib.vitk_sumsq.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.vitk_sumsq_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.vitk_sumsq_scratch_floats.restype = c_int32
+    lib.vitk_dropout_mask.argtypes = [c_void_p, c_int64, c_float, c_uint64, c_uint64, c_void_p]
+    lib.vitk_mask_mul_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_float, c_void_p]
+    lib.vitk_mask_mul_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_float, c_void_p]
     lib.vitk_mixup_batch.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_double, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_void_p]
     lib.vitk_colscale_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p]
@@ -254,8 +259,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          rowscale: Optional[torch.Tensor] = None, rows_per_group: int = 1,
          colscale: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
          tokens_per_img: int = 0, prefix: int = 0, splits: int = 0, block_n: int = 0,
-         colsum: Optional[torch.Tensor] = None, image: Optional[tuple] = None) -> None:
+         colsum: Optional[torch.Tensor] = None, image: Optional[tuple] = None,
+         mask: Optional[torch.Tensor] = None, mask_scale: float = 1.0) -> None:
     """D[M,N] = opA(a) @ opB(b)^T with a fused epilogue; see ``enum vitk_epilogue`` in include/vitk.h.
+
+    ``mask`` (uint8 [M, N], 1 = keep) with ``mask_scale = 1 / (1 - p)`` is a dropout applied inside the GELU / RESID epilogues.
 
     ``image = (which, C, H, W, patch, gwp)`` makes operand ``which`` ('a' or 'b') a bf16 NCHW image batch read through TMA
     as its patch matrix (im2col-free; ``struct vitk_gemm_args``: a_image / b_image)."""
@@ -272,6 +280,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     args.bias = _ptr(bias)
     args.resid, args.ld_resid = _ptr(resid), N
     args.rowscale, args.rows_per_group = _ptr(rowscale), rows_per_group
+    if mask is not None:
+        _req(mask, torch.uint8, "gemm mask")
+        if mask.numel() != M * N:
+            raise VitkError(f"gemm mask: expected {M} x {N} keep bytes, got {tuple(mask.shape)}")
+        args.mask, args.ld_mask, args.mask_scale = mask.data_ptr(), N, float(mask_scale)
     args.colscale = _ptr(colscale)
     args.pos, args.tokens_per_img, args.prefix = _ptr(pos), tokens_per_img, prefix
     args.splits, args.block_n = splits, block_n
@@ -400,6 +413,33 @@ def droppath_masks(rs: torch.Tensor, drop_probs, seed: int, offset: int) -> None
     with _Timed("droppath_masks"):
         _check(load().vitk_droppath_masks(rs.data_ptr(), arr, rows, B, seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
                                           _stream()), "vitk_droppath_masks")
+    _count()
+
+
+def dropout_mask(mask: torch.Tensor, p: float, seed: int, offset: int) -> None:
+    """mask uint8 (any shape, contiguous) <- 1 with probability 1 - p, else 0."""
+    _req(mask, torch.uint8, "dropout_mask mask")
+    with _Timed("dropout_mask"):
+        _check(load().vitk_dropout_mask(mask.data_ptr(), mask.numel(), float(p), seed & 0xFFFFFFFFFFFFFFFF,
+                                        offset & 0xFFFFFFFFFFFFFFFF, _stream()), "vitk_dropout_mask")
+    _count()
+
+
+def mask_mul_(x: torch.Tensor, mask: torch.Tensor, scale: float, rows: int, cols: int, ld_x: Optional[int] = None) -> None:
+    """x[r, c] *= mask[r, c] ? scale : 0 in place (x bf16 or fp32, viewed as [rows, cols] with row pitch ``ld_x``)."""
+    _req(mask, torch.uint8, "mask_mul mask")
+    if mask.numel() != rows * cols:
+        raise VitkError(f"mask_mul: expected {rows} x {cols} keep bytes, got {tuple(mask.shape)}")
+    ld = cols if ld_x is None else ld_x
+    with _Timed("mask_mul"):
+        if x.dtype == torch.bfloat16:
+            _req(x, torch.bfloat16, "mask_mul x")
+            _check(load().vitk_mask_mul_bf16(x.data_ptr(), ld, mask.data_ptr(), cols, rows, cols, float(scale), _stream()),
+                   "vitk_mask_mul_bf16")
+        else:
+            _req(x, torch.float32, "mask_mul x")
+            _check(load().vitk_mask_mul_f32(x.data_ptr(), ld, mask.data_ptr(), cols, rows, cols, float(scale), _stream()),
+                   "vitk_mask_mul_f32")
     _count()
 
 

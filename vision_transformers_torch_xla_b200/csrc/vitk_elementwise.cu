@@ -786,6 +786,87 @@ extern "C" int vitk_scale_f32(float* x, const float* scale_dev, int64_t n, void*
   return vitk_check_launch("scale_f32");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dropout masks and the in-place multiplies that go with them (see include/vitk.h)
+// ------------------------------------------------------------------------------------------------
+// one Philox call -> 4 x 32 random bits -> 8 keep bytes (16 random bits per element: p is honoured to 2^-16)
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, uint32_t thresh, unsigned long long seed,
+                                    unsigned long long offset) {
+  const long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i8 * 8 >= n) return;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)i8, (uint32_t)(i8 >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t o[2] = {0u, 0u};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[k >> 1] |= ((w[k] & 0xffffu) >= thresh ? 1u : 0u) << (16 * (k & 1));
+    o[k >> 1] |= ((w[k] >> 16) >= thresh ? 1u : 0u) << (16 * (k & 1) + 8);
+  }
+  if (i8 * 8 + 8 <= n) {
+    *reinterpret_cast<uint2*>(mask + i8 * 8) = make_uint2(o[0], o[1]);
+  } else {
+    for (long long j = i8 * 8; j < n; ++j) mask[j] = (uint8_t)((o[(j & 7) >> 2] >> (8 * (j & 3))) & 0xffu);
+  }
+}
+
+template <typename T, int V>   // V elements per thread: 8 bf16 (16 B) or 4 fp32 (16 B)
+__global__ void mask_mul_kernel(T* __restrict__ x, long long ld_x, const uint8_t* __restrict__ mask, long long ld_mask,
+                                long long rows, int cols, float scale) {
+  const int per_row = cols / V;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * per_row) return;
+  const long long r = idx / per_row;
+  const int c = (int)(idx - r * per_row) * V;
+  const uint8_t* mp = mask + r * ld_mask + c;
+  float m[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) m[j] = mp[j] ? scale : 0.f;
+  if constexpr (V == 8) {
+    uint4* px = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(x) + r * ld_x + c);
+    uint4 u = *px;
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c2 = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    u.x = pack_bf16x2(a.x * m[0], a.y * m[1]);
+    u.y = pack_bf16x2(b.x * m[2], b.y * m[3]);
+    u.z = pack_bf16x2(c2.x * m[4], c2.y * m[5]);
+    u.w = pack_bf16x2(d.x * m[6], d.y * m[7]);
+    *px = u;
+  } else {
+    float4* px = reinterpret_cast<float4*>(reinterpret_cast<float*>(x) + r * ld_x + c);
+    float4 u = *px;
+    *px = make_float4(u.x * m[0], u.y * m[1], u.z * m[2], u.w * m[3]);
+  }
+}
+
+extern "C" int vitk_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  VITK_REQUIRE(mask != nullptr && n >= 0 && ((uintptr_t)mask & 15) == 0, VITK_ERR_ALIGN, "dropout_mask: 16-byte aligned mask required");
+  VITK_REQUIRE(p >= 0.f && p < 1.f, VITK_ERR_SHAPE, "dropout_mask: p=%f not in [0, 1)", p);
+  if (n == 0) return VITK_OK;
+  const uint32_t thresh = (uint32_t)(p * 65536.f + 0.5f);   // keep iff a 16-bit uniform >= thresh
+  dropout_mask_kernel<<<blocks_for((n + 7) / 8, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, thresh, seed, offset);
+  return vitk_check_launch("dropout_mask");
+}
+
+extern "C" int vitk_mask_mul_bf16(void* x, int64_t ld_x, const uint8_t* mask, int64_t ld_mask, int64_t rows, int32_t cols,
+                                  float scale, void* stream) {
+  VITK_REQUIRE(x && mask && rows >= 0 && cols > 0 && cols % 8 == 0 && ld_x % 8 == 0 && ((uintptr_t)x & 15) == 0, VITK_ERR_ALIGN,
+               "mask_mul_bf16: cols and ld_x must be multiples of 8, x 16-byte aligned");
+  if (rows == 0) return VITK_OK;
+  mask_mul_kernel<__nv_bfloat16, 8><<<blocks_for(rows * (cols / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(x), ld_x, mask, ld_mask, rows, cols, scale);
+  return vitk_check_launch("mask_mul_bf16");
+}
+
+extern "C" int vitk_mask_mul_f32(float* x, int64_t ld_x, const uint8_t* mask, int64_t ld_mask, int64_t rows, int32_t cols,
+                                 float scale, void* stream) {
+  VITK_REQUIRE(x && mask && rows >= 0 && cols > 0 && cols % 4 == 0 && ld_x % 4 == 0 && ((uintptr_t)x & 15) == 0, VITK_ERR_ALIGN,
+               "mask_mul_f32: cols and ld_x must be multiples of 4, x 16-byte aligned");
+  if (rows == 0) return VITK_OK;
+  mask_mul_kernel<float, 4><<<blocks_for(rows * (cols / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, ld_x, mask, ld_mask, rows, cols,
+                                                                                                 scale);
+  return vitk_check_launch("mask_mul_f32");
+}
+
 extern "C" int vitk_droppath_masks(float* rs, const float* drop_probs, int32_t rows, int32_t B, uint64_t seed, uint64_t offset,
                                    void* stream) {
   VITK_REQUIRE(rs && drop_probs && rows > 0 && rows <= DROPPATH_MAX_ROWS && B > 0, VITK_ERR_SHAPE,

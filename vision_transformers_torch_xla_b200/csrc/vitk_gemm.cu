@@ -56,6 +56,10 @@ struct GemmParams {
   // im2col-free patch view of a bf16 NCHW image (see include/vitk.h): which operand, and its geometry
   int a_image, b_image;
   int img_c, img_gh, img_gw, img_gwp, img_ps;
+  // dropout keep-mask bytes [M, N] for the GELU / RESID epilogues (staged-panel variants), or null
+  const uint8_t* mask;
+  long long ld_mask;
+  float mask_scale;
 };
 
 // One [8 patch rows][64 columns] piece of the patch matrix of an NCHW image (patch 16) = one TMA box (px, gx, y, bc) =
@@ -373,6 +377,18 @@ __device__ __forceinline__ void row_put_f32(uint8_t* stg, int r, const float* v)
     *reinterpret_cast<float4*>(stg + stg_f32(r, u)) = make_float4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
 }
 
+// Dropout in the epilogue: this thread's 32 keep bytes (row `row`, columns col0 .. col0 + 31) -> v[j] *= keep ? scale : 0.
+// Rows >= M and columns >= N are never stored, so they read as "drop" instead of touching memory.
+__device__ __forceinline__ void load_keep_mask(const GemmParams& p, int row, int col0, uint32_t (&w)[8]) {
+  const uint32_t* mp = reinterpret_cast<const uint32_t*>(p.mask + (long long)row * p.ld_mask + col0);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) w[u] = (row < p.M && col0 + u * 4 < p.N) ? __ldg(mp + u) : 0u;
+}
+__device__ __forceinline__ void apply_keep_mask(const uint32_t (&w)[8], float scale, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = ((w[j >> 2] >> ((j & 3) * 8)) & 0xffu) ? v[j] * scale : 0.f;
+}
+
 // `acc`: this thread's row (lane) of the panel, 32 fp32 accumulators.  row0 = first row of the warp's 32 rows.
 template <int EPI>
 __device__ __forceinline__ void epilogue_panel(const GemmParams& p, uint32_t (&acc)[32], uint8_t* stg, int lane,
@@ -403,6 +419,12 @@ __device__ __forceinline__ void epilogue_panel(const GemmParams& p, uint32_t (&a
     float gd[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) gelu_fwd_bwd(v[j], v[j], gd[j]);
+    if (p.mask != nullptr) {   // Mlp.drop1: the mask rides in the saved derivative too, the backward multiply stays as it is
+      uint32_t w[8];
+      load_keep_mask(p, row0 + lane, col0, w);
+      apply_keep_mask(w, p.mask_scale, v);
+      apply_keep_mask(w, p.mask_scale, gd);
+    }
     row_put_b16(stg, lane, v);
     __syncwarp();
     panel_io_b16<false>(stg, reinterpret_cast<__nv_bfloat16*>(p.out), p.ld_out, row0, col0, p.M, p.N, lane);
@@ -438,6 +460,11 @@ __device__ __forceinline__ void epilogue_panel(const GemmParams& p, uint32_t (&a
     __syncwarp();
   } else if constexpr (EPI == EPI_RESID) {
     // the residual panel was loaded (coalesced) into the staging buffer by the caller before the TMEM wait
+    if (p.mask != nullptr) {   // proj_drop / Mlp.drop2: on the branch (acc + bias), before LayerScale, DropPath and the residual
+      uint32_t w[8];
+      load_keep_mask(p, row0 + lane, col0, w);
+      apply_keep_mask(w, p.mask_scale, v);
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       float4 cs = make_float4(rs, rs, rs, rs);
@@ -1250,6 +1277,7 @@ int launch_gemm(const vitk_gemm_args* a, cudaStream_t stream) {
   p.prefix = a->prefix;
   p.ragged = (EPI == EPI_F32 && (a->N % 8 != 0 || a->ld_out % 4 != 0)) ? 1 : 0;
   p.colsum_out = (EPI == EPI_ATOMIC && A_MN) ? a->colsum_out : nullptr;
+  p.mask = a->mask; p.ld_mask = a->ld_mask; p.mask_scale = a->mask_scale;
   p.a_image = (a->a_image && !A_MN) ? 1 : 0;
   p.b_image = (a->b_image && B_MN) ? 1 : 0;
   p.img_c = a->img_c; p.img_ps = a->img_patch > 0 ? a->img_patch : 16; p.img_gwp = a->img_gwp > 0 ? a->img_gwp : 16;
@@ -1309,7 +1337,8 @@ int dispatch2(const vitk_gemm_args* a, cudaStream_t stream) {
         break;
       case EPI_RESID:
         if constexpr (CTA2 || BLOCK_N < 256) {
-          if (a->K <= kResidTmaMaxK && resid_tma_ok(a)) return launch_gemm<BLOCK_N, false, false, EPI_RESID_TMA, CTA2>(a, stream);
+          if (a->K <= kResidTmaMaxK && resid_tma_ok(a) && a->mask == nullptr)   // the dropout mask lives in the staged-panel epilogue
+            return launch_gemm<BLOCK_N, false, false, EPI_RESID_TMA, CTA2>(a, stream);
         }
         return launch_gemm<BLOCK_N, false, false, EPI_RESID, CTA2>(a, stream);
       case EPI_F32:   return launch_gemm<BLOCK_N, false, false, EPI_F32, CTA2>(a, stream);
@@ -1395,6 +1424,13 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream_) {
                    "gemm: b_image needs MN-major B, N = C * patch^2 and K a multiple of img_gwp");
   }
 
+  if (a->mask != nullptr) {
+    VITK_REQUIRE(a->epilogue == EPI_GELU || a->epilogue == EPI_RESID, VITK_ERR_UNSUPPORTED,
+                 "gemm: a dropout mask goes with the GELU and RESID epilogues (epilogue=%d)", a->epilogue);
+    VITK_REQUIRE(a->ld_mask % 4 == 0 && a->ld_mask >= a->N && (reinterpret_cast<uintptr_t>(a->mask) & 3) == 0, VITK_ERR_ALIGN,
+                 "gemm: mask must be 4-byte aligned with ld_mask a multiple of 4 and >= N");
+    VITK_REQUIRE(a->mask_scale > 0.f, VITK_ERR_SHAPE, "gemm: mask_scale = 1 / (1 - p) must be positive");
+  }
   int bn = a->block_n;
   if (bn == 0) {
     // 256-wide pair tiles are the most efficient ones, even with a partly empty last column of tiles, as long as that
@@ -1406,6 +1442,8 @@ extern "C" int vitk_gemm_bf16(const vitk_gemm_args* a, void* stream_) {
     else if (a->N % 128 == 0) bn = 128;
     else bn = (a->N > 192) ? 256 : (a->N > 128 ? 192 : 128);
   }
+  // GELU with a dropout mask: 256-wide tiles take the TMA-staged GELU epilogue, which has no mask path
+  if (a->mask != nullptr && a->epilogue == EPI_GELU && bn == 256) bn = 192;
   switch (bn) {
     case 256: return dispatch<256>(a, stream);
     case 192: return dispatch<192>(a, stream);

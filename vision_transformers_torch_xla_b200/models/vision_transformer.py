@@ -118,7 +118,7 @@ class PatchEmbed(nn.Module):
 
 
 class Attention(nn.Module):
-    """timm Attention: qkv Linear -> SDPA -> proj Linear (qk_norm / dropout / masks not built)."""
+    """timm Attention: qkv Linear -> SDPA -> proj Linear -> proj_drop (qk_norm / attn_drop / masks not built)."""
 
     fused_attn = True
 
@@ -129,8 +129,9 @@ class Attention(nn.Module):
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
         if qk_norm or scale_norm:
             raise NotImplementedError("Attention: qk_norm / scale_norm are not built")
-        if attn_drop != 0.0 or proj_drop != 0.0:
-            raise NotImplementedError("Attention: attn_drop / proj_drop > 0 are not built (all reference configs use 0)")
+        if attn_drop != 0.0:
+            raise NotImplementedError("Attention: attn_drop > 0 (dropout on the softmax inside the fused attention kernel) is not "
+                                      "built; every reference config uses 0")
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         if self.head_dim % 8 != 0 or not 16 <= self.head_dim <= 80:
@@ -152,7 +153,10 @@ class Attention(nn.Module):
         st = store_for(self)
         st.sync_shadow()
         st.attach_grads()
-        return ops.AttentionFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
+        x = ops.AttentionFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
+        if self.training and self.proj_drop.p > 0.0:   # stand-alone use; inside a Block the mask rides in the proj epilogue
+            x = ops.DropoutFn.apply(x, st, "attn.proj_drop", self.proj_drop.p)
+        return x
 
 
 class Mlp(nn.Module):
@@ -163,22 +167,25 @@ class Mlp(nn.Module):
         super().__init__()
         if act_layer is not nn.GELU or norm_layer is not None or use_conv:
             raise NotImplementedError("Mlp: only act_layer=nn.GELU without norm/conv is built")
-        if (drop if isinstance(drop, (int, float)) else max(drop)) != 0.0:
-            raise NotImplementedError("Mlp: drop > 0 is not built (all reference configs use 0)")
+        drop_probs = (drop, drop) if isinstance(drop, (int, float)) else tuple(drop)
         out_features = out_features or in_features
         hidden_features = hidden_features or in_features
         self.fc1 = nn.Linear(in_features, hidden_features, bias=bias)
         self.act = nn.GELU()
-        self.drop1 = nn.Dropout(0.0)
+        self.drop1 = nn.Dropout(drop_probs[0])
         self.norm = nn.Identity()
         self.fc2 = nn.Linear(hidden_features, out_features, bias=bias)
-        self.drop2 = nn.Dropout(0.0)
+        self.drop2 = nn.Dropout(drop_probs[1])
 
     def forward(self, x):
         st = store_for(self)
         st.sync_shadow()
         st.attach_grads()
-        return ops.MlpFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
+        # stand-alone use (inside a Block both masks ride in the GEMM epilogues): drop1 in the fc1 GELU epilogue, drop2 after
+        x = ops.MlpFn.apply(x, st.anchor, self, st, torch.is_grad_enabled(), self.drop1.p if self.training else 0.0)
+        if self.training and self.drop2.p > 0.0:
+            x = ops.DropoutFn.apply(x, st, "mlp.drop2", self.drop2.p)
+        return x
 
 
 # --------------------------------------------------------------------------------------------------
@@ -234,7 +241,19 @@ class Block(nn.Module):
             rs1 = own[0] if own is not None and dp1 > 0.0 else None
             rs2 = own[1] if own is not None and dp2 > 0.0 else None
         prev_rs = st.__dict__.get("_last_rs")
-        out = ops.BlockFn.apply(x, st.anchor, self, st, rs1, rs2, prev_rs, torch.is_grad_enabled(), self._vitk_tag)
+        # nn.Dropout sites of the block (timm Attention.proj_drop, Mlp.drop1 / drop2; one rate: Block(proj_drop=...)): three keep
+        # masks per pass, applied inside the proj / fc1 / fc2 GEMM epilogues
+        drop = None
+        pd = self.attn.proj_drop.p
+        if self.training and pd > 0.0:
+            if self.mlp.drop1.p != pd or self.mlp.drop2.p != pd:
+                raise NotImplementedError("Block: Attention.proj_drop and Mlp.drop must share one rate (Block(proj_drop=...))")
+            M, D, F = x.shape[0] * x.shape[1], x.shape[2], self.mlp.fc1.out_features
+            site = f"blocks.{self._vitk_index}."
+            drop = (ops.dropout_keep_mask(site + "attn.proj_drop", M, D, pd, x.device),
+                    ops.dropout_keep_mask(site + "mlp.drop1", M, F, pd, x.device),
+                    ops.dropout_keep_mask(site + "mlp.drop2", M, D, pd, x.device), 1.0 / (1.0 - pd))
+        out = ops.BlockFn.apply(x, st.anchor, self, st, rs1, rs2, prev_rs, torch.is_grad_enabled(), self._vitk_tag, drop)
         st.__dict__["_last_rs"] = rs2
         return out
 
@@ -287,8 +306,7 @@ class VisionTransformer(nn.Module):
         unsupported = dict(qk_norm=qk_norm, scale_attn_norm=scale_attn_norm, scale_mlp_norm=scale_mlp_norm,
                            no_embed_class=no_embed_class, reg_tokens=reg_tokens, pre_norm=pre_norm,
                            pool_include_prefix=pool_include_prefix, dynamic_img_size=dynamic_img_size,
-                           dynamic_img_pad=dynamic_img_pad, drop_rate=drop_rate, pos_drop_rate=pos_drop_rate,
-                           patch_drop_rate=patch_drop_rate, proj_drop_rate=proj_drop_rate,
+                           dynamic_img_pad=dynamic_img_pad, patch_drop_rate=patch_drop_rate,
                            attn_drop_rate=attn_drop_rate, fix_init=fix_init, embed_norm_layer=embed_norm_layer)
         bad = {k: v for k, v in unsupported.items() if v}
         if bad:
@@ -325,15 +343,15 @@ class VisionTransformer(nn.Module):
         self.reg_token = None
         embed_len = num_patches + self.num_prefix_tokens
         self.pos_embed = nn.Parameter(torch.randn(1, embed_len, embed_dim) * 0.02)
-        self.pos_drop = nn.Dropout(p=0.0)
+        self.pos_drop = nn.Dropout(p=pos_drop_rate)
         self.patch_drop = nn.Identity()
         self.norm_pre = nn.Identity()
 
         dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth, device="cpu")]  # stochastic depth decay rule
         self.blocks = nn.Sequential(*[
             block_fn(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, proj_bias=proj_bias,
-                     init_values=init_values, drop_path=dpr[i], norm_layer=norm_layer, act_layer=act_layer,
-                     mlp_layer=mlp_layer)
+                     init_values=init_values, proj_drop=proj_drop_rate, drop_path=dpr[i], norm_layer=norm_layer,
+                     act_layer=act_layer, mlp_layer=mlp_layer)
             for i in range(depth)])
         for i, blk in enumerate(self.blocks):
             blk._vitk_tag = f"blocks.{i}."
@@ -342,7 +360,7 @@ class VisionTransformer(nn.Module):
         self.norm = norm_layer(embed_dim) if final_norm and not use_fc_norm else nn.Identity()
         self.attn_pool = None
         self.fc_norm = norm_layer(embed_dim) if final_norm and use_fc_norm else nn.Identity()
-        self.head_drop = nn.Dropout(0.0)
+        self.head_drop = nn.Dropout(drop_rate)
         self.head = nn.Linear(self.embed_dim, num_classes) if num_classes > 0 else nn.Identity()
         if weight_init != "skip":
             self.init_weights(weight_init)
@@ -404,6 +422,8 @@ class VisionTransformer(nn.Module):
             x = x.float()
         x = x if x.is_contiguous() else x.contiguous()
         x = ops.EmbedFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
+        if self.training and self.pos_drop.p > 0.0:   # _pos_embed ends in pos_drop (vision_transformer.py:780, deit.py:106)
+            x = ops.DropoutFn.apply(x, st, "pos_drop", self.pos_drop.p)
         st.__dict__["_in_root"] = self
         # every DropPath mask of this pass in one launch, in the reference's draw order (Block.forward :175-178)
         st.__dict__["_dp_masks"] = (ops.drop_path_masks([p for blk in self.blocks for p in blk._drop_probs()],
@@ -440,7 +460,8 @@ class VisionTransformer(nn.Module):
         with use_store(st):
             x = self.pool(x).contiguous()
             x = self.fc_norm(x)
-            x = self.head_drop(x)
+            if self.training and self.head_drop.p > 0.0:
+                x = ops.DropoutFn.apply(x.contiguous(), st, "head_drop", self.head_drop.p)
             return x if pre_logits else self._linear(self.head, x, st)
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -451,7 +472,8 @@ class VisionTransformer(nn.Module):
         st = self._begin()
         with use_store(st):
             x = self._features(x, st)
-            return ops.HeadFn.apply(x, st.anchor, self, st, st.__dict__.get("_last_rs"), torch.is_grad_enabled())
+            return ops.HeadFn.apply(x, st.anchor, self, st, st.__dict__.get("_last_rs"), torch.is_grad_enabled(),
+                                    self.head_drop.p if self.training else 0.0)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -158,9 +158,60 @@ class EmbedFn(torch.autograd.Function):
 # ================================================================================================
 # Transformer block
 # ================================================================================================
+#: test hook: callable(site, rows, cols, p, device) -> uint8 [rows, cols] keep mask (1 = keep), used INSTEAD of the Philox
+#: kernel (the parity tests replay masks against the oracle; tests/test_gpu_dropout.py)
+dropout_source = None
+_drop_calls = 0
+
+
+def dropout_keep_mask(site: str, rows: int, cols: int, p: float, device) -> Optional[torch.Tensor]:
+    """Keep mask of one nn.Dropout site (timm: pos_drop, Attention.proj_drop, Mlp.drop1 / drop2, head_drop) for one forward
+    pass, or None when p == 0.  Seeded like the DropPath masks: torch's CUDA seed plus a per-process call counter."""
+    global _drop_calls
+    if p <= 0.0:
+        return None
+    if not 0.0 < p < 1.0:
+        raise ValueError(f"dropout probability {p} not in [0, 1)")
+    if dropout_source is not None:
+        m = dropout_source(site, rows, cols, p, device)
+        assert m.shape == (rows, cols) and m.dtype == torch.uint8 and m.is_cuda, (site, m.shape, m.dtype)
+        return m.contiguous()
+    m = _empty((rows, cols), torch.uint8, device)
+    _drop_calls += 1
+    L.dropout_mask(m, p, torch.cuda.initial_seed() ^ 0x5DEECE66D, _drop_calls)
+    return m
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout on an fp32 activation that has no GEMM epilogue in front of it (pos_drop; the stand-alone leaf modules)."""
+
+    @staticmethod
+    def forward(ctx, x, store, site: str, p: float):
+        x = _require_f32_cuda(x, "Dropout input")
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        mask = dropout_keep_mask(site, rows, cols, p, x.device)
+        y = x.clone()
+        L.mask_mul_(y, mask, 1.0 / (1.0 - p), rows, cols)
+        ctx.mask, ctx.p, ctx.store = mask, p, store
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _require_f32_cuda(g, "Dropout grad")
+        if ctx.store is not None:
+            ctx.store.chain.pop(g.data_ptr(), None)   # a bf16 copy made by the consumer stage does not carry the mask
+        cols = g.shape[-1]
+        gx = g.clone()
+        L.mask_mul_(gx, ctx.mask, 1.0 / (1.0 - ctx.p), g.numel() // cols, cols)
+        ctx.mask = None
+        return gx, None, None, None
+
+
 class BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, blk, store: ParamStore, rs1, rs2, prev_rs, save: bool, tag: str):
+    def forward(ctx, x, anchor, blk, store: ParamStore, rs1, rs2, prev_rs, save: bool, tag: str, drop=None):
+        # drop = (keep masks of attn.proj_drop [M, D], mlp.drop1 [M, F], mlp.drop2 [M, D], 1 / (1 - p)) or None
         x = _require_f32_cuda(x, "Block input")
         B, N, D = x.shape
         M = B * N
@@ -183,23 +234,26 @@ class BlockFn(torch.autograd.Function):
         # LayerScale (vision_transformer.py:80-106): gamma rides in the residual epilogue as a per-column scale
         g1 = blk.ls1.gamma.data if hasattr(blk.ls1, "gamma") else None
         g2 = blk.ls2.gamma.data if hasattr(blk.ls2, "gamma") else None
+        md1, md2, md3, dscale = drop if drop is not None else (None, None, None, 1.0)
         x_mid = _empty((B, N, D), torch.float32, dev)
         L.gemm(att, sh(blk.attn.proj.weight), x_mid, M=M, N=D, K=D, epilogue=L.EPI_RESID, bias=bias(blk.attn.proj),
-               resid=x, rowscale=rs1, rows_per_group=N, colscale=g1)
+               resid=x, rowscale=rs1, rows_per_group=N, colscale=g1, mask=md1, mask_scale=dscale)
         ln2 = _empty((M, D), torch.bfloat16, dev)
         mean2, rstd2 = _empty((M,), torch.float32, dev), _empty((M,), torch.float32, dev)
         L.layernorm_fwd(x_mid, blk.norm2.weight.data, blk.norm2.bias.data, ln2, mean2, rstd2, M, D, eps)
-        epi_gelu, _, aux_dtype = _gelu_codes(F)
-        h = _empty((M, F), aux_dtype, dev)  # receives gelu'(fc1 out): all the backward needs of it
+        epi_gelu, _, aux_dtype = _gelu_codes(F) if md2 is None else (L.EPI_GELU, L.EPI_DGELU, torch.bfloat16)
+        h = _empty((M, F), aux_dtype, dev)  # receives gelu'(fc1 out) (x the drop1 mask): all the backward needs of it
         act = _empty((M, F), torch.bfloat16, dev)
-        L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=epi_gelu, bias=bias(blk.mlp.fc1), aux=h)
+        L.gemm(ln2, sh(blk.mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=epi_gelu, bias=bias(blk.mlp.fc1), aux=h,
+               mask=md2, mask_scale=dscale)
         x_out = _empty((B, N, D), torch.float32, dev)
         L.gemm(act, sh(blk.mlp.fc2.weight), x_out, M=M, N=D, K=F, epilogue=L.EPI_RESID, bias=bias(blk.mlp.fc2),
-               resid=x_mid, rowscale=rs2, rows_per_group=N, colscale=g2)
+               resid=x_mid, rowscale=rs2, rows_per_group=N, colscale=g2, mask=md3, mask_scale=dscale)
         if save:
             ctx.blk, ctx.store, ctx.tag = blk, store, tag
             ctx.dims = (B, N, D, H, hd, F)
             ctx.rs = (rs1, rs2, prev_rs)
+            ctx.drop = (md1, md3, dscale, md2 is not None)
             ctx.saved = (x, ln1, mean1, rstd1, qkv, att, lse, x_mid, ln2, mean2, rstd2, h, act)
         return x_out
 
@@ -232,12 +286,17 @@ class BlockFn(torch.autograd.Function):
                 L.layerscale_grad(lin.weight.data, gr(lin.weight), None if lin.bias is None else lin.bias.data,
                                   None if lin.bias is None else gr(lin.bias), ls.gamma.data, gr(ls.gamma))
 
+        md1, md3, dscale, gelu_masked = ctx.drop
         gb2 = _bf16_grad(store, g, rs2, N * D).view(M, D)
         ls_bwd_scale(gb2, blk.ls2)   # gb2 is exclusively ours (popped from the side channel or freshly made)
+        if md3 is not None:          # Mlp.drop2 sits between fc2 and LayerScale / DropPath: its mask goes on the branch gradient
+            L.mask_mul_(gb2, md3, dscale, M, D)
         wgrad(gb2, act, blk.mlp.fc2, D, F)
         ls_bwd_grad(blk.ls2, blk.mlp.fc2)
         dh = act  # reuse: gelu output is dead after the fc2 wgrad above
-        L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=_gelu_codes(F)[1], b_mn=True, aux=h)
+        # (Mlp.drop1: the saved derivative already carries mask / keep_prob, so this multiply is the same launch)
+        L.gemm(gb2, sh(blk.mlp.fc2.weight), dh, M=M, N=F, K=D, epilogue=L.EPI_DGELU if gelu_masked else _gelu_codes(F)[1],
+               b_mn=True, aux=h)
         del gb2, h
         wgrad(dh, ln2, blk.mlp.fc1, F, D)
         dln2 = ln2  # reuse: ln2 output is dead after the fc1 wgrad above
@@ -251,6 +310,8 @@ class BlockFn(torch.autograd.Function):
 
         # ---------------- attention branch: x_mid = x + rs1 * proj(attn(qkv(ln1))) ----------------
         ls_bwd_scale(gb1, blk.ls1)
+        if md1 is not None:          # Attention.proj_drop
+            L.mask_mul_(gb1, md1, dscale, M, D)
         wgrad(gb1, att, blk.attn.proj, D, D)
         ls_bwd_grad(blk.ls1, blk.attn.proj)
         datt = _empty((M, D), torch.bfloat16, dev)
@@ -268,7 +329,7 @@ class BlockFn(torch.autograd.Function):
                         gr(blk.norm1.weight), gr(blk.norm1.bias), M, D)
         store.chain[g_in.data_ptr()] = gb_prev
         store.fire_grad_ready(ctx.tag)
-        return g_in, None, None, None, None, None, None, None, None
+        return g_in, None, None, None, None, None, None, None, None, None
 
 
 # ================================================================================================
@@ -279,7 +340,9 @@ class HeadFn(torch.autograd.Function):
        token: logits = head(norm(x)[:, 0])   (+ head_dist(norm(x)[:, 1]) for the distilled model)"""
 
     @staticmethod
-    def forward(ctx, x, anchor, model, store: ParamStore, prev_rs, save: bool):
+    def forward(ctx, x, anchor, model, store: ParamStore, prev_rs, save: bool, head_drop: float = 0.0):
+        # head_drop > 0: nn.Dropout between fc_norm and the classifier (vision_transformer.py:987-990; the distilled
+        # model's forward_head, deit.py:108-119, has none)
         x = _require_f32_cuda(x, "head input")
         B, N, D = x.shape
         dev = x.device
@@ -290,7 +353,7 @@ class HeadFn(torch.autograd.Function):
         heads = [model.head] + ([model.head_dist] if getattr(model, "head_dist", None) is not None else [])
         C = heads[0].out_features
         sh = store.shadow_of
-        feats, stats, outs = [], [], []
+        feats, stats, outs, hmasks = [], [], [], []
         pooled = None
         if avg:
             pooled = _empty((B, D), torch.float32, dev)
@@ -303,16 +366,21 @@ class HeadFn(torch.autograd.Function):
                 L.layernorm_fwd(src, norm.weight.data, norm.bias.data, f, mean, rstd, B, D, norm.eps, ld_x=ld)
             else:
                 L.cast_bf16(src.view(B, -1)[:, :D].contiguous(), f)
+            hmask = dropout_keep_mask("head_drop", B, D, head_drop, dev) if (head_drop > 0.0 and len(heads) == 1) else None
+            if hmask is not None:
+                L.mask_mul_(f, hmask, 1.0 / (1.0 - head_drop), B, D)   # the classifier and its weight gradient see the dropped features
             logits = _empty((B, C), torch.float32, dev)
             L.gemm(f, sh(head.weight), logits, M=B, N=C, K=D, epilogue=L.EPI_F32,
                    bias=None if head.bias is None else head.bias.data)
             feats.append(f)
+            hmasks.append(hmask)
             stats.append((mean, rstd))
             outs.append(logits)
         if save:
             ctx.model, ctx.store = model, store
             ctx.dims = (B, N, D, C, prefix, avg, has_norm)
             ctx.saved = (x, pooled, feats, stats)
+            ctx.hdrop = (hmasks, head_drop)
             ctx.prev_rs = prev_rs
         return tuple(outs) if len(outs) > 1 else outs[0]
 
@@ -345,6 +413,8 @@ class HeadFn(torch.autograd.Function):
             # K = C with row pitch Cp: both tensor maps end at the true class count, so TMA zero-fills the k >= C part
             # of the last k-block on both operands and nothing past head.weight is ever read
             L.gemm(dlb, sh(head.weight), df, M=B, N=D, K=C, epilogue=L.EPI_BF16, b_mn=True, lda=Cp)
+            if ctx.hdrop[0][j] is not None:
+                L.mask_mul_(df, ctx.hdrop[0][j], 1.0 / (1.0 - ctx.hdrop[1]), B, D)
             mean, rstd = stats[j]
             if not has_norm:
                 raise NotImplementedError("final_norm=False head backward is not built")
@@ -360,7 +430,7 @@ class HeadFn(torch.autograd.Function):
         gb = _empty((B, N, D), torch.bfloat16, dev)
         L.rowscale_cast_bf16(g, ctx.prev_rs, N * D, gb)
         store.chain[g.data_ptr()] = gb
-        return g, None, None, None, None, None
+        return g, None, None, None, None, None, None
 
 
 # ================================================================================================
@@ -542,17 +612,21 @@ class AttentionFn(torch.autograd.Function):
 
 class MlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, mlp, store: ParamStore, save: bool):
+    def forward(ctx, x, anchor, mlp, store: ParamStore, save: bool, drop1: float = 0.0):
         x = _require_f32_cuda(x, "Mlp input")
         D, F, O = mlp.fc1.in_features, mlp.fc1.out_features, mlp.fc2.out_features
         M = x.numel() // D
         dev = x.device
         sh = store.shadow_of
         xb = _to_bf16(x).view(M, D)
-        h = _empty((M, F), _gelu_codes(F)[2], dev)
+        m1 = dropout_keep_mask("mlp.drop1", M, F, drop1, dev)
+        codes = _gelu_codes(F) if m1 is None else (L.EPI_GELU, L.EPI_DGELU, torch.bfloat16)
+        h = _empty((M, F), codes[2], dev)
         act = _empty((M, F), torch.bfloat16, dev)
-        L.gemm(xb, sh(mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=_gelu_codes(F)[0],
-               bias=None if mlp.fc1.bias is None else mlp.fc1.bias.data, aux=h)
+        L.gemm(xb, sh(mlp.fc1.weight), act, M=M, N=F, K=D, epilogue=codes[0],
+               bias=None if mlp.fc1.bias is None else mlp.fc1.bias.data, aux=h, mask=m1,
+               mask_scale=1.0 / (1.0 - drop1) if m1 is not None else 1.0)
+        ctx.dgelu = codes[1]
         out = _empty(x.shape[:-1] + (O,), torch.float32, dev)
         L.gemm(act, sh(mlp.fc2.weight), out, M=M, N=O, K=F, epilogue=L.EPI_F32,
                bias=None if mlp.fc2.bias is None else mlp.fc2.bias.data)
@@ -572,12 +646,12 @@ class MlpFn(torch.autograd.Function):
         L.gemm(dyb, act, gr(mlp.fc2.weight), M=O, N=F, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
                colsum=None if mlp.fc2.bias is None else gr(mlp.fc2.bias))
         dh = act
-        L.gemm(dyb, sh(mlp.fc2.weight), dh, M=M, N=F, K=O, epilogue=_gelu_codes(F)[1], b_mn=True, aux=h)
+        L.gemm(dyb, sh(mlp.fc2.weight), dh, M=M, N=F, K=O, epilogue=ctx.dgelu, b_mn=True, aux=h)
         L.gemm(dh, xb, gr(mlp.fc1.weight), M=F, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
                colsum=None if mlp.fc1.bias is None else gr(mlp.fc1.bias))
         dx = _empty(ctx.shape, torch.float32, dy.device)
         L.gemm(dh, sh(mlp.fc1.weight), dx, M=M, N=D, K=F, epilogue=L.EPI_F32, b_mn=True)
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class PatchEmbedFn(torch.autograd.Function):
