@@ -16,7 +16,9 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvitk.so")
+#: VITK_LIB: another build of the same sources (A/B experiments, e.g. tools/gpu_gelu_fast.sh); the ABI and build-id checks
+#: below still apply (VITK_ALLOW_STALE_LIB=1 for a build with different compile-time flags)
+LIB_PATH = os.environ.get("VITK_LIB") or os.path.join(_HERE, "libvitk.so")
 
 EPI_BF16, EPI_GELU, EPI_RESID, EPI_F32, EPI_DGELU, EPI_ATOMIC, EPI_PATCH, EPI_GELU_Q8, EPI_DGELU_Q8 = range(9)
 
