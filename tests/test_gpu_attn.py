@@ -113,14 +113,13 @@ def test_attn_unsupported_raises(cuda_device):
         L.attn_fwd(qkv, out, lse, 1, 300, 1, 72, 72 ** -0.5)   # wide heads: N <= 256
 
 
-@pytest.mark.parametrize("fwd,bwd,N,extra", [("1", "1", 197, {}), ("5", "0", 577, {}), ("5", "0", 197, {}), ("6", "0", 197, {}),
+@pytest.mark.parametrize("fwd,bwd,N,extra", [("1", "1", 197, {}), ("6", "0", 197, {}),
                                                ("6", "0", 577, {"VITK_ATTN_FWD6_LAZY": "8"}),
                                                ("6", "0", 385, {"VITK_ATTN_FWD6_STAGGER": "0"})])
 def test_attn_selectable_kernels_still_agree(cuda_device, fwd, bwd, N, extra):
     """The kernels that are not the default for a sequence length stay selectable (VITK_ATTN_FWD / VITK_ATTN_BWD, read once
     per process, so this runs them in a child process) and must give the same answers: the simple one-CTA-per-tile
-    kernels (1), the previous kv-loop forward (5), the current one (6) at N <= 256 and with its lazy-reference and
-    unstaggered modes."""
+    kernels (1), the kv-loop forward (6) at N <= 256 and with its lazy-reference and unstaggered modes."""
     import os
     import subprocess
     import sys

@@ -872,370 +872,17 @@ int launch_fwd4(const CUtensorMap& tm, const CUtensorMap& tm_out, float* lse, in
 }
 
 // ================================================================================================
-// Forward for 256 < N <= 640 (ViT-L/16 at 384 px: N = 577): the roles of attn_fwd4 with a flash-style kv loop.
-// Work item = (b, h, round): in round r warpgroup g owns q tile 2r + g (one thread per row); both groups walk the
-// same K_j / V_j tiles, which stream through a 4-stage TMA ring shared by the two groups.  Per kv tile the 128 score
-// columns of a row are read out of TMEM ONCE into registers (max and exp both work from there), P goes back over S
-// as packed bf16 and feeds O += P V_j as the TMEM A operand; O stays in TMEM across the kv loop and is rescaled in
-// place (tcgen05.ld / st, only when some row of the warp raised its maximum) before the next P V is issued.
-// TMEM per group: S / P [0,128) | O [128,192).   smem: Q_0 Q_1 (also the O staging tiles) | 4 x (K_j V_j) | barriers
-// ================================================================================================
-constexpr int FWD5_THREADS = 12 * 32;   // softmax g0 | softmax g1 | MMA g0, MMA g1, TMA, idle
-
-struct Fwd5Smem {
-  static constexpr uint32_t Q_OFF = 0;
-  static constexpr uint32_t KV_OFF = 2 * TILE_BYTES;
-  static constexpr int STAGES = 4;
-  static constexpr uint32_t BAR_OFF = KV_OFF + STAGES * 2 * TILE_BYTES;
-  static constexpr uint32_t BYTES = BAR_OFF + 256;
-};
-
-__global__ void __launch_bounds__(FWD5_THREADS, 1)
-attn_fwd5_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_out, float* __restrict__ lse,
-                 int B, int N, int H, float scale, long long* trace) {
-  using L = Fwd5Smem;
-  int tslot = 0;
-#define FWD5_STAMP(base) do { if (trace != nullptr && blockIdx.x == 0 && lane == 0 && tslot < 16 && it == (int)(blockIdx.x + gridDim.x)) trace[(base) + tslot++] = clock64(); } while (0)
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // [g] TMA -> MMA g: Q tile landed
-  uint64_t* q_empty = q_full + 2;                                      // [g] MMA g -> TMA: O staging tile stored, Q_g reusable
-  uint64_t* kv_full = q_empty + 2;                                     // [4] TMA -> MMA warps
-  uint64_t* kv_empty = kv_full + L::STAGES;                            // [4] both MMA warps -> TMA
-  uint64_t* s_full = kv_empty + L::STAGES;                             // [g] MMA -> group: S_j ready (and O stable)
-  uint64_t* p_full = s_full + 2;                                       // [g] group -> MMA: P_j written, O rescaled
-  uint64_t* o_full = p_full + 2;                                       // [g] MMA -> group: last P V of the q tile retired
-  uint64_t* o_free = o_full + 2;                                       // [g] group -> MMA: O read out
-  uint64_t* o_staged = o_free + 2;                                     // [g] group -> MMA: bf16 O tile in smem
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_staged + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int QT = (N + TILE - 1) / TILE;     // q tiles == kv tiles
-  const int R = (QT + 1) / 2;               // rounds per (b, h)
-  const int items = B * H * R;
-
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 4);
-      mbar_init(&o_staged[i], 4);
-    }
-    for (int i = 0; i < L::STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 2);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 10) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // Register re-allocation between whole warpgroups (the softmax threads hold a 128-column score row in registers).
-  // The setmaxnreg sits INSIDE each role's branch: ptxas budgets the code it dominates, and a diamond that merges
-  // before the roles split would leave every role with the smaller budget.
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  }
-  if (warp == 11) {
-    // idle: completes the control warpgroup (setmaxnreg is a warpgroup-wide instruction)
-  } else if (warp == 10) {
-    // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tm_qkv);
-      int qcnt[2] = {0, 0};
-      int kvc = 0;
-      for (int it = blockIdx.x; it < items; it += gridDim.x) {
-        const int r = it % R, bh = it / R, h = bh % H, b = bh / H;
-        for (int g = 0; g < 2; ++g) {
-          const int qt = 2 * r + g;
-          if (qt >= QT) continue;
-          mbar_wait(&q_empty[g], (qcnt[g] & 1) ^ 1);
-          ++qcnt[g];
-          mbar_arrive_expect_tx(&q_full[g], TILE_BYTES);
-          tma_load_head(smem + L::Q_OFF + g * TILE_BYTES, &tm_qkv, &q_full[g], h, qt * TILE, b);
-        }
-        for (int j = 0; j < QT; ++j, ++kvc) {
-          const int st = kvc % L::STAGES;
-          mbar_wait(&kv_empty[st], ((kvc / L::STAGES) & 1) ^ 1);
-          uint8_t* base = smem + L::KV_OFF + st * 2 * TILE_BYTES;
-          mbar_arrive_expect_tx(&kv_full[st], 2 * TILE_BYTES);
-          tma_load_head(base, &tm_qkv, &kv_full[st], H + h, j * TILE, b);
-          tma_load_head(base + TILE_BYTES, &tm_qkv, &kv_full[st], 2 * H + h, j * TILE, b);
-        }
-      }
-    }
-  } else if (warp >= 8) {
-    // ------------------------------ MMA issuer of group g (uniform control flow, one elected lane issues) ------------------------------
-    const int g = warp - 8;   // warps 8, 9
-    const uint32_t idesc_o = umma_idesc(TILE, HD, 1, false, true);  // A = P (TMEM, K-major), B = V MN-major
-    const uint32_t slot = tmem_base + g * 256;
-    const uint32_t sQ = smem_u32(smem + L::Q_OFF + g * TILE_BYTES);
-    int kvc = 0, rounds = 0, steps = 0;   // kv tiles seen by the ring / q tiles and kv steps done by THIS group
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int r = it % R, bh = it / R, h = bh % H, b = bh / H;
-      const int qt = 2 * r + g;
-      if (qt >= QT) {
-        // this group sits the round out but still hands every kv stage back (in step with the loads)
-        for (int j = 0; j < QT; ++j, ++kvc) {
-          const int st = kvc % L::STAGES;
-          mbar_wait(&kv_full[st], (kvc / L::STAGES) & 1);
-          if (lane == 0) mbar_arrive(&kv_empty[st]);
-          __syncwarp();
-        }
-        continue;
-      }
-      mbar_wait(&q_full[g], rounds & 1);
-      if (g == 1 && rounds == 0) mbar_wait(&p_full[0], 0);   // start half a step behind group 0: exps overlap the other group's MMA hop
-      // Everything the issue path needs is formed before the waits: the group idles from "P written" until the next
-      // S is ready, and this warp shares its scheduler with busy softmax warps (~10 cycles per dependent instruction).
-      const uint64_t qdesc = umma_desc_kmajor(sQ);
-      const uint64_t kdesc0 = umma_desc_kmajor(smem_u32(smem + L::KV_OFF));
-      const uint64_t vdesc0 = umma_desc_mnmajor(smem_u32(smem + L::KV_OFF + TILE_BYTES), TILE_BYTES);
-      constexpr uint64_t STAGE_STEP = (2 * TILE_BYTES) >> 4;
-      const uint32_t n_last = roundup16(N - (QT - 1) * TILE);
-      const uint32_t idesc_full = umma_idesc(TILE, TILE, 1, false, false), idesc_last = umma_idesc(TILE, n_last, 1, false, false);
-      {   // S_0
-        const int st = kvc % L::STAGES;
-        mbar_wait(&kv_full[st], (kvc / L::STAGES) & 1);
-        tc_fence_after();
-        const uint64_t kd = kdesc0 + (uint64_t)st * STAGE_STEP;
-        const uint32_t ids = (QT == 1) ? idesc_last : idesc_full;
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kd + (uint64_t)(k * 2), ids, k > 0);
-          umma_commit(&s_full[g]);
-        }
-        __syncwarp();
-      }
-      for (int j = 0; j < QT; ++j, ++kvc) {
-        const int st = kvc % L::STAGES, stn = (kvc + 1) % L::STAGES;
-        const bool last = j == QT - 1;
-        const int ksteps = (int)(last ? n_last : (uint32_t)TILE) / 16;
-        const uint64_t vd = vdesc0 + (uint64_t)st * STAGE_STEP, kdn = kdesc0 + (uint64_t)stn * STAGE_STEP;
-        const uint32_t idn = (j + 1 == QT - 1) ? idesc_last : idesc_full;
-        if (!last) mbar_wait(&kv_full[stn], ((kvc + 1) / L::STAGES) & 1);   // K_{j+1} is there before P_j arrives
-        mbar_wait(&p_full[g], steps & 1);
-        ++steps;
-        if (j == 0 && rounds > 0) mbar_wait(&o_free[g], (rounds - 1) & 1);   // the previous q tile's O has been read out
-        tc_fence_after();
-        if (elect_one()) {
-          for (int ks = 0; ks < ksteps; ++ks) umma_bf16_ts(slot + 128, slot + 8 * ks, vd + (uint64_t)(ks * 128), idesc_o, (j > 0 || ks > 0));
-          umma_commit(&kv_empty[st]);
-          if (last) {
-            umma_commit(&o_full[g]);
-          } else {   // S_{j+1} right behind (it overwrites P_j, which the P V just issued reads first: same issue order)
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k) umma_bf16_ss(slot, qdesc + (uint64_t)(k * 2), kdn + (uint64_t)(k * 2), idn, k > 0);
-            umma_commit(&s_full[g]);
-          }
-        }
-        __syncwarp();
-      }
-      // bf16 O tile (staged by the group in the Q_g tile) -> global; then the Q_g tile may be reloaded
-      mbar_wait(&o_staged[g], rounds & 1);
-      if (elect_one()) {
-        tma_store_head(&tm_out, smem + L::Q_OFF + g * TILE_BYTES, h, qt * TILE, b);  // rows >= N clipped
-        tma_store_commit_and_wait_read();
-        mbar_arrive(&q_empty[g]);
-      }
-      __syncwarp();
-      ++rounds;
-    }
-    if (elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // smem must outlive the store
-    __syncwarp();
-  } else {
-    // ------------------------------ softmax group g: 128 threads, thread = score row ------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int g = warp >> 2, quarter = warp & 3;
-    const int rr = quarter * 32 + lane;
-    const uint32_t slot = tmem_base + g * 256 + (static_cast<uint32_t>(quarter * 32) << 16);
-    const float c2 = scale * LOG2E;
-    uint8_t* stg = smem + L::Q_OFF + g * TILE_BYTES;
-    int steps = 0, rounds = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x) {
-      const int r = it % R, bh = it / R, h = bh % H, b = bh / H;
-      const int qt = 2 * r + g;
-      if (qt >= QT) continue;
-      const int qn = min(TILE, N - qt * TILE);
-      const bool active = quarter * 32 < qn;   // warp-uniform
-      float m = -INFINITY, l = 0.f;
-      for (int j = 0; j < QT; ++j, ++steps) {
-        const int kvn = min(TILE, N - j * TILE);
-        const uint32_t n_eff = roundup16(kvn);
-        const int nch = ((int)n_eff + 31) / 32;
-        mbar_wait(&s_full[g], steps & 1);
-        tc_fence_after();
-        if (quarter == 0) FWD5_STAMP(16 * g);
-        if (active) {
-          // the row's 128 scores of this kv tile: one TMEM round trip, then max and exp from registers
-          uint32_t sv[4][32];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            if (c < nch) tmem_ld_32x32(slot + c * 32, sv[c]);
-          tmem_ld_wait();
-          if (quarter == 0 && g == 0 && trace != nullptr && blockIdx.x == 0 && lane == 0 && it == (int)(blockIdx.x + gridDim.x) && j < 3) trace[64 + j * 4 + 0] = clock64();
-          float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nch) {
-              if (c * 32 + 32 <= kvn) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  m0 = fmaxf(m0, __uint_as_float(sv[c][i]));
-                  m1 = fmaxf(m1, __uint_as_float(sv[c][i + 1]));
-                  m2 = fmaxf(m2, __uint_as_float(sv[c][i + 2]));
-                  m3 = fmaxf(m3, __uint_as_float(sv[c][i + 3]));
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (c * 32 + i < kvn) m0 = fmaxf(m0, __uint_as_float(sv[c][i]));
-              }
-            }
-          }
-          const float m_new = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          const float alpha = ex2_approx((m - m_new) * c2);   // 0 on the first tile (m = -inf)
-          const float mc = m_new * c2;
-          if (quarter == 0 && g == 0 && trace != nullptr && blockIdx.x == 0 && lane == 0 && it == (int)(blockIdx.x + gridDim.x) && j < 3) trace[64 + j * 4 + 1] = clock64();
-          float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nch) {
-              uint32_t pk[16];
-              if (c * 32 + 32 <= kvn) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float e0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i]), c2, -mc));
-                  const float e1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i + 1]), c2, -mc));
-                  s0 += e0;
-                  s1 += e1;
-                  pk[i] = pack_bf16x2(e0, e1);
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  float e0 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i]), c2, -mc));
-                  float e1 = ex2_approx(fmaf(__uint_as_float(sv[c][2 * i + 1]), c2, -mc));
-                  e0 = (c * 32 + 2 * i < kvn) ? e0 : 0.f;
-                  e1 = (c * 32 + 2 * i + 1 < kvn) ? e1 : 0.f;
-                  s0 += e0;
-                  s1 += e1;
-                  pk[i] = pack_bf16x2(e0, e1);
-                }
-              }
-              tmem_st_32x16(slot + c * 16, pk);
-            }
-          }
-          l = fmaf(l, alpha, s0 + s1);
-          if (quarter == 0 && g == 0 && trace != nullptr && blockIdx.x == 0 && lane == 0 && it == (int)(blockIdx.x + gridDim.x) && j < 3) trace[64 + j * 4 + 2] = clock64();
-          // O <- alpha * O before the next P V accumulates into it (only if some row of the warp raised its maximum)
-          if (j > 0 && __any_sync(0xffffffffu, m_new > m)) {
-            uint32_t o0[32], o1[32];
-            tmem_ld_32x32(slot + 128, o0);
-            tmem_ld_32x32(slot + 160, o1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
-              o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              uint32_t t16[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) t16[i] = o0[u * 16 + i];
-              tmem_st_32x16(slot + 128 + u * 16, t16);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              uint32_t t16[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) t16[i] = o1[u * 16 + i];
-              tmem_st_32x16(slot + 160 + u * 16, t16);
-            }
-          }
-          m = m_new;
-          tmem_st_wait();
-          if (quarter == 0 && g == 0 && trace != nullptr && blockIdx.x == 0 && lane == 0 && it == (int)(blockIdx.x + gridDim.x) && j < 3) trace[64 + j * 4 + 3] = clock64();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[g]);
-        if (quarter == 0) FWD5_STAMP(16 * g);
-      }
-
-      // ---- O read-out, normalisation, staging ----
-      mbar_wait(&o_full[g], rounds & 1);
-      tc_fence_after();
-      uint32_t ra[32], rb[32];
-      if (active) {
-        tmem_ld_32x32(slot + 128, ra);
-        tmem_ld_32x32(slot + 160, rb);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[g]);
-      if (active) {
-        const float inv = 1.0f / l;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t(&o)[32] = u < 4 ? ra : rb;
-          const int e = (u & 3) * 8;
-          uint4 v4;
-          v4.x = pack_bf16x2(__uint_as_float(o[e + 0]) * inv, __uint_as_float(o[e + 1]) * inv);
-          v4.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
-          v4.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
-          v4.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
-          st_swz(stg, rr, u, v4);
-        }
-        const int q = qt * TILE + rr;
-        if (q < N && lse) lse[((long long)b * H + h) * N + q] = m * scale + __logf(l);
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_staged[g]);
-      ++rounds;
-    }
-  }
-#undef FWD5_STAMP
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 10) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-int launch_fwd5(const CUtensorMap& tm, const CUtensorMap& tm_out, float* lse, int B, int N, int H, float scale, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fwd5Smem::BYTES);
-    if (e != cudaSuccess) return vitk_set_error(VITK_ERR_CUDA, "attn_fwd5: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int QT = (N + TILE - 1) / TILE;
-  const int items = B * H * ((QT + 1) / 2);
-  const int grid = items < vitk_num_sms() ? items : vitk_num_sms();
-  attn_fwd5_kernel<<<grid, FWD5_THREADS, Fwd5Smem::BYTES, s>>>(tm, tm_out, lse, B, N, H, scale, g_trace_buf);
-  return vitk_check_launch("attn_fwd5");
-}
-
-// ================================================================================================
-// attn_fwd6: the kv-loop forward with the score MMA taken OFF the softmax's critical path (128 < N <= 640).
-// In attn_fwd5 S and P share TMEM columns, so S_{j+1} = Q K_{j+1}^T can only be issued after P_j has been written and both
-// groups end up in phase (timeline, tools/attn_trace5.py): ~2 700 cycles of two groups fighting for the MUFU pipe, then
-// ~1 350 cycles in which both wait for the P V / S hop and nobody issues an exp.  Here P has its own columns:
+// attn_fwd6: flash-style kv-loop forward for 256 < N <= 640 (ViT-L/16 at 384 px: N = 577), the roles of attn_fwd4 with the
+// score MMA taken OFF the softmax's critical path.
+// Work item = (b, h, round): in round r group g owns q tile 2r + g (one thread per score row); both groups walk the same
+// K_j / V_j tiles, which stream through a 4-stage TMA ring shared by the two groups.  Per kv tile the 128 score columns of a
+// row are read out of TMEM ONCE into registers (max and exp both work from there); P goes back to TMEM as packed bf16 and
+// feeds O += P V_j as the TMEM A operand; O stays in TMEM across the kv loop and is rescaled in place (tcgen05.ld / st,
+// only when some row of the warp raised its maximum).
+// Its predecessor (attn_fwd5, removed) kept S and P in the SAME TMEM columns, so S_{j+1} = Q K_{j+1}^T could only be issued
+// after P_j had been written, and both groups ended up in phase (timeline in profiles/r02_ncu_attn_fwd6.txt): ~2 700 cycles
+// of two groups fighting for the MUFU pipe, then ~1 350 cycles in which both wait for the P V / S hop and nobody issues an
+// exp.  Here P has its own columns:
 //   TMEM per group (256 columns): S [0,128) fp32 | P [128,192) packed bf16 | O [192,256) fp32
 // and the MMA warp issues S_{k+1} as soon as the softmax group has S_k in REGISTERS (s_read) — across kv tiles, q tiles
 // and work items (Q is double-buffered), so the next score tile is always waiting in TMEM when a group finishes a step
@@ -2522,16 +2169,15 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
     return T == 1 ? launch_fwd<1, true>(tm, out, lse, B, N, H, hd, scale, s) : launch_fwd<2, true>(tm, out, lse, B, N, H, hd, scale, s);
   // VITK_ATTN_FWD: unset = attn_fwd4 (whole score row in TMEM, one thread per row) for 128 < N <= 256, attn_fwd6 (kv loop,
   // score MMA off the softmax's critical path) above that, the tiled one-CTA-per-q-tile kernel for N <= 128;
-  // "1" = tiled kernel everywhere; "5" / "6" = attn_fwd5 (the previous kv-loop kernel) / attn_fwd6 for every N > 128
+  // "1" = tiled kernel everywhere; "6" = attn_fwd6 for every N > 128
   static const int variant = [] {
     const char* e = getenv("VITK_ATTN_FWD");
     return e ? atoi(e) : 0;
   }();
-  if ((variant == 0 || variant == 5 || variant == 6) && T >= 2) {
+  if ((variant == 0 || variant == 6) && T >= 2) {
     rc = make_head_tmap(&tm_out, out, H, hd, N, B, TILE);
     if (rc) return rc;
     if (variant == 0 && T == 2) return launch_fwd4(tm, tm_out, lse, B, N, H, scale, s);
-    if (variant == 5) return launch_fwd5(tm, tm_out, lse, B, N, H, scale, s);
     return launch_fwd6(tm, tm_out, lse, B, N, H, scale, s);
   }
   switch (T) {
