@@ -1,4 +1,5 @@
-"""Timeline (SM cycles) of items 2 and 3 of CTA 0 of the warp-specialised attention forward kernel (attn_fwd3).
+"""Timeline (SM cycles) of items 2 and 3 of CTA 0 of the warp-specialised attention kernels for 128 < N <= 256 (attn_fwd4 /
+attn_bwd4; written for their predecessors attn_fwd3 / attn_bwd3, whose exchange events stay empty).
 usage: attn_trace3.py [B] [N] [H]"""
 import os
 import sys

@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B on one box: GELU epilogue outputs through st.shared + TMA store (default) against direct 256-bit global stores
+# A/B on one box: GELU epilogue outputs through st.shared + TMA store (default) against direct 256-bit global stores.
+# Record of a REVERTED experiment (profiles/r02_ab_gelu_direct_stores.txt): VITK_GEMM_GELU_STG is no longer read by the library.
 set -u
 mkdir -p gpurun_out
 {
