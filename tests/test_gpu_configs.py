@@ -345,3 +345,59 @@ def test_optimizer_state_loads_before_first_forward_and_survives_a_plan_rebuild(
     assert float(m_before.abs().max()) > 0
     # m_after = 0.9 * m_before + 0.1 * g: had the moments been reset it would be 0.1 * g, uncorrelated with m_before
     assert cos_sim(m_after, m_before) > 0.5
+
+
+def test_grad_checkpointing_gives_the_same_step_with_less_memory(cuda_device):
+    """set_grad_checkpointing(True) (/root/reference/models/vision_transformer.py:686-694, 945-946): every block keeps only
+    its input and re-runs its forward kernels in the backward, with the DropPath / dropout masks of the forward pass.  Same
+    logits bit for bit, the same gradients up to the summation order of the split-K weight gradients, a smaller peak."""
+    from vision_transformers_torch_xla_b200 import ops
+    from vision_transformers_torch_xla_b200.losses import SoftTargetCrossEntropy
+    from vision_transformers_torch_xla_b200.models import create_model
+
+    dev, B = cuda_device, 16
+    torch.manual_seed(0)
+    model = create_model("vit_small_patch16_224", num_classes=1000, global_pool="avg", drop_path_rate=0.1, proj_drop_rate=0.1).to(dev)
+    model.train()
+    x = torch.randn(B, 3, 224, 224, device=dev)
+    tgt = torch.softmax(torch.randn(B, 1000, device=dev), -1)
+    crit = SoftTargetCrossEntropy()
+    masks, drops = {}, {}
+
+    def dp_source(drop_probs, nb, device):      # the same DropPath factors and dropout masks in both passes
+        key = tuple(drop_probs)
+        if key not in masks:
+            g = torch.Generator().manual_seed(5)
+            masks[key] = torch.stack([(torch.rand(nb, generator=g) >= p).float() / (1 - p) for p in drop_probs]).to(device)
+        return masks[key]
+
+    def do_source(site, rows, cols, p, device):
+        if site not in drops:
+            g = torch.Generator().manual_seed(hash(site) % 2 ** 31)
+            drops[site] = (torch.rand(rows, cols, generator=g) >= p).to(torch.uint8).to(device)
+        return drops[site]
+
+    def run(ckpt):
+        model.set_grad_checkpointing(ckpt)
+        model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        ops.mask_source, ops.dropout_source = dp_source, do_source
+        try:
+            out = model(x)
+            crit(out, tgt).backward()
+        finally:
+            ops.mask_source, ops.dropout_source = None, None
+        torch.cuda.synchronize()
+        peak = torch.cuda.max_memory_allocated() - base
+        return out.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters()}, peak
+
+    out_a, grads_a, peak_a = run(False)
+    out_b, grads_b, peak_b = run(True)
+    model.set_grad_checkpointing(False)
+    assert torch.equal(out_a, out_b)
+    for n in grads_a:
+        assert rms_err(grads_b[n], grads_a[n]) < 1e-5, (n, rms_err(grads_b[n], grads_a[n]))
+    print(f"[ckpt] peak activation memory {peak_a / 2 ** 20:.0f} MiB -> {peak_b / 2 ** 20:.0f} MiB")
+    assert peak_b < 0.5 * peak_a

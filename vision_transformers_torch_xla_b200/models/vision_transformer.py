@@ -253,7 +253,9 @@ class Block(nn.Module):
             drop = (ops.dropout_keep_mask(site + "attn.proj_drop", M, D, pd, x.device),
                     ops.dropout_keep_mask(site + "mlp.drop1", M, F, pd, x.device),
                     ops.dropout_keep_mask(site + "mlp.drop2", M, D, pd, x.device), 1.0 / (1.0 - pd))
-        out = ops.BlockFn.apply(x, st.anchor, self, st, rs1, rs2, prev_rs, torch.is_grad_enabled(), self._vitk_tag, drop)
+        root = st.__dict__.get("_in_root")
+        ckpt = bool(getattr(root, "grad_checkpointing", False)) and torch.is_grad_enabled()
+        out = ops.BlockFn.apply(x, st.anchor, self, st, rs1, rs2, prev_rs, torch.is_grad_enabled(), self._vitk_tag, drop, ckpt)
         st.__dict__["_last_rs"] = rs2
         return out
 
@@ -387,9 +389,9 @@ class VisionTransformer(nn.Module):
 
     @torch.jit.ignore
     def set_grad_checkpointing(self, enable: bool = True) -> None:
-        if enable:
-            raise NotImplementedError("gradient checkpointing is not built (activations fit in 180 GB HBM)")
-        self.grad_checkpointing = False
+        """/root/reference/models/vision_transformer.py:686-694, 945-946 (``checkpoint_seq`` over the blocks): every block keeps
+        only its fp32 input and runs its forward kernels again at the start of its backward."""
+        self.grad_checkpointing = bool(enable)
 
     @torch.jit.ignore
     def get_classifier(self) -> nn.Module:

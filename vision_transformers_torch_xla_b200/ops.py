@@ -210,9 +210,8 @@ class DropoutFn(torch.autograd.Function):
 
 class BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, blk, store: ParamStore, rs1, rs2, prev_rs, save: bool, tag: str, drop=None):
-        # drop = (keep masks of attn.proj_drop [M, D], mlp.drop1 [M, F], mlp.drop2 [M, D], 1 / (1 - p)) or None
-        x = _require_f32_cuda(x, "Block input")
+    def _run(x, blk, store: ParamStore, rs1, rs2, drop):
+        """The forward kernels of one block.  Returns (x_out, everything the backward reads)."""
         B, N, D = x.shape
         M = B * N
         H = blk.attn.num_heads
@@ -249,12 +248,25 @@ class BlockFn(torch.autograd.Function):
         x_out = _empty((B, N, D), torch.float32, dev)
         L.gemm(act, sh(blk.mlp.fc2.weight), x_out, M=M, N=D, K=F, epilogue=L.EPI_RESID, bias=bias(blk.mlp.fc2),
                resid=x_mid, rowscale=rs2, rows_per_group=N, colscale=g2, mask=md3, mask_scale=dscale)
+        return x_out, (x, ln1, mean1, rstd1, qkv, att, lse, x_mid, ln2, mean2, rstd2, h, act)
+
+    @staticmethod
+    def forward(ctx, x, anchor, blk, store: ParamStore, rs1, rs2, prev_rs, save: bool, tag: str, drop=None,
+                checkpoint: bool = False):
+        # drop = (keep masks of attn.proj_drop [M, D], mlp.drop1 [M, F], mlp.drop2 [M, D], 1 / (1 - p)) or None
+        # checkpoint (set_grad_checkpointing, vision_transformer.py:686-694, 945-946): keep only the block input and run the
+        # forward kernels again at the start of the backward (same DropPath / dropout masks: they are inputs, not redrawn)
+        x = _require_f32_cuda(x, "Block input")
+        B, N, D = x.shape
+        x_out, saved = BlockFn._run(x, blk, store, rs1, rs2, drop)
         if save:
             ctx.blk, ctx.store, ctx.tag = blk, store, tag
-            ctx.dims = (B, N, D, H, hd, F)
+            ctx.dims = (B, N, D, blk.attn.num_heads, blk.attn.head_dim, blk.mlp.fc1.out_features)
             ctx.rs = (rs1, rs2, prev_rs)
+            md1, md2, md3, dscale = drop if drop is not None else (None, None, None, 1.0)
             ctx.drop = (md1, md3, dscale, md2 is not None)
-            ctx.saved = (x, ln1, mean1, rstd1, qkv, att, lse, x_mid, ln2, mean2, rstd2, h, act)
+            ctx.recompute = (x, drop) if checkpoint else None
+            ctx.saved = None if checkpoint else saved
         return x_out
 
     @staticmethod
@@ -263,6 +275,10 @@ class BlockFn(torch.autograd.Function):
         B, N, D, H, hd, F = ctx.dims
         M = B * N
         rs1, rs2, prev_rs = ctx.rs
+        if ctx.recompute is not None:
+            x_in, drop_in = ctx.recompute
+            ctx.recompute = None
+            ctx.saved = BlockFn._run(x_in, blk, store, rs1, rs2, drop_in)[1]
         x, ln1, mean1, rstd1, qkv, att, lse, x_mid, ln2, mean2, rstd2, h, act = ctx.saved
         ctx.saved = None
         g = _require_f32_cuda(g, "Block.backward grad")
@@ -329,7 +345,7 @@ class BlockFn(torch.autograd.Function):
                         gr(blk.norm1.weight), gr(blk.norm1.bias), M, D)
         store.chain[g_in.data_ptr()] = gb_prev
         store.fire_grad_ready(ctx.tag)
-        return g_in, None, None, None, None, None, None, None, None, None
+        return g_in, None, None, None, None, None, None, None, None, None, None
 
 
 # ================================================================================================
