@@ -29,7 +29,7 @@ Each class/function cites the reference lines it follows.
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, Iterable, List, Optional, Sequence, Set, Tuple, Union
+from typing import Dict, Iterable, List, Set, Tuple
 
 import numpy as np
 import torch

@@ -34,7 +34,6 @@ from __future__ import annotations
 
 import ast
 import copy
-import io
 import math
 import os
 import sys

@@ -3,7 +3,6 @@ all-reduce fired by the backward hooks, pre-step wait, 1/world folded into the o
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

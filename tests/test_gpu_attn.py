@@ -1,5 +1,4 @@
 """tcgen05 attention fwd/bwd vs torch fp32 softmax attention on the same bf16-rounded qkv."""
-import math
 
 import pytest
 import torch

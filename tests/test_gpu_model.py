@@ -8,7 +8,6 @@ Metrics and stated tolerances for bf16 tensor-core compute against the fp32 orac
   * rms_err  = rms(a-b) / rms(b)          typical error: <= 1e-2, and cosine similarity >= 0.999 for gradients
   * loss trajectories over 200 AdamW steps: <= 5e-3 relative over the first 20 steps, <= 5e-2 throughout.
 """
-import copy
 import math
 
 import pytest

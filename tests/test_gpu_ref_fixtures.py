@@ -12,9 +12,8 @@ import sys
 
 import pytest
 import torch
-import torch.nn.functional as F
 
-from conftest import cos_sim, elem_err, rel_err, report, rms_err
+from conftest import cos_sim, rel_err, report, rms_err
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))

@@ -1,6 +1,5 @@
 """Host-side logic on CPU: registry / factory, module surface and state_dict layout against the oracle,
 parameter-group rule, schedules, meters — and that the product refuses to compute without its CUDA kernels."""
-import math
 
 import numpy as np
 import pytest

@@ -10,7 +10,7 @@ from __future__ import annotations
 import ctypes
 import hashlib
 import os
-from ctypes import c_double, POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint8, c_uint64, c_void_p
+from ctypes import c_double, POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_uint64, c_void_p
 from typing import Optional
 
 import torch

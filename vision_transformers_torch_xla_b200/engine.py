@@ -15,8 +15,7 @@ from __future__ import annotations
 
 import contextlib
 import os
-import time
-from typing import Iterable, Optional
+from typing import Iterable
 
 import torch
 

@@ -10,7 +10,6 @@ configs' feature set raise ``NotImplementedError`` — there is no eager fallbac
 """
 from __future__ import annotations
 
-import math
 from typing import Callable, Optional, Set, Tuple, Type, Union
 
 import torch

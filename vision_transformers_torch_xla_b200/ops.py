@@ -15,7 +15,7 @@ next stage's backward so that no separate cast pass is needed.
 from __future__ import annotations
 
 import os
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

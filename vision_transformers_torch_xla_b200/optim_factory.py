@@ -2,8 +2,7 @@
 ``--opt adamw`` with the decay / no_decay parameter-group rule) on the fused flat AdamW kernel."""
 from __future__ import annotations
 
-import math
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn
