@@ -154,3 +154,25 @@ def test_distillation_wrapper_contract_on_cpu_models():
     crit = losses.DistillationLoss(torch.nn.MSELoss(), 0.7, 4.0)
     with pytest.raises(NotImplementedError):
         crit((s, t), torch.zeros(2, 3))  # base criterion the fused kernel cannot absorb
+
+
+def test_dropout_and_checkpointing_options_are_accepted_on_the_host_side():
+    """The nn.Dropout sites of the reference (pos_drop, proj_drop, Mlp.drop1 / drop2, head_drop) and gradient checkpointing are
+    built (DESIGN.md sections 4.7 / 4.8); attention dropout is not."""
+    from vision_transformers_torch_xla_b200 import ops
+
+    m = VisionTransformer(embed_dim=64, depth=2, num_heads=1, drop_rate=0.1, pos_drop_rate=0.2, proj_drop_rate=0.3)
+    assert m.head_drop.p == 0.1 and m.pos_drop.p == 0.2
+    assert all(b.attn.proj_drop.p == 0.3 and b.mlp.drop1.p == 0.3 and b.mlp.drop2.p == 0.3 for b in m.blocks)
+    mlp = Mlp(64, 128, drop=(0.1, 0.2))
+    assert (mlp.drop1.p, mlp.drop2.p) == (0.1, 0.2)
+    with pytest.raises(NotImplementedError):
+        Attention(64, num_heads=1, attn_drop=0.1)
+    assert ops.dropout_keep_mask("site", 4, 8, 0.0, "cpu") is None          # p = 0: no mask, no kernel
+    with pytest.raises(ValueError):
+        ops.dropout_keep_mask("site", 4, 8, 1.0, "cpu")
+    assert m.grad_checkpointing is False
+    m.set_grad_checkpointing()
+    assert m.grad_checkpointing is True
+    m.set_grad_checkpointing(False)
+    assert m.grad_checkpointing is False
