@@ -259,12 +259,17 @@ def roofline(by_shape, family_tf, n_launches, gemm_ms_per_step, pk, build_id):
     launch was bracketed by CUDA events on the launching stream.  `family_*` is the same over all gemm_kernel launches."""
     if not by_shape:
         return None
+    from vision_transformers_torch_xla_b200 import _lib as L
+
     fam, (fl, ms, n) = max(by_shape.items(), key=lambda kv: kv[1][1])
     tf = fl / (ms * 1e-3) / 1e12
     t = ncu_traffic().get(fam, {})
     return {"bound": "tensor", "kernel": f"vitk gemm_kernel (tcgen05 cta_group::2) {fam}", "achieved": tf, "peak": pk["tf"],
             "unit": "TFLOP/s", "frac": tf / pk["tf"], "traffic": t.get("bytes"), "traffic_source": t.get("source"),
             "traffic_build": t.get("build_id"), "build": build_id,
+            # the capture is of THIS kernel as long as the GEMM sources are the ones it was taken from
+            "traffic_kernel_source_id": t.get("kernel_source_id"),
+            "kernel_source_id": L.source_id(("csrc/vitk_gemm.cu", "csrc/vitk_common.cuh")),
             "launches_timed": n, "us_per_launch": ms * 1e3 / n, "flop_per_launch": fl / n,
             "peak_source": f"bf16_tflops_sustained, {pk['src']}",
             "family_achieved": family_tf, "family_frac": (family_tf / pk["tf"]) if family_tf else None,

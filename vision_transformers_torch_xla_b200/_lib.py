@@ -39,6 +39,22 @@ _BUILD_SOURCES = ("csrc/vitk_host.cu", "csrc/vitk_gemm.cu", "csrc/vitk_attn.cu",
                   "csrc/vitk_elementwise.cu", "csrc/vitk_common.cuh", "csrc/vitk_internal.h", "../include/vitk.h")
 
 
+def source_id(files) -> Optional[str]:
+    """sha256 (first 16 hex digits) over the given source files (paths relative to this package), or None if one is missing.
+    ``source_id(("csrc/vitk_gemm.cu", "csrc/vitk_common.cuh"))`` identifies the GEMM kernel's sources: an ncu capture of that
+    kernel stays valid across builds that only touch other files (profiles/ncu_traffic.json: ``kernel_source_id``)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    try:
+        for rel in files:
+            with open(os.path.join(_HERE, rel), "rb") as f:
+                h.update(f.read())
+    except OSError:
+        return None
+    return h.hexdigest()[:16]
+
+
 def source_build_id() -> Optional[str]:
     """sha256 (first 16 hex digits) over the kernel sources next to this package, or None if they are not there."""
     h = hashlib.sha256()
