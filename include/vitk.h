@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define VITK_ABI_VERSION 3
+#define VITK_ABI_VERSION 4
 
 enum vitk_status {
   VITK_STATUS_OK = 0,
@@ -142,6 +142,16 @@ int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t h
 int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim,
                   float scale, void* stream);
+/* Attention dropout (timm Attention.attn_drop: softmax -> Dropout -> @ v; dropout_p of the fused SDPA call): keep_mask holds
+ * keep bytes [B, H, N, N] (1 = keep; vitk_dropout_mask), keep_scale = 1 / (1 - p).  out = (softmax(S) * m * keep_scale) V, lse is
+ * the log-sum-exp of the undropped scores; the backward sees the same mask.  Runs on the one-CTA-per-tile forward and the
+ * streaming backward for every N (the mask is read per element); the backward workspace always holds the fp32 dQ accumulator. */
+int vitk_attn_fwd_dropout(const void* qkv, void* out, float* lse, const uint8_t* keep_mask, float keep_scale, int32_t B,
+                          int32_t N, int32_t H, int32_t head_dim, float scale, void* stream);
+int64_t vitk_attn_bwd_dropout_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim);
+int vitk_attn_bwd_dropout(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace,
+                          const uint8_t* keep_mask, float keep_scale, int32_t B, int32_t N, int32_t H, int32_t head_dim,
+                          float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Patch embedding helpers (PatchEmbed + _pos_embed: vision_transformer.py:552-560, 743-780)

@@ -107,6 +107,36 @@ def test_gemm_mask_is_rejected_where_it_has_no_epilogue(cuda_device):
         L.gemm(x, w, out, M=128, N=64, K=64, epilogue=L.EPI_BF16, mask=m, mask_scale=2.0)
 
 
+@pytest.mark.parametrize("B,N,H,hd", [(2, 197, 3, 64), (1, 100, 2, 64), (1, 300, 2, 64), (2, 197, 2, 72), (2, 198, 2, 48)])
+def test_attention_dropout_kernels(cuda_device, B, N, H, hd):
+    """attn_drop: out = (softmax(S) * m / keep) V with lse of the undropped scores; backward through the same mask.
+    Against torch on the same bf16-rounded qkv and the same mask (N <= 128, 128 < N <= 256, N > 256, wide and narrow heads)."""
+    from vision_transformers_torch_xla_b200 import _lib as L
+    torch.manual_seed(0)
+    p_drop = 0.2
+    s = 1.0 / (1.0 - p_drop)
+    qkv = torch.randn(B, N, 3 * H * hd, device=cuda_device).bfloat16()
+    dout = torch.randn(B, N, H * hd, device=cuda_device).bfloat16()
+    mask = (torch.rand(B, H, N, N, device=cuda_device) >= p_drop).to(torch.uint8)
+    out = torch.full((B, N, H * hd), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    lse = torch.full((B, H, N), float("nan"), device=cuda_device)
+    dqkv = torch.full((B, N, 3 * H * hd), float("nan"), device=cuda_device, dtype=torch.bfloat16)
+    L.attn_fwd(qkv, out, lse, B, N, H, hd, hd ** -0.5, keep_mask=mask, keep_scale=s)
+    L.attn_bwd(qkv, out, dout, lse, dqkv, B, N, H, hd, hd ** -0.5, keep_mask=mask, keep_scale=s)
+    q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().view(B, N, 3, H, hd).permute(2, 0, 3, 1, 4).unbind(0))
+    sc = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    ref = ((torch.softmax(sc, -1) * mask.float() * s) @ v).transpose(1, 2).reshape(B, N, H * hd)
+    ref.backward(dout.float())
+    g = torch.stack([q.grad, k.grad, v.grad], 0).permute(1, 3, 0, 2, 4).reshape(B, N, 3 * H * hd)
+    report("attn_drop out", out.float(), ref.detach())
+    assert elem_err(out.float(), ref.detach()) < 1.5e-2 and rms_err(out.float(), ref.detach()) < 5e-3
+    assert rel_err(lse, torch.logsumexp(sc.detach(), -1)) < 5e-3
+    d, r = dqkv.float().view(B, N, 3, H * hd), g.view(B, N, 3, H * hd)
+    for i, name in enumerate("qkv"):
+        report(f"attn_drop d{name}", d[:, :, i], r[:, :, i])
+        assert rms_err(d[:, :, i], r[:, :, i]) < 8e-3 and elem_err(d[:, :, i], r[:, :, i]) < 3e-2, name
+
+
 class fixed_dropout:
     """Fixes the keep mask of every nn.Dropout site: forward hooks on the oracle's modules, ops.dropout_source for the CUDA
     path.  Masks are drawn once per site name from a seeded CPU generator."""
@@ -143,8 +173,9 @@ class fixed_dropout:
 
 @pytest.mark.parametrize("kw", [dict(proj_drop_rate=0.1), dict(pos_drop_rate=0.1, drop_rate=0.2),
                                 dict(proj_drop_rate=0.2, pos_drop_rate=0.1, drop_rate=0.1, drop_path_rate=0.1, init_values=0.1),
-                                dict(proj_drop_rate=0.1, global_pool="token")],
-                         ids=["proj", "pos+head", "all+droppath+layerscale", "proj-token"])
+                                dict(proj_drop_rate=0.1, global_pool="token"), dict(attn_drop_rate=0.1),
+                                dict(attn_drop_rate=0.2, proj_drop_rate=0.1, drop_path_rate=0.1)],
+                         ids=["proj", "pos+head", "all+droppath+layerscale", "proj-token", "attn", "attn+proj+droppath"])
 def test_model_with_dropout_matches_oracle(cuda_device, kw):
     """ViT-Ti/16 with dropout at every built site against the fp32 oracle with the SAME masks: logits, loss, every block's
     output, every parameter gradient.  Tolerances are those of tests/test_gpu_configs.py."""
@@ -157,7 +188,9 @@ def test_model_with_dropout_matches_oracle(cuda_device, kw):
     dev, B = cuda_device, 6
     kw = dict(dict(num_classes=1000, global_pool="avg"), **kw)
     torch.manual_seed(0)
-    ref = O.create_model("vit_tiny_patch16_224", **kw).to(dev)
+    # attn_drop: the oracle's unfused attention path applies it as an nn.Dropout module on the softmax (hookable); the fused
+    # SDPA call would draw its own mask inside the kernel
+    ref = O.create_model("vit_tiny_patch16_224", fused_attn=not kw.get("attn_drop_rate"), **kw).to(dev)
     mine = create_model("vit_tiny_patch16_224", **kw).to(dev)
     mine.load_state_dict(ref.state_dict())
     ref.train()

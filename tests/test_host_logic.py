@@ -61,7 +61,7 @@ def test_create_model_kwargs_contract():
 
 def test_options_outside_the_fast_path_raise_instead_of_falling_back():
     for kw in (dict(qk_norm=True), dict(reg_tokens=4), dict(pre_norm=True), dict(global_pool="map"),
-               dict(dynamic_img_size=True), dict(attn_drop_rate=0.1), dict(no_embed_class=True)):
+               dict(dynamic_img_size=True), dict(patch_drop_rate=0.1), dict(no_embed_class=True)):
         with pytest.raises(NotImplementedError):
             VisionTransformer(embed_dim=64, depth=1, num_heads=1, **kw)
     with pytest.raises(NotImplementedError):
@@ -157,17 +157,17 @@ def test_distillation_wrapper_contract_on_cpu_models():
 
 
 def test_dropout_and_checkpointing_options_are_accepted_on_the_host_side():
-    """The nn.Dropout sites of the reference (pos_drop, proj_drop, Mlp.drop1 / drop2, head_drop) and gradient checkpointing are
-    built (DESIGN.md sections 4.7 / 4.8); attention dropout is not."""
+    """The nn.Dropout sites of the reference (pos_drop, attn_drop, proj_drop, Mlp.drop1 / drop2, head_drop) and gradient
+    checkpointing are built (DESIGN.md sections 4.7 / 4.8)."""
     from vision_transformers_torch_xla_b200 import ops
 
-    m = VisionTransformer(embed_dim=64, depth=2, num_heads=1, drop_rate=0.1, pos_drop_rate=0.2, proj_drop_rate=0.3)
-    assert m.head_drop.p == 0.1 and m.pos_drop.p == 0.2
+    m = VisionTransformer(embed_dim=64, depth=2, num_heads=1, drop_rate=0.1, pos_drop_rate=0.2, proj_drop_rate=0.3,
+                          attn_drop_rate=0.4)
+    assert m.head_drop.p == 0.1 and m.pos_drop.p == 0.2 and all(b.attn.attn_drop.p == 0.4 for b in m.blocks)
     assert all(b.attn.proj_drop.p == 0.3 and b.mlp.drop1.p == 0.3 and b.mlp.drop2.p == 0.3 for b in m.blocks)
     mlp = Mlp(64, 128, drop=(0.1, 0.2))
     assert (mlp.drop1.p, mlp.drop2.p) == (0.1, 0.2)
-    with pytest.raises(NotImplementedError):
-        Attention(64, num_heads=1, attn_drop=0.1)
+    assert Attention(64, num_heads=1, attn_drop=0.1).attn_drop.p == 0.1
     assert ops.dropout_keep_mask("site", 4, 8, 0.0, "cpu") is None          # p = 0: no mask, no kernel
     with pytest.raises(ValueError):
         ops.dropout_keep_mask("site", 4, 8, 1.0, "cpu")

@@ -31,9 +31,10 @@ EXPORTED_SYMBOLS = (
     "vitk_debug_set_trace", "vitk_mixup_batch", "vitk_mixup_target", "vitk_colscale_bf16", "vitk_layerscale_grad",
     "vitk_build_id", "vitk_droppath_masks", "vitk_scale_f32", "vitk_clip_coef", "vitk_sumsq_bf16", "vitk_sumsq_scratch_floats",
     "vitk_dropout_mask", "vitk_mask_mul_bf16", "vitk_mask_mul_f32",
+    "vitk_attn_fwd_dropout", "vitk_attn_bwd_dropout", "vitk_attn_bwd_dropout_workspace_bytes",
 )
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 #: the files whose sha256 csrc/Makefile bakes into the library (same list, same order)
 _BUILD_SOURCES = ("csrc/vitk_host.cu", "csrc/vitk_gemm.cu", "csrc/vitk_attn.cu", "csrc/vitk_norm.cu",
                   "csrc/vitk_elementwise.cu", "csrc/vitk_common.cuh", "csrc/vitk_internal.h", "../include/vitk.h")
@@ -153,6 +154,12 @@ def load() -> ctypes.CDLL:
     lib.vitk_sumsq_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.vitk_sumsq_scratch_floats.restype = c_int32
     lib.vitk_dropout_mask.argtypes = [c_void_p, c_int64, c_float, c_uint64, c_uint64, c_void_p]
+    lib.vitk_attn_fwd_dropout.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32, c_int32, c_int32,
+                                          c_float, c_void_p]
+    lib.vitk_attn_bwd_dropout_workspace_bytes.argtypes = [c_int32, c_int32, c_int32, c_int32]
+    lib.vitk_attn_bwd_dropout_workspace_bytes.restype = c_int64
+    lib.vitk_attn_bwd_dropout.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32,
+                                          c_int32, c_int32, c_int32, c_float, c_void_p]
     lib.vitk_mask_mul_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_float, c_void_p]
     lib.vitk_mask_mul_f32.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_float, c_void_p]
     lib.vitk_mixup_batch.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_double, c_int32, c_int32, c_int32, c_int32,
@@ -165,6 +172,7 @@ def load() -> ctypes.CDLL:
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("vitk_last_error", "vitk_arch", "vitk_abi_version", "vitk_attn_bwd_workspace_bytes",
+                        "vitk_attn_bwd_dropout_workspace_bytes",
                         "vitk_debug_set_trace", "vitk_build_id", "vitk_sumsq_scratch_floats"):
             fn.restype = c_int32
     _lib = lib
@@ -365,26 +373,46 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
 # ------------------------------------------------------------------------------------------------
 # Attention
 # ------------------------------------------------------------------------------------------------
+def _req_attn_mask(mask: torch.Tensor, B: int, N: int, H: int) -> None:
+    _req(mask, torch.uint8, "attn keep mask")
+    if mask.numel() != B * H * N * N:
+        raise VitkError(f"attn keep mask: expected {B} x {H} x {N} x {N} keep bytes, got {tuple(mask.shape)}")
+
+
 def attn_fwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, B: int, N: int, H: int, hd: int,
-             scale: float) -> None:
+             scale: float, keep_mask: Optional[torch.Tensor] = None, keep_scale: float = 1.0) -> None:
+    """``keep_mask`` (uint8 [B, H, N, N], 1 = keep) with ``keep_scale = 1 / (1 - p)``: attention dropout on the softmax."""
     _req(qkv, torch.bfloat16, "attn qkv")
     _req(out, torch.bfloat16, "attn out")
     _req(lse, torch.float32, "attn lse")
     with _Timed("attn_fwd"):
-        _check(load().vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd, scale, _stream()),
-               "vitk_attn_fwd")
+        if keep_mask is None:
+            _check(load().vitk_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, hd, scale, _stream()),
+                   "vitk_attn_fwd")
+        else:
+            _req_attn_mask(keep_mask, B, N, H)
+            _check(load().vitk_attn_fwd_dropout(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), keep_mask.data_ptr(),
+                                                float(keep_scale), B, N, H, hd, scale, _stream()), "vitk_attn_fwd_dropout")
     _count()
 
 
 def attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, dqkv: torch.Tensor,
-             B: int, N: int, H: int, hd: int, scale: float) -> None:
+             B: int, N: int, H: int, hd: int, scale: float, keep_mask: Optional[torch.Tensor] = None,
+             keep_scale: float = 1.0) -> None:
     for t, nm in ((qkv, "qkv"), (out, "out"), (dout, "dout"), (dqkv, "dqkv")):
         _req(t, torch.bfloat16, f"attn_bwd {nm}")
-    ws_bytes = load().vitk_attn_bwd_workspace_bytes(B, N, H, hd)
+    lib = load()
+    ws_bytes = (lib.vitk_attn_bwd_workspace_bytes if keep_mask is None else lib.vitk_attn_bwd_dropout_workspace_bytes)(B, N, H, hd)
     ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=qkv.device) if ws_bytes > 0 else None
     with _Timed("attn_bwd"):
-        _check(load().vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                    _ptr(ws), B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
+        if keep_mask is None:
+            _check(lib.vitk_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                     _ptr(ws), B, N, H, hd, scale, _stream()), "vitk_attn_bwd")
+        else:
+            _req_attn_mask(keep_mask, B, N, H)
+            _check(lib.vitk_attn_bwd_dropout(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                             _ptr(ws), keep_mask.data_ptr(), float(keep_scale), B, N, H, hd, scale, _stream()),
+                   "vitk_attn_bwd_dropout")
     _count()
 
 

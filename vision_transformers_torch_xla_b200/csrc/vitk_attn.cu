@@ -85,7 +85,10 @@ __device__ __forceinline__ void load_head_tiles(uint8_t* dst, const CUtensorMap*
 template <int T, bool WIDE>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
-                float* __restrict__ lse, int N, int H, int hd, float scale, long long* trace) {
+                float* __restrict__ lse, int N, int H, int hd, float scale, const uint8_t* __restrict__ drop_mask,
+                float drop_scale, long long* trace) {
+  // drop_mask (attn_drop, timm Attention: softmax -> Dropout -> @ v): keep bytes [B, H, N, N] or null.  The row sum (the
+  // softmax normaliser) is taken BEFORE the mask, the mask / keep_prob goes onto the P tile that feeds P V.
   VITK_STAMP(0);
   using L = FwdSmem<T, WIDE>;
   constexpr int HDW = WIDE ? HDW_MAX : HD;   // accumulator columns of O
@@ -208,10 +211,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __res
             u.y = pack_bf16x2(p[2], p[3]);
             u.z = pack_bf16x2(p[4], p[5]);
             u.w = pack_bf16x2(p[6], p[7]);
-            st_swz(sP, r, c * 4 + g, u);
             // the row sum uses the bf16-rounded probabilities so that P*V and l stay consistent
             const float2 a0 = unpack_bf16x2(u.x), a1 = unpack_bf16x2(u.y), a2 = unpack_bf16x2(u.z), a3 = unpack_bf16x2(u.w);
             rowsum += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+            if (drop_mask != nullptr) {   // the dropped, rescaled probabilities are what multiplies V
+              const int qrow = q0 + r, col = j * TILE + c * 32 + g * 8;
+              const uint8_t* mrow = drop_mask + (((long long)b * H + h) * N + qrow) * N + col;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) p[i] = (qrow < N && col + i < N && mrow[i]) ? p[i] * drop_scale : 0.f;
+              u.x = pack_bf16x2(p[0], p[1]);
+              u.y = pack_bf16x2(p[2], p[3]);
+              u.z = pack_bf16x2(p[4], p[5]);
+              u.w = pack_bf16x2(p[6], p[7]);
+            }
+            st_swz(sP, r, c * 4 + g, u);
           }
         }
       }
@@ -1859,7 +1872,9 @@ template <bool WIDE>
 __global__ void __launch_bounds__(128)
 attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                        const float* __restrict__ dsum, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                       float* __restrict__ dq32, int N, int H, int hd, float scale) {
+                       float* __restrict__ dq32, int N, int H, int hd, float scale, const uint8_t* __restrict__ drop_mask,
+                       float drop_scale) {
+  // drop_mask (attn_drop): keep bytes [B, H, N, N] or null: dV sees P m / keep, dS = P (dP m / keep - D)
   using L = BwdStreamSmem<WIDE>;
   constexpr int HDW = WIDE ? HDW_MAX : HD;   // accumulator columns of dV / dK / dQ, head pitch of the dQ workspace
   constexpr int NBUF = L::NBUF;
@@ -1971,9 +1986,16 @@ attn_bwd_stream_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           for (int k = 0; k < 4; ++k) {
             const float e0 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + 2 * k]), c2, -my_lse2));
             const float e1 = ex2_approx(fmaf(__uint_as_float(sv[g * 8 + 2 * k + 1]), c2, -my_lse2));
-            pk[k] = pack_bf16x2(e0, e1);
-            dk[k] = pack_bf16x2(e0 * fmaf(__uint_as_float(dv[g * 8 + 2 * k]), scale, -my_ds),
-                                e1 * fmaf(__uint_as_float(dv[g * 8 + 2 * k + 1]), scale, -my_ds));
+            float m0 = 1.f, m1 = 1.f;   // dropout factor of the two elements (mask / keep_prob)
+            if (drop_mask != nullptr) {
+              const int col = j * TILE + c * 32 + g * 8 + 2 * k;
+              const uint8_t* mrow = drop_mask + (((long long)b * H + h) * N + q) * N + col;
+              m0 = (row_ok && col < N && mrow[0]) ? drop_scale : 0.f;
+              m1 = (row_ok && col + 1 < N && mrow[1]) ? drop_scale : 0.f;
+            }
+            pk[k] = pack_bf16x2(e0 * m0, e1 * m1);
+            dk[k] = pack_bf16x2(e0 * fmaf(__uint_as_float(dv[g * 8 + 2 * k]), scale * m0, -my_ds),
+                                e1 * fmaf(__uint_as_float(dv[g * 8 + 2 * k + 1]), scale * m1, -my_ds));
           }
           st_swz(sP, r, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
           st_swz(sDS, r, c * 4 + g, make_uint4(dk[0], dk[1], dk[2], dk[3]));
@@ -2122,7 +2144,8 @@ __global__ void dq_cast_kernel(const float* __restrict__ dq32, __nv_bfloat16* __
 }
 
 template <int T, bool WIDE = false>
-int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s) {
+int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H, int hd, float scale, cudaStream_t s,
+               const uint8_t* drop_mask = nullptr, float drop_scale = 1.f) {
   auto kern = attn_fwd_kernel<T, WIDE>;
   using L = FwdSmem<T, WIDE>;
   static bool attr_set = false;
@@ -2132,7 +2155,7 @@ int launch_fwd(const CUtensorMap& tm, void* out, float* lse, int B, int N, int H
     attr_set = true;
   }
   dim3 grid((N + TILE - 1) / TILE, H, B);
-  kern<<<grid, 128, L::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, hd, scale, g_trace_buf);
+  kern<<<grid, 128, L::BYTES, s>>>(tm, (__nv_bfloat16*)out, lse, N, H, hd, scale, drop_mask, drop_scale, g_trace_buf);
   return vitk_check_launch("attn_fwd");
 }
 
@@ -2151,8 +2174,8 @@ constexpr int WIDE_MAX_N = 2 * TILE;   // heads wider than 64: the forward keeps
 
 }  // namespace
 
-extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t head_dim,
-                             float scale, void* stream) {
+static int attn_fwd_impl(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
+                         const uint8_t* drop_mask, float drop_scale, void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_fwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_fwd: head_dim=%d (built for multiples of 8 in [16, 80])", head_dim);
   VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_fwd: N=%d > %d", N, FWD_MAX_T * TILE);
@@ -2166,7 +2189,17 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   const int T = (N + TILE - 1) / TILE;
   cudaStream_t s = (cudaStream_t)stream;
   if (hd > HD)   // my_vit_xs (head_dim 72): the tiled kernel with [tile][tail] operands
-    return T == 1 ? launch_fwd<1, true>(tm, out, lse, B, N, H, hd, scale, s) : launch_fwd<2, true>(tm, out, lse, B, N, H, hd, scale, s);
+    return T == 1 ? launch_fwd<1, true>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale)
+                  : launch_fwd<2, true>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale);
+  if (drop_mask != nullptr) {   // attention dropout: the tiled kernel for every N (the mask is read per element)
+    switch (T) {
+      case 1: return launch_fwd<1>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale);
+      case 2: return launch_fwd<2>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale);
+      case 3: return launch_fwd<3>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale);
+      case 4: return launch_fwd<4>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale);
+      default: return launch_fwd<5>(tm, out, lse, B, N, H, hd, scale, s, drop_mask, drop_scale);
+    }
+  }
   // VITK_ATTN_FWD: unset = attn_fwd4 (whole score row in TMEM, one thread per row) for 128 < N <= 256, attn_fwd6 (kv loop,
   // score MMA off the softmax's critical path) above that, the tiled one-CTA-per-q-tile kernel for N <= 128;
   // "1" = tiled kernel everywhere; "6" = attn_fwd6 for every N > 128
@@ -2189,6 +2222,17 @@ extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, 
   }
 }
 
+extern "C" int vitk_attn_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t head_dim,
+                             float scale, void* stream) {
+  return attn_fwd_impl(qkv, out, lse, B, N, H, head_dim, scale, nullptr, 1.f, stream);
+}
+
+extern "C" int vitk_attn_fwd_dropout(const void* qkv, void* out, float* lse, const uint8_t* keep_mask, float keep_scale, int32_t B,
+                                     int32_t N, int32_t H, int32_t head_dim, float scale, void* stream) {
+  VITK_REQUIRE(keep_mask != nullptr && keep_scale > 0.f, VITK_ERR_SHAPE, "attn_fwd_dropout: keep mask [B, H, N, N] and 1 / (1 - p) required");
+  return attn_fwd_impl(qkv, out, lse, B, N, H, head_dim, scale, keep_mask, keep_scale, stream);
+}
+
 extern "C" void vitk_debug_set_trace(long long* device_buf) { g_trace_buf = device_buf; }
 
 static int64_t dsum_bytes(int32_t B, int32_t N, int32_t H) {
@@ -2204,9 +2248,14 @@ extern "C" int64_t vitk_attn_bwd_workspace_bytes(int32_t B, int32_t N, int32_t H
   return bytes;
 }
 
-extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                             void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
-                             void* stream) {
+extern "C" int64_t vitk_attn_bwd_dropout_workspace_bytes(int32_t B, int32_t N, int32_t H, int32_t head_dim) {
+  // attention dropout runs the streaming backward for every N: D plus the fp32 dQ accumulator
+  return dsum_bytes(B, N, H) + (int64_t)B * N * H * (head_dim > HD ? HDW_MAX : HD) * (int64_t)sizeof(float);
+}
+
+static int attn_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* workspace, int32_t B,
+                         int32_t N, int32_t H, int32_t head_dim, float scale, const uint8_t* drop_mask, float drop_scale,
+                         void* stream) {
   VITK_REQUIRE(B > 0 && N > 0 && H > 0, VITK_ERR_SHAPE, "attn_bwd: bad shape B=%d N=%d H=%d", B, N, H);
   VITK_REQUIRE(head_dim_ok(head_dim), VITK_ERR_UNSUPPORTED, "attn_bwd: head_dim=%d (built for multiples of 8 in [16, 80])", head_dim);
   VITK_REQUIRE(N <= FWD_MAX_T * TILE, VITK_ERR_UNSUPPORTED, "attn_bwd: N=%d > %d", N, FWD_MAX_T * TILE);
@@ -2244,7 +2293,7 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     rc = vitk_check_launch("attn_dsum");
     if (rc) return rc;
   }
-  if (N > BWD_MAX_T * TILE || hd > HD) {
+  if (N > BWD_MAX_T * TILE || hd > HD || drop_mask != nullptr) {
     // one CTA per (b, h, kv tile): dQ partials are red.add'ed into the fp32 workspace (156 of the ~820 us per layer at
     // ViT-L/384, B = 64, H = 16, N = 577; ~90 us are the memset / cast / D kernels around it)
     const long long rows = (long long)B * N;
@@ -2254,10 +2303,10 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
     dim3 grid((N + TILE - 1) / TILE, H, B);
     if (hd > HD)
       attn_bwd_stream_kernel<true><<<grid, 128, BwdStreamSmem<true>::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, dq32,
-                                                                                  N, H, hd, scale);
+                                                                                  N, H, hd, scale, drop_mask, drop_scale);
     else
       attn_bwd_stream_kernel<false><<<grid, 128, BwdStreamSmem<false>::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv,
-                                                                                    dq32, N, H, hd, scale);
+                                                                                    dq32, N, H, hd, scale, drop_mask, drop_scale);
     rc = vitk_check_launch("attn_bwd_stream");
     if (rc) return rc;
     const long long n8 = rows * H * (hd / 8);
@@ -2282,4 +2331,17 @@ extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout,
   dim3 grid(H, B);
   attn_bwd_kernel<<<grid, 128, BwdSmem::BYTES, st>>>(tm_qkv, tm_do, dsum, lse, (__nv_bfloat16*)dqkv, N, H, hd, scale, g_trace_buf);
   return vitk_check_launch("attn_bwd");
+}
+
+extern "C" int vitk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                             void* workspace, int32_t B, int32_t N, int32_t H, int32_t head_dim, float scale,
+                             void* stream) {
+  return attn_bwd_impl(qkv, out, dout, lse, dqkv, workspace, B, N, H, head_dim, scale, nullptr, 1.f, stream);
+}
+
+extern "C" int vitk_attn_bwd_dropout(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                     void* workspace, const uint8_t* keep_mask, float keep_scale, int32_t B, int32_t N, int32_t H,
+                                     int32_t head_dim, float scale, void* stream) {
+  VITK_REQUIRE(keep_mask != nullptr && keep_scale > 0.f, VITK_ERR_SHAPE, "attn_bwd_dropout: keep mask [B, H, N, N] and 1 / (1 - p) required");
+  return attn_bwd_impl(qkv, out, dout, lse, dqkv, workspace, B, N, H, head_dim, scale, keep_mask, keep_scale, stream);
 }

@@ -117,7 +117,7 @@ class PatchEmbed(nn.Module):
 
 
 class Attention(nn.Module):
-    """timm Attention: qkv Linear -> SDPA -> proj Linear -> proj_drop (qk_norm / attn_drop / masks not built)."""
+    """timm Attention: qkv Linear -> SDPA (softmax dropout = attn_drop) -> proj Linear -> proj_drop (qk_norm / masks not built)."""
 
     fused_attn = True
 
@@ -128,9 +128,6 @@ class Attention(nn.Module):
         assert dim % num_heads == 0, "dim should be divisible by num_heads"
         if qk_norm or scale_norm:
             raise NotImplementedError("Attention: qk_norm / scale_norm are not built")
-        if attn_drop != 0.0:
-            raise NotImplementedError("Attention: attn_drop > 0 (dropout on the softmax inside the fused attention kernel) is not "
-                                      "built; every reference config uses 0")
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
         if self.head_dim % 8 != 0 or not 16 <= self.head_dim <= 80:
@@ -152,7 +149,7 @@ class Attention(nn.Module):
         st = store_for(self)
         st.sync_shadow()
         st.attach_grads()
-        x = ops.AttentionFn.apply(x, st.anchor, self, st, torch.is_grad_enabled())
+        x = ops.AttentionFn.apply(x, st.anchor, self, st, torch.is_grad_enabled(), self.attn_drop.p if self.training else 0.0)
         if self.training and self.proj_drop.p > 0.0:   # stand-alone use; inside a Block the mask rides in the proj epilogue
             x = ops.DropoutFn.apply(x, st, "attn.proj_drop", self.proj_drop.p)
         return x
@@ -243,15 +240,18 @@ class Block(nn.Module):
         # nn.Dropout sites of the block (timm Attention.proj_drop, Mlp.drop1 / drop2; one rate: Block(proj_drop=...)): three keep
         # masks per pass, applied inside the proj / fc1 / fc2 GEMM epilogues
         drop = None
-        pd = self.attn.proj_drop.p
-        if self.training and pd > 0.0:
+        pd, pa = self.attn.proj_drop.p, self.attn.attn_drop.p
+        if self.training and (pd > 0.0 or pa > 0.0):
             if self.mlp.drop1.p != pd or self.mlp.drop2.p != pd:
                 raise NotImplementedError("Block: Attention.proj_drop and Mlp.drop must share one rate (Block(proj_drop=...))")
-            M, D, F = x.shape[0] * x.shape[1], x.shape[2], self.mlp.fc1.out_features
+            B, N, D = x.shape
+            M, F, H = B * N, self.mlp.fc1.out_features, self.attn.num_heads
             site = f"blocks.{self._vitk_index}."
+            # (a site with p = 0 gets no mask; attn_drop: keep bytes [B, H, N, N] read by the attention kernels)
             drop = (ops.dropout_keep_mask(site + "attn.proj_drop", M, D, pd, x.device),
                     ops.dropout_keep_mask(site + "mlp.drop1", M, F, pd, x.device),
-                    ops.dropout_keep_mask(site + "mlp.drop2", M, D, pd, x.device), 1.0 / (1.0 - pd))
+                    ops.dropout_keep_mask(site + "mlp.drop2", M, D, pd, x.device), 1.0 / (1.0 - pd),
+                    ops.dropout_keep_mask(site + "attn.attn_drop", B * H * N, N, pa, x.device), 1.0 / (1.0 - pa))
         root = st.__dict__.get("_in_root")
         ckpt = bool(getattr(root, "grad_checkpointing", False)) and torch.is_grad_enabled()
         out = ops.BlockFn.apply(x, st.anchor, self, st, rs1, rs2, prev_rs, torch.is_grad_enabled(), self._vitk_tag, drop, ckpt)
@@ -308,7 +308,7 @@ class VisionTransformer(nn.Module):
                            no_embed_class=no_embed_class, reg_tokens=reg_tokens, pre_norm=pre_norm,
                            pool_include_prefix=pool_include_prefix, dynamic_img_size=dynamic_img_size,
                            dynamic_img_pad=dynamic_img_pad, patch_drop_rate=patch_drop_rate,
-                           attn_drop_rate=attn_drop_rate, fix_init=fix_init, embed_norm_layer=embed_norm_layer)
+                           fix_init=fix_init, embed_norm_layer=embed_norm_layer)
         bad = {k: v for k, v in unsupported.items() if v}
         if bad:
             raise NotImplementedError(f"VisionTransformer: options outside the built fast path: {bad}")
@@ -351,7 +351,8 @@ class VisionTransformer(nn.Module):
         dpr = [x.item() for x in torch.linspace(0, drop_path_rate, depth, device="cpu")]  # stochastic depth decay rule
         self.blocks = nn.Sequential(*[
             block_fn(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, proj_bias=proj_bias,
-                     init_values=init_values, proj_drop=proj_drop_rate, drop_path=dpr[i], norm_layer=norm_layer,
+                     init_values=init_values, proj_drop=proj_drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i],
+                     norm_layer=norm_layer,
                      act_layer=act_layer, mlp_layer=mlp_layer)
             for i in range(depth)])
         for i, blk in enumerate(self.blocks):

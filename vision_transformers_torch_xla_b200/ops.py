@@ -229,11 +229,11 @@ class BlockFn(torch.autograd.Function):
         L.gemm(ln1, sh(blk.attn.qkv.weight), qkv, M=M, N=3 * D, K=D, epilogue=L.EPI_BF16, bias=bias(blk.attn.qkv))
         att = _empty((M, D), torch.bfloat16, dev)
         lse = _empty((B, H, N), torch.float32, dev)
-        L.attn_fwd(qkv, att, lse, B, N, H, hd, blk.attn.scale)
+        md1, md2, md3, dscale, ma, ascale = drop if drop is not None else (None, None, None, 1.0, None, 1.0)
+        L.attn_fwd(qkv, att, lse, B, N, H, hd, blk.attn.scale, keep_mask=ma, keep_scale=ascale)
         # LayerScale (vision_transformer.py:80-106): gamma rides in the residual epilogue as a per-column scale
         g1 = blk.ls1.gamma.data if hasattr(blk.ls1, "gamma") else None
         g2 = blk.ls2.gamma.data if hasattr(blk.ls2, "gamma") else None
-        md1, md2, md3, dscale = drop if drop is not None else (None, None, None, 1.0)
         x_mid = _empty((B, N, D), torch.float32, dev)
         L.gemm(att, sh(blk.attn.proj.weight), x_mid, M=M, N=D, K=D, epilogue=L.EPI_RESID, bias=bias(blk.attn.proj),
                resid=x, rowscale=rs1, rows_per_group=N, colscale=g1, mask=md1, mask_scale=dscale)
@@ -253,7 +253,8 @@ class BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, blk, store: ParamStore, rs1, rs2, prev_rs, save: bool, tag: str, drop=None,
                 checkpoint: bool = False):
-        # drop = (keep masks of attn.proj_drop [M, D], mlp.drop1 [M, F], mlp.drop2 [M, D], 1 / (1 - p)) or None
+        # drop = (keep masks of attn.proj_drop [M, D], mlp.drop1 [M, F], mlp.drop2 [M, D], 1 / (1 - p_proj),
+        #         keep mask of attn.attn_drop [B * H * N, N], 1 / (1 - p_attn)) or None; a mask that is None is a site with p = 0
         # checkpoint (set_grad_checkpointing, vision_transformer.py:686-694, 945-946): keep only the block input and run the
         # forward kernels again at the start of the backward (same DropPath / dropout masks: they are inputs, not redrawn)
         x = _require_f32_cuda(x, "Block input")
@@ -263,8 +264,8 @@ class BlockFn(torch.autograd.Function):
             ctx.blk, ctx.store, ctx.tag = blk, store, tag
             ctx.dims = (B, N, D, blk.attn.num_heads, blk.attn.head_dim, blk.mlp.fc1.out_features)
             ctx.rs = (rs1, rs2, prev_rs)
-            md1, md2, md3, dscale = drop if drop is not None else (None, None, None, 1.0)
-            ctx.drop = (md1, md3, dscale, md2 is not None)
+            md1, md2, md3, dscale, ma, ascale = drop if drop is not None else (None, None, None, 1.0, None, 1.0)
+            ctx.drop = (md1, md3, dscale, md2 is not None, ma, ascale)
             ctx.recompute = (x, drop) if checkpoint else None
             ctx.saved = None if checkpoint else saved
         return x_out
@@ -302,7 +303,7 @@ class BlockFn(torch.autograd.Function):
                 L.layerscale_grad(lin.weight.data, gr(lin.weight), None if lin.bias is None else lin.bias.data,
                                   None if lin.bias is None else gr(lin.bias), ls.gamma.data, gr(ls.gamma))
 
-        md1, md3, dscale, gelu_masked = ctx.drop
+        md1, md3, dscale, gelu_masked, ma, ascale = ctx.drop
         gb2 = _bf16_grad(store, g, rs2, N * D).view(M, D)
         ls_bwd_scale(gb2, blk.ls2)   # gb2 is exclusively ours (popped from the side channel or freshly made)
         if md3 is not None:          # Mlp.drop2 sits between fc2 and LayerScale / DropPath: its mask goes on the branch gradient
@@ -333,7 +334,7 @@ class BlockFn(torch.autograd.Function):
         datt = _empty((M, D), torch.bfloat16, dev)
         L.gemm(gb1, sh(blk.attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
         dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
-        L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, blk.attn.scale)
+        L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, blk.attn.scale, keep_mask=ma, keep_scale=ascale)
         del gb1, datt, att, qkv, lse
         wgrad(dqkv, ln1, blk.attn.qkv, 3 * D, D)
         dln1 = ln1
@@ -583,7 +584,7 @@ class LinearFn(torch.autograd.Function):
 
 class AttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, anchor, attn, store: ParamStore, save: bool):
+    def forward(ctx, x, anchor, attn, store: ParamStore, save: bool, attn_drop: float = 0.0):
         x = _require_f32_cuda(x, "Attention input")
         B, N, D = x.shape
         M, H, hd = B * N, attn.num_heads, attn.head_dim
@@ -595,12 +596,15 @@ class AttentionFn(torch.autograd.Function):
                bias=None if attn.qkv.bias is None else attn.qkv.bias.data)
         att = _empty((M, D), torch.bfloat16, dev)
         lse = _empty((B, H, N), torch.float32, dev)
-        L.attn_fwd(qkv, att, lse, B, N, H, hd, attn.scale)
+        ma = dropout_keep_mask("attn.attn_drop", B * H * N, N, attn_drop, dev)
+        ascale = 1.0 / (1.0 - attn_drop) if ma is not None else 1.0
+        L.attn_fwd(qkv, att, lse, B, N, H, hd, attn.scale, keep_mask=ma, keep_scale=ascale)
         out = _empty((B, N, D), torch.float32, dev)
         L.gemm(att, sh(attn.proj.weight), out, M=M, N=D, K=D, epilogue=L.EPI_F32,
                bias=None if attn.proj.bias is None else attn.proj.bias.data)
         if save:
             ctx.attn, ctx.store, ctx.saved, ctx.dims = attn, store, (xb, qkv, att, lse), (B, N, D, H, hd)
+            ctx.adrop = (ma, ascale)
         return out
 
     @staticmethod
@@ -618,12 +622,12 @@ class AttentionFn(torch.autograd.Function):
         datt = _empty((M, D), torch.bfloat16, dev)
         L.gemm(dyb, sh(attn.proj.weight), datt, M=M, N=D, K=D, epilogue=L.EPI_BF16, b_mn=True)
         dqkv = _empty((M, 3 * D), torch.bfloat16, dev)
-        L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, attn.scale)
+        L.attn_bwd(qkv, att, datt, lse, dqkv, B, N, H, hd, attn.scale, keep_mask=ctx.adrop[0], keep_scale=ctx.adrop[1])
         L.gemm(dqkv, xb, gr(attn.qkv.weight), M=3 * D, N=D, K=M, epilogue=L.EPI_ATOMIC, a_mn=True, b_mn=True,
                colsum=None if attn.qkv.bias is None else gr(attn.qkv.bias))
         dx = _empty((B, N, D), torch.float32, dev)
         L.gemm(dqkv, sh(attn.qkv.weight), dx, M=M, N=D, K=3 * D, epilogue=L.EPI_F32, b_mn=True)
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 class MlpFn(torch.autograd.Function):
